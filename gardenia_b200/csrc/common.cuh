@@ -1,0 +1,149 @@
+// common.cuh -- shared device helpers and the library's internal state.
+// sm_100a only (B200); no CUB/Thrust, no multi-arch dispatch.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include "../../include/gdn_b200.h"
+
+namespace gdn {
+
+// ---------------------------------------------------------------- error plumbing
+void set_error(const char *fmt, ...);
+struct Lib {
+  bool inited = false;
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  void *pinned = nullptr;          // small pinned mailbox for per-step counters
+  size_t pinned_bytes = 0;
+};
+Lib &lib();
+int ensure_init();
+
+#define GDN_CUDA(call)                                                                  \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess) {                                                            \
+      gdn::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      return (e_ == cudaErrorMemoryAllocation) ? GDN_ERR_NOMEM : GDN_ERR_CUDA;          \
+    }                                                                                   \
+  } while (0)
+
+#define GDN_CHECK(call)            \
+  do {                             \
+    int rc_ = (call);              \
+    if (rc_ != GDN_OK) return rc_; \
+  } while (0)
+
+// ---------------------------------------------------------------- device-side CSR
+// One direction of the graph as the kernels see it.  Offsets are LOCAL to this
+// GPU's row partition (32-bit whenever the local nnz fits), column indices are
+// GLOBAL vertex ids.  `col` is 256-B aligned and padded by >= 16 B so that
+// 128-bit loads may over-read the tail.
+struct DevCsr {
+  int64_t rows = 0;        // local rows
+  uint64_t nnz = 0;        // local non-zeros
+  bool off64 = false;
+  void *rowptr = nullptr;  // uint32_t[rows+1] or uint64_t[rows+1]
+  int32_t *col = nullptr;
+  // row-block schedule for the pull gather (gather.cu)
+  int32_t n_chunks = 0;        // light blocks: rows [chunk_row[k], chunk_row[k+1]) minus a heavy last row
+  int32_t *chunk_row = nullptr;    // int32[n_chunks+1]
+  int32_t n_heavy_rows = 0;
+  int32_t n_heavy_segs = 0;
+  int32_t *heavy_row = nullptr;    // int32[n_heavy_rows]      local row id
+  int32_t *heavy_first = nullptr;  // int32[n_heavy_rows+1]    first segment index of that row
+  int2 *heavy_seg = nullptr;       // int2[n_heavy_segs]       {local row, segment number within the row}
+  float *heavy_partial = nullptr;  // float[n_heavy_segs]
+};
+
+}  // namespace gdn
+
+struct gdn_graph {
+  int64_t m = 0;                 // global vertex count
+  int64_t row_lo = 0, row_hi = 0;
+  bool symmetric = false;        // in-CSR aliases out-CSR
+  bool has_out = false, has_in = false;
+  gdn::DevCsr out, in;
+  size_t device_bytes = 0;
+  // PageRank scratch
+  float *contrib[2] = {nullptr, nullptr};
+  int32_t *out_degree = nullptr;     // int32[rows]; for PR on directed graphs
+  double *err_partial = nullptr;     // per-warp partial L1 deltas
+  double *err_trace = nullptr;       // double[GDN_MAX_PR_ITER] on device
+  int32_t *pr_done = nullptr;        // device flag: converged
+  int n_err_partial = 0;
+  // BFS scratch
+  uint32_t *visited = nullptr, *front = nullptr, *next = nullptr;
+  int32_t *queue[2] = {nullptr, nullptr};
+  int32_t *heavy_queue = nullptr;
+  void *counters = nullptr;          // BfsCounters on device
+  int64_t n_words = 0;               // bitmap words (32-bit), padded to a multiple of 32
+};
+
+namespace gdn {
+
+// ---------------------------------------------------------------- device helpers
+#ifdef __CUDACC__
+constexpr unsigned kFull = 0xffffffffu;
+
+// Streaming 256-bit load (Blackwell LDG.E.256) of column indices / matrix
+// values: read-only path, no L1 allocation (L1 is kept for the gathered
+// vector), L2 evict-first so the one-pass stream does not displace the
+// gathered vector from the 126 MB L2.  p must be 32-byte aligned.
+__device__ __forceinline__ void ld_stream_v8(const void *p, int (&q)[8]) {
+  asm volatile(
+      "ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7])
+      : "l"(p));
+}
+__device__ __forceinline__ void ld_stream_v8(const void *p, float (&q)[8]) {
+  asm volatile(
+      "ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(q[0]), "=f"(q[1]), "=f"(q[2]), "=f"(q[3]), "=f"(q[4]), "=f"(q[5]), "=f"(q[6]), "=f"(q[7])
+      : "l"(p));
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+// Gathered vector element: read-only path, L1 allocate, L2 evict-last.
+__device__ __forceinline__ float ld_gather_f32(const float *p, uint64_t pol) {
+  float r;
+  asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(pol));
+  return r;
+}
+// Scalar streaming load (row tails / unaligned heads).
+__device__ __forceinline__ int ld_stream_s32(const int *p, uint64_t pol) {
+  int r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ long long warp_sum(long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+#endif
+
+}  // namespace gdn

@@ -1,0 +1,438 @@
+// gather.cu -- the pull-direction CSR gather shared by PageRank and SpMV.
+//
+// Replaces (not ports) the reference's src/pr/{base,warp,vector,lb}.cu and
+// src/spmv/{base,warp,vector}.cu.  Semantics follow the OpenMP variants the
+// results are checked against: src/pr/omp_base.cc:21-37, src/spmv/omp_base.cc:22-33.
+//
+// Load balancing is chosen from the degree distribution once, at upload
+// (build_schedule): the row space is cut at every kChunk-th non-zero into
+// "light blocks" of whole rows (< 2*kChunk non-zeros each); rows longer than
+// kChunk are "heavy" and are cut into kSeg-non-zero segments.  Every work item
+// (light block or heavy segment) is about the same size and is processed by
+// one warp:
+//   phase 1  stream column indices (and SpMV values) with 256-bit coalesced
+//            L1-bypassing loads, gather the vector element for each, and
+//            stage the products in shared memory -- 8 independent gathers in
+//            flight per lane;
+//   phase 2  (light blocks) one lane per row sums its staged products in row
+//            order, i.e. in exactly the sequential fp32 order of the reference,
+//            so light rows are bit-identical to the OpenMP result;
+//            (heavy segments) warp-shuffle reduction into a partial, summed
+//            per row by finalize_heavy in a fixed order.
+// No atomics, deterministic run to run.
+#include "common.cuh"
+
+namespace gdn {
+
+constexpr int kChunk = 512;            // non-zeros per light block (target)
+constexpr int kCap = 2 * kChunk + 8;   // staged products per warp
+constexpr int kSeg = 1024;             // non-zeros per heavy-row segment
+constexpr int kWarps = 8;              // warps per CTA
+constexpr int kThreads = kWarps * 32;
+
+enum { kModeSpmv = 0, kModePr = 1 };
+
+struct GatherArgs {
+  // schedule
+  const int32_t *chunk_row;
+  int32_t n_chunks;
+  const int2 *heavy_seg;
+  int32_t n_heavy_segs;
+  float *heavy_partial;
+  const int32_t *heavy_row;
+  const int32_t *heavy_first;
+  int32_t n_heavy_rows;
+  int64_t rows;
+  // SpMV:  y[r] += sum Ax[j] * x[col[j]]
+  const float *Ax;
+  uint64_t nnz;           // bound for guarded Ax tail loads
+  const float *vec;       // x (SpMV) or contrib_in (PR), GLOBAL length m
+  float *y;               // SpMV y (local rows)
+  // PR
+  float *scores;          // local rows
+  float *contrib_out;     // GLOBAL length m; this GPU writes [row_lo, row_lo+rows)
+  const int32_t *out_degree;  // local rows; nullptr -> degree = row length (symmetric graph)
+  int64_t row_lo;
+  float base, damp;
+  double *err_partial;
+  const int32_t *done;    // device flag set once converged: later launches are no-ops
+  int err_slot0;          // first err_partial slot of this kernel
+};
+
+template <int MODE>
+__device__ __forceinline__ void row_epilogue(const GatherArgs &a, int64_t r, float acc, int32_t row_len,
+                                             double &err) {
+  if (MODE == kModeSpmv) {
+    a.y[r] = acc;                                      // acc started from y[r], omp_base.cc:25,32
+  } else {
+    const float old_score = a.scores[r];
+    const float nw = __fadd_rn(a.base, __fmul_rn(a.damp, acc));   // pr/omp_base.cc:32, no FMA contraction
+    a.scores[r] = nw;
+    err += (double)fabsf(__fsub_rn(nw, old_score));                // :33, double accumulator :22
+    const int32_t deg = a.out_degree ? a.out_degree[r] : row_len;
+    a.contrib_out[a.row_lo + r] = __fdiv_rn(nw, (float)deg);       // next iteration's :24-25
+  }
+}
+
+// Stream [b,e) of this CSR, gather, and either stage the products (STAGE) or
+// accumulate them per lane.  a0 = b rounded down to a 32-byte boundary.
+template <typename OffT, int MODE, bool STAGE>
+__device__ __forceinline__ float stream_gather(const GatherArgs &a, const int32_t *__restrict__ col, OffT b,
+                                               OffT e, OffT a0, float *sv, uint64_t pol, int lane) {
+  float acc0 = 0.f, acc1 = 0.f;
+  for (OffT i = a0 + (OffT)lane * 8; i < e; i += 256) {
+    int q[8];
+    float ax[8];
+    float v[8];
+    ld_stream_v8(col + i, q);
+    if (MODE == kModeSpmv) {
+      if ((uint64_t)i + 8 <= a.nnz) {
+        ld_stream_v8(a.Ax + i, ax);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) ax[j] = ((uint64_t)i + j < a.nnz) ? a.Ax[i + j] : 0.f;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const bool ok = (i + j >= b) && (i + j < e);
+      float g = 0.f;
+      if (ok) g = ld_gather_f32(a.vec + q[j], pol);
+      v[j] = (MODE == kModeSpmv) ? __fmul_rn(g, ax[j]) : g;
+    }
+    if (STAGE) {
+      float4 *dst = reinterpret_cast<float4 *>(sv + (i - a0));
+      dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+      dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+      acc0 += (v[0] + v[1]) + (v[2] + v[3]);
+      acc1 += (v[4] + v[5]) + (v[6] + v[7]);
+    }
+  }
+  return acc0 + acc1;
+}
+
+template <typename OffT, int MODE>
+__global__ void __launch_bounds__(kThreads, 4)
+gather_kernel(const OffT *__restrict__ rowptr, const int32_t *__restrict__ col, GatherArgs a) {
+  __shared__ __align__(32) float s_vals[kWarps][kCap];
+  if (MODE == kModePr && *a.done) return;
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int64_t warp = (int64_t)blockIdx.x * kWarps + wib;
+  const int64_t nwarps = (int64_t)gridDim.x * kWarps;
+  const int64_t n_items = (int64_t)a.n_chunks + a.n_heavy_segs;
+  float *sv = s_vals[wib];
+  const uint64_t pol = l2_policy_evict_last();
+  double err = 0.0;
+
+  for (int64_t item = warp; item < n_items; item += nwarps) {
+    if (item < a.n_chunks) {
+      // ---- light block: whole rows [r0, r1)
+      const int32_t r0 = a.chunk_row[item];
+      int32_t r1 = a.chunk_row[item + 1];
+      if (r1 > r0) {
+        const OffT lb = rowptr[r1 - 1], le = rowptr[r1];
+        if (le - lb > (OffT)kChunk) r1--;               // heavy last row: handled as segments
+      }
+      if (r1 <= r0) continue;                           // warp-uniform
+      const OffT b = rowptr[r0], e = rowptr[r1];
+      const OffT a0 = b & ~(OffT)7;
+      stream_gather<OffT, MODE, true>(a, col, b, e, a0, sv, pol, lane);
+      __syncwarp();
+      for (int32_t r = r0 + lane; r < r1; r += 32) {
+        const int32_t s = (int32_t)(rowptr[r] - a0), t = (int32_t)(rowptr[r + 1] - a0);
+        float acc = (MODE == kModeSpmv) ? a.y[r] : 0.f;
+        for (int32_t j = s; j < t; j++) acc = __fadd_rn(acc, sv[j]);
+        row_epilogue<MODE>(a, r, acc, t - s, err);
+      }
+      __syncwarp();
+    } else {
+      // ---- heavy segment: kSeg non-zeros of one long row -> one partial
+      const int32_t h = (int32_t)(item - a.n_chunks);
+      const int2 hs = a.heavy_seg[h];
+      const OffT rb = rowptr[hs.x], re = rowptr[hs.x + 1];
+      const OffT b = rb + (OffT)hs.y * kSeg;
+      const OffT e = (re - b > (OffT)kSeg) ? b + kSeg : re;
+      const OffT a0 = b & ~(OffT)7;
+      float acc = stream_gather<OffT, MODE, false>(a, col, b, e, a0, nullptr, pol, lane);
+      acc = warp_sum(acc);
+      if (lane == 0) a.heavy_partial[h] = acc;
+    }
+  }
+  if (MODE == kModePr) {
+    err = warp_sum(err);
+    if (lane == 0) a.err_partial[a.err_slot0 + warp] = err;
+  }
+}
+
+// One warp per heavy row: sum its segment partials in a fixed order, epilogue.
+template <typename OffT, int MODE>
+__global__ void __launch_bounds__(kThreads, 4)
+finalize_heavy(const OffT *__restrict__ rowptr, GatherArgs a) {
+  if (MODE == kModePr && *a.done) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarps;
+  double err = 0.0;
+  for (int64_t hr = warp; hr < a.n_heavy_rows; hr += nwarps) {
+    const int32_t row = a.heavy_row[hr];
+    const int32_t first = a.heavy_first[hr];
+    const OffT len = rowptr[row + 1] - rowptr[row];
+    const int32_t nseg = (int32_t)((len + kSeg - 1) / kSeg);
+    float acc = 0.f;
+    for (int32_t s = lane; s < nseg; s += 32) acc += a.heavy_partial[first + s];
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      if (MODE == kModeSpmv) acc = __fadd_rn(a.y[row], acc);
+      row_epilogue<MODE>(a, row, acc, (int32_t)len, err);
+    }
+  }
+  if (MODE == kModePr) {
+    err = warp_sum(err);
+    if (lane == 0) a.err_partial[a.err_slot0 + warp] = err;
+  }
+}
+
+// contrib[v] = scores[v] / out_degree(v)  (src/pr/omp_base.cc:24-25) for the local rows.
+template <typename OffT>
+__global__ void pr_init_contrib(const OffT *__restrict__ rowptr, const int32_t *__restrict__ out_degree,
+                                const float *__restrict__ scores, float *__restrict__ contrib, int64_t rows,
+                                int64_t row_lo) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t deg = out_degree ? out_degree[r] : (int32_t)(rowptr[r + 1] - rowptr[r]);
+    contrib[row_lo + r] = __fdiv_rn(scores[r], (float)deg);
+  }
+}
+
+// Fixed-order reduction of the per-warp partial L1 deltas -> err_trace[iter];
+// raises the done flag when the total drops below eps (src/pr/omp_base.cc:36).
+__global__ void __launch_bounds__(256)
+pr_reduce_err(const double *__restrict__ partial, int n, double *err_trace, int iter, double eps, int32_t *done) {
+  __shared__ double s[256];
+  if (*done) return;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) acc += partial[i];
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    err_trace[iter] = s[0];
+    if (s[0] < eps) *done = iter + 1;
+  }
+}
+
+// ---------------------------------------------------------------- schedule build
+// chunk_row[k] = first row whose first non-zero is at or after k*kChunk.
+template <typename OffT>
+__global__ void build_chunk_rows(const OffT *__restrict__ rowptr, int64_t rows, int32_t n_chunks,
+                                 int32_t *__restrict__ chunk_row) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > n_chunks) return;
+  if (k == n_chunks) { chunk_row[k] = (int32_t)rows; return; }
+  const OffT target = (OffT)k * kChunk;
+  int64_t lo = 0, hi = rows;            // lower_bound over rowptr[0..rows]
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (rowptr[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  chunk_row[k] = (int32_t)lo;
+}
+
+// counters: one 64-bit word, high 32 = heavy rows, low 32 = heavy segments, so
+// that a row's slot and its first segment are allocated by ONE atomic.
+template <typename OffT, bool FILL>
+__global__ void scan_heavy(const OffT *__restrict__ rowptr, int64_t rows, unsigned long long *counter,
+                           int32_t *heavy_row, int32_t *heavy_first, int2 *heavy_seg) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+    const OffT len = rowptr[r + 1] - rowptr[r];
+    if (len > (OffT)kChunk) {
+      const unsigned nseg = (unsigned)((len + kSeg - 1) / kSeg);
+      const unsigned long long old = atomicAdd(counter, (1ull << 32) | nseg);
+      if (FILL) {
+        const int32_t slot = (int32_t)(old >> 32), first = (int32_t)(old & 0xffffffffu);
+        heavy_row[slot] = (int32_t)r;
+        heavy_first[slot] = first;
+        for (unsigned s = 0; s < nseg; s++) heavy_seg[first + s] = make_int2((int)r, (int)s);
+      }
+    }
+  }
+}
+
+static int dev_alloc(gdn_graph *g, void **p, size_t bytes) {
+  GDN_CUDA(cudaMalloc(p, bytes ? bytes : 16));
+  g->device_bytes += bytes;
+  return GDN_OK;
+}
+
+template <typename OffT>
+static int build_schedule_t(gdn_graph *g, DevCsr &c) {
+  cudaStream_t st = lib().stream;
+  const uint64_t nch = c.nnz / kChunk + 1;
+  if (nch > 0x7ffffff0ull) { set_error("too many row blocks"); return GDN_ERR_ARG; }
+  c.n_chunks = (int32_t)nch;
+  GDN_CHECK(dev_alloc(g, (void **)&c.chunk_row, sizeof(int32_t) * (nch + 1)));
+  const OffT *rp = (const OffT *)c.rowptr;
+  build_chunk_rows<OffT><<<(unsigned)((nch + 1 + 255) / 256), 256, 0, st>>>(rp, c.rows, c.n_chunks, c.chunk_row);
+  unsigned long long *counter;
+  GDN_CUDA(cudaMalloc((void **)&counter, 8));
+  GDN_CUDA(cudaMemsetAsync(counter, 0, 8, st));
+  const int grid = (int)std::min<int64_t>((c.rows + 255) / 256 + 1, 148 * 16);
+  scan_heavy<OffT, false><<<grid, 256, 0, st>>>(rp, c.rows, counter, nullptr, nullptr, nullptr);
+  unsigned long long h = 0;
+  GDN_CUDA(cudaMemcpyAsync(&h, counter, 8, cudaMemcpyDeviceToHost, st));
+  GDN_CUDA(cudaStreamSynchronize(st));
+  c.n_heavy_rows = (int32_t)(h >> 32);
+  c.n_heavy_segs = (int32_t)(h & 0xffffffffu);
+  if (c.n_heavy_rows > 0) {
+    GDN_CHECK(dev_alloc(g, (void **)&c.heavy_row, sizeof(int32_t) * c.n_heavy_rows));
+    GDN_CHECK(dev_alloc(g, (void **)&c.heavy_first, sizeof(int32_t) * c.n_heavy_rows));
+    GDN_CHECK(dev_alloc(g, (void **)&c.heavy_seg, sizeof(int2) * c.n_heavy_segs));
+    GDN_CHECK(dev_alloc(g, (void **)&c.heavy_partial, sizeof(float) * c.n_heavy_segs));
+    GDN_CUDA(cudaMemsetAsync(counter, 0, 8, st));
+    scan_heavy<OffT, true><<<grid, 256, 0, st>>>(rp, c.rows, counter, c.heavy_row, c.heavy_first, c.heavy_seg);
+  }
+  GDN_CUDA(cudaStreamSynchronize(st));
+  GDN_CUDA(cudaFree(counter));
+  GDN_CUDA(cudaGetLastError());
+  return GDN_OK;
+}
+
+int build_schedule(gdn_graph *g, DevCsr &c) {
+  return c.off64 ? build_schedule_t<uint64_t>(g, c) : build_schedule_t<uint32_t>(g, c);
+}
+
+// ---------------------------------------------------------------- launch helpers
+static int gather_grid(const DevCsr &c) {
+  const int64_t items = (int64_t)c.n_chunks + c.n_heavy_segs;
+  const int64_t want = (items + kWarps - 1) / kWarps;
+  const int64_t cap = (int64_t)lib().sm_count * 4 * 2;      // 2 waves of 4 resident CTAs per SM
+  return (int)std::max<int64_t>(1, std::min(want, cap));
+}
+static int heavy_grid(const DevCsr &c) {
+  const int64_t want = ((int64_t)c.n_heavy_rows + kWarps - 1) / kWarps;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)lib().sm_count * 4));
+}
+
+static void fill_sched(const DevCsr &c, GatherArgs &a) {
+  a.chunk_row = c.chunk_row; a.n_chunks = c.n_chunks;
+  a.heavy_seg = c.heavy_seg; a.n_heavy_segs = c.n_heavy_segs;
+  a.heavy_partial = c.heavy_partial; a.heavy_row = c.heavy_row;
+  a.heavy_first = c.heavy_first; a.n_heavy_rows = c.n_heavy_rows;
+  a.rows = c.rows; a.nnz = c.nnz;
+}
+
+template <typename OffT>
+static int spmv_t(gdn_graph *g, const float *d_Ax, const float *d_x, float *d_y, gdn_stats *st) {
+  const DevCsr &c = g->in;
+  GatherArgs a = {};
+  fill_sched(c, a);
+  a.Ax = d_Ax; a.vec = d_x; a.y = d_y;
+  cudaStream_t s = lib().stream;
+  const OffT *rp = (const OffT *)c.rowptr;
+  GDN_CUDA(cudaEventRecord(lib().ev0, s));
+  gather_kernel<OffT, kModeSpmv><<<gather_grid(c), kThreads, 0, s>>>(rp, c.col, a);
+  int launches = 1;
+  if (c.n_heavy_rows > 0) {
+    finalize_heavy<OffT, kModeSpmv><<<heavy_grid(c), kThreads, 0, s>>>(rp, a);
+    launches++;
+  }
+  GDN_CUDA(cudaEventRecord(lib().ev1, s));
+  GDN_CUDA(cudaStreamSynchronize(s));
+  GDN_CUDA(cudaGetLastError());
+  if (st) {
+    float ms = 0;
+    GDN_CUDA(cudaEventElapsedTime(&ms, lib().ev0, lib().ev1));
+    st->solve_ms = ms; st->kernel_launches = launches; st->iterations = 1;
+  }
+  return GDN_OK;
+}
+
+int spmv_run(gdn_graph *g, const float *d_Ax, const float *d_x, float *d_y, gdn_stats *st) {
+  if (((uintptr_t)d_Ax & 31) != 0) { set_error("d_Ax must be 32-byte aligned"); return GDN_ERR_ARG; }
+  return g->in.off64 ? spmv_t<uint64_t>(g, d_Ax, d_x, d_y, st) : spmv_t<uint32_t>(g, d_Ax, d_x, d_y, st);
+}
+
+int pr_exchange(gdn_graph *g, float *contrib, double *err_slot);   // comm.cu: allgather over NVLink (no-op at 1 GPU)
+int comm_size();
+int64_t partition_width(int64_t m, int nparts);
+
+template <typename OffT>
+static int pr_t(gdn_graph *g, float *d_scores, float damp, double eps, int max_iter, gdn_stats *st) {
+  const DevCsr &c = g->in;
+  cudaStream_t s = lib().stream;
+  const OffT *rp = (const OffT *)c.rowptr;
+  const int ggrid = gather_grid(c), hgrid = heavy_grid(c);
+  const int n_partial = ggrid * kWarps + (c.n_heavy_rows > 0 ? hgrid * kWarps : 0);
+  if (!g->contrib[0]) {
+    // full-length vector, padded so that every rank's allgather slice has equal width
+    const int64_t len = std::max<int64_t>(g->m, partition_width(g->m, comm_size()) * comm_size());
+    GDN_CHECK(dev_alloc(g, (void **)&g->contrib[0], sizeof(float) * len));
+    GDN_CHECK(dev_alloc(g, (void **)&g->contrib[1], sizeof(float) * len));
+    GDN_CHECK(dev_alloc(g, (void **)&g->err_trace, sizeof(double) * GDN_MAX_PR_ITER));
+    GDN_CHECK(dev_alloc(g, (void **)&g->pr_done, sizeof(int32_t)));
+  }
+  if (g->n_err_partial < n_partial) {
+    if (g->err_partial) GDN_CUDA(cudaFree(g->err_partial));
+    GDN_CHECK(dev_alloc(g, (void **)&g->err_partial, sizeof(double) * n_partial));
+    g->n_err_partial = n_partial;
+  }
+  if (max_iter > GDN_MAX_PR_ITER - 1) max_iter = GDN_MAX_PR_ITER - 1;
+  GatherArgs a = {};
+  fill_sched(c, a);
+  a.scores = d_scores; a.out_degree = g->out_degree; a.row_lo = g->row_lo;
+  a.base = (1.0f - damp) / (float)(int32_t)g->m;            // pr/omp_base.cc:16
+  a.damp = damp; a.err_partial = g->err_partial; a.done = g->pr_done;
+  double *h_err = (double *)lib().pinned;
+  int64_t launches = 0;
+
+  GDN_CUDA(cudaEventRecord(lib().ev0, s));
+  GDN_CUDA(cudaMemsetAsync(g->pr_done, 0, sizeof(int32_t), s));
+  const int igrid = (int)std::min<int64_t>((c.rows + 255) / 256 + 1, (int64_t)lib().sm_count * 8);
+  pr_init_contrib<OffT><<<igrid, 256, 0, s>>>(rp, g->out_degree, d_scores, g->contrib[0], c.rows, g->row_lo);
+  launches++;
+  GDN_CHECK(pr_exchange(g, g->contrib[0], nullptr));
+  int iter, cur = 0;
+  for (iter = 0; iter < max_iter; iter++) {
+    a.vec = g->contrib[cur];
+    a.contrib_out = g->contrib[cur ^ 1];
+    a.err_slot0 = 0;
+    gather_kernel<OffT, kModePr><<<ggrid, kThreads, 0, s>>>(rp, c.col, a);
+    launches++;
+    if (c.n_heavy_rows > 0) {
+      a.err_slot0 = ggrid * kWarps;
+      finalize_heavy<OffT, kModePr><<<hgrid, kThreads, 0, s>>>(rp, a);
+      launches++;
+    }
+    // multi-GPU: the stop test needs the all-reduced delta, so the host decides
+    pr_reduce_err<<<1, 256, 0, s>>>(g->err_partial, n_partial, g->err_trace, iter, comm_size() > 1 ? -1.0 : eps, g->pr_done);
+    launches++;
+    GDN_CHECK(pr_exchange(g, g->contrib[cur ^ 1], g->err_trace + iter));
+    GDN_CUDA(cudaMemcpyAsync(h_err, g->err_trace + iter, sizeof(double), cudaMemcpyDeviceToHost, s));
+    GDN_CUDA(cudaStreamSynchronize(s));
+    if (st) st->pr_err[iter] = *h_err;
+    cur ^= 1;
+    if (*h_err < eps) break;                                 // pr/omp_base.cc:36
+  }
+  GDN_CUDA(cudaEventRecord(lib().ev1, s));
+  GDN_CUDA(cudaStreamSynchronize(s));
+  GDN_CUDA(cudaGetLastError());
+  if (st) {
+    float ms = 0;
+    GDN_CUDA(cudaEventElapsedTime(&ms, lib().ev0, lib().ev1));
+    st->solve_ms = ms;
+    st->kernel_launches = launches;
+    st->iterations = iter + 1;                               // printf("iterations = %d", iter+1), :38
+  }
+  return GDN_OK;
+}
+
+int pr_run(gdn_graph *g, float *d_scores, float damp, double eps, int max_iter, gdn_stats *st) {
+  return g->in.off64 ? pr_t<uint64_t>(g, d_scores, damp, eps, max_iter, st)
+                     : pr_t<uint32_t>(g, d_scores, damp, eps, max_iter, st);
+}
+
+}  // namespace gdn

@@ -1,0 +1,307 @@
+// graph.cu -- library state, device-resident CSR (gdn_graph) and the C-ABI
+// entry points of include/gdn_b200.h that touch the device.
+//
+// gdn_graph_create replaces the cudaMalloc+cudaMemcpy prologue that every
+// reference CUDA solver repeats (e.g. src/pr/warp.cu:137-155): offsets are
+// narrowed to 32 bits on the device when the local nnz allows it (the reference
+// narrows uint64 -> int unconditionally), column indices stay global.
+#include "common.cuh"
+#include <cstdarg>
+#include <cstring>
+#include <chrono>
+#include <vector>
+
+namespace gdn {
+
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+Lib &lib() { static Lib l; return l; }
+
+int ensure_init() {
+  if (lib().inited) return GDN_OK;
+  return gdn_init(0);
+}
+
+int build_schedule(gdn_graph *g, DevCsr &c);
+int bfs_run(gdn_graph *g, int32_t source, int32_t *d_depth, int32_t *d_parent, gdn_stats *st);
+int pr_run(gdn_graph *g, float *d_scores, float damp, double eps, int max_iter, gdn_stats *st);
+int spmv_run(gdn_graph *g, const float *d_Ax, const float *d_x, float *d_y, gdn_stats *st);
+
+// in[i] - base -> out[i]
+template <typename InT, typename OutT>
+__global__ void convert_offsets(const InT *__restrict__ in, OutT *__restrict__ out, int64_t n, uint64_t base) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (OutT)((uint64_t)in[i] - base);
+}
+
+template <typename OffT>
+__global__ void row_lengths(const OffT *__restrict__ rp, int32_t *__restrict__ deg, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    deg[i] = (int32_t)(rp[i + 1] - rp[i]);
+}
+
+// Checks monotone offsets and 0 <= col < m; flag[0] != 0 on violation.
+template <typename OffT>
+__global__ void validate_csr(const OffT *__restrict__ rp, const int32_t *__restrict__ col, int64_t rows,
+                             uint64_t nnz, int64_t m, int *flag) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = tid; r < rows; r += nth)
+    if (rp[r] > rp[r + 1]) atomicExch(flag, 1);
+  if (tid == 0 && (rp[0] != 0 || (uint64_t)rp[rows] != nnz)) atomicExch(flag, 2);
+  for (uint64_t e = tid; e < nnz; e += nth) {
+    const int32_t c = col[e];
+    if (c < 0 || c >= m) atomicExch(flag, 3);
+  }
+}
+
+template <typename HostOffT>
+static int upload_csr(gdn_graph *g, DevCsr &c, const HostOffT *h_rowptr, const int32_t *h_col, int64_t row_lo,
+                      int64_t row_hi, bool want_schedule) {
+  cudaStream_t st = lib().stream;
+  c.rows = row_hi - row_lo;
+  const uint64_t base = (uint64_t)h_rowptr[row_lo];
+  c.nnz = (uint64_t)h_rowptr[row_hi] - base;
+  c.off64 = c.nnz >= 0xffff0000ull;
+  const size_t off_bytes = (c.off64 ? 8 : 4) * (size_t)(c.rows + 1);
+  GDN_CUDA(cudaMalloc(&c.rowptr, off_bytes));
+  const size_t col_bytes = sizeof(int32_t) * c.nnz + 256;          // slack for 256-bit over-reads
+  GDN_CUDA(cudaMalloc((void **)&c.col, col_bytes));
+  g->device_bytes += off_bytes + col_bytes;
+  // offsets: stage the host-typed slice, narrow/rebase on the device
+  HostOffT *tmp = nullptr;
+  GDN_CUDA(cudaMalloc((void **)&tmp, sizeof(HostOffT) * (c.rows + 1)));
+  GDN_CUDA(cudaMemcpyAsync(tmp, h_rowptr + row_lo, sizeof(HostOffT) * (c.rows + 1), cudaMemcpyHostToDevice, st));
+  const int grid = (int)std::min<int64_t>((c.rows + 256) / 256, (int64_t)lib().sm_count * 8);
+  if (c.off64) convert_offsets<HostOffT, uint64_t><<<grid, 256, 0, st>>>(tmp, (uint64_t *)c.rowptr, c.rows + 1, base);
+  else convert_offsets<HostOffT, uint32_t><<<grid, 256, 0, st>>>(tmp, (uint32_t *)c.rowptr, c.rows + 1, base);
+  GDN_CUDA(cudaMemcpyAsync(c.col, h_col + base, sizeof(int32_t) * c.nnz, cudaMemcpyHostToDevice, st));
+  GDN_CUDA(cudaMemsetAsync((char *)c.col + sizeof(int32_t) * c.nnz, 0, 256, st));
+  int *flag = nullptr;
+  GDN_CUDA(cudaMalloc((void **)&flag, sizeof(int)));
+  GDN_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
+  const int vgrid = lib().sm_count * 8;
+  if (c.off64) validate_csr<uint64_t><<<vgrid, 256, 0, st>>>((const uint64_t *)c.rowptr, c.col, c.rows, c.nnz, g->m, flag);
+  else validate_csr<uint32_t><<<vgrid, 256, 0, st>>>((const uint32_t *)c.rowptr, c.col, c.rows, c.nnz, g->m, flag);
+  int hflag = 0;
+  GDN_CUDA(cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  GDN_CUDA(cudaStreamSynchronize(st));
+  GDN_CUDA(cudaFree(tmp));
+  GDN_CUDA(cudaFree(flag));
+  GDN_CUDA(cudaGetLastError());
+  if (hflag) {
+    set_error("malformed CSR (%s)", hflag == 1 ? "row offsets not monotone" : hflag == 2 ? "offset ends" : "column index out of range");
+    return GDN_ERR_GRAPH;
+  }
+  if (want_schedule) GDN_CHECK(build_schedule(g, c));
+  return GDN_OK;
+}
+
+static void free_csr(DevCsr &c) {
+  cudaFree(c.rowptr); cudaFree(c.col); cudaFree(c.chunk_row); cudaFree(c.heavy_row);
+  cudaFree(c.heavy_first); cudaFree(c.heavy_seg); cudaFree(c.heavy_partial);
+  c = DevCsr();
+}
+
+template <typename HostOffT>
+static int graph_create_t(int64_t m, int64_t nnz, const HostOffT *out_rowptr, const int32_t *out_colidx,
+                          const HostOffT *in_rowptr, const int32_t *in_colidx, int64_t row_lo, int64_t row_hi,
+                          gdn_graph **out) {
+  GDN_CHECK(ensure_init());
+  if (!out || m <= 0 || m > 0x7fffffffll || nnz < 0 || row_lo < 0 || row_hi > m || row_lo > row_hi) {
+    set_error("gdn_graph_create: bad sizes (m=%lld nnz=%lld rows=[%lld,%lld))", (long long)m, (long long)nnz,
+              (long long)row_lo, (long long)row_hi);
+    return GDN_ERR_ARG;
+  }
+  if (!out_rowptr && !in_rowptr) { set_error("gdn_graph_create: no CSR given"); return GDN_ERR_ARG; }
+  gdn_graph *g = new gdn_graph();
+  g->m = m; g->row_lo = row_lo; g->row_hi = row_hi;
+  int rc = GDN_OK;
+  if (out_rowptr && (!in_rowptr || (in_rowptr == out_rowptr && in_colidx == out_colidx))) {
+    // one CSR serves both directions (symmetrized graph, include/csr_graph.h:241-246)
+    rc = upload_csr(g, g->out, out_rowptr, out_colidx, row_lo, row_hi, true);
+    g->symmetric = true;
+    g->has_out = g->has_in = true;
+    g->in = g->out;      // shallow alias; freed once
+  } else if (!out_rowptr) {
+    // pull-only graph: PageRank additionally needs gdn_graph_set_out_degree
+    rc = upload_csr(g, g->in, in_rowptr, in_colidx, row_lo, row_hi, true);
+    g->has_in = true;
+  } else {
+    rc = upload_csr(g, g->out, out_rowptr, out_colidx, row_lo, row_hi, false);
+    if (rc == GDN_OK) rc = upload_csr(g, g->in, in_rowptr, in_colidx, row_lo, row_hi, true);
+    g->has_out = g->has_in = true;
+    if (rc == GDN_OK) {
+      // PageRank divides by the OUT degree (src/pr/omp_base.cc:25)
+      cudaStream_t st = lib().stream;
+      const int64_t rows = row_hi - row_lo;
+      if (cudaMalloc((void **)&g->out_degree, sizeof(int32_t) * (rows + 1)) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("out of device memory");
+        rc = GDN_ERR_NOMEM;
+      } else {
+        g->device_bytes += sizeof(int32_t) * (rows + 1);
+        const int grid = (int)std::min<int64_t>((rows + 256) / 256, (int64_t)lib().sm_count * 8);
+        if (g->out.off64) row_lengths<uint64_t><<<grid, 256, 0, st>>>((const uint64_t *)g->out.rowptr, g->out_degree, rows);
+        else row_lengths<uint32_t><<<grid, 256, 0, st>>>((const uint32_t *)g->out.rowptr, g->out_degree, rows);
+        if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("row_lengths failed"); rc = GDN_ERR_CUDA; }
+      }
+    }
+  }
+  if (rc != GDN_OK) { gdn_graph_destroy(g); return rc; }
+  *out = g;
+  return GDN_OK;
+}
+
+}  // namespace gdn
+
+using namespace gdn;
+
+extern "C" {
+
+int gdn_version(void) { return GDN_VERSION; }
+const char *gdn_last_error(void) { return g_err; }
+
+int gdn_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int gdn_init(int device) {
+  Lib &l = lib();
+  if (l.inited && l.device == device) return GDN_OK;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    set_error("no CUDA device: libgdn_b200 has no CPU fallback (%s)", e != cudaSuccess ? cudaGetErrorString(e) : "0 devices");
+    return GDN_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= n) { set_error("device %d out of range (%d devices)", device, n); return GDN_ERR_ARG; }
+  cudaDeviceProp p;
+  GDN_CUDA(cudaGetDeviceProperties(&p, device));
+  if (p.major != 10) {
+    set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, p.major, p.minor);
+    return GDN_ERR_NO_DEVICE;
+  }
+  if (l.inited) gdn_finalize();
+  GDN_CUDA(cudaSetDevice(device));
+  l.device = device;
+  l.sm_count = p.multiProcessorCount;
+  GDN_CUDA(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+  GDN_CUDA(cudaEventCreate(&l.ev0));
+  GDN_CUDA(cudaEventCreate(&l.ev1));
+  l.pinned_bytes = 4096;
+  GDN_CUDA(cudaHostAlloc(&l.pinned, l.pinned_bytes, cudaHostAllocDefault));
+  l.inited = true;
+  return GDN_OK;
+}
+
+int gdn_finalize(void) {
+  Lib &l = lib();
+  if (!l.inited) return GDN_OK;
+  cudaStreamSynchronize(l.stream);
+  cudaStreamDestroy(l.stream);
+  cudaEventDestroy(l.ev0);
+  cudaEventDestroy(l.ev1);
+  cudaFreeHost(l.pinned);
+  l = Lib();
+  return GDN_OK;
+}
+
+int gdn_graph_create(int64_t m, int64_t nnz, const uint64_t *out_rowptr, const int32_t *out_colidx,
+                     const uint64_t *in_rowptr, const int32_t *in_colidx, int64_t row_lo, int64_t row_hi,
+                     gdn_graph **g) {
+  return graph_create_t<uint64_t>(m, nnz, out_rowptr, out_colidx, in_rowptr, in_colidx, row_lo, row_hi, g);
+}
+
+int gdn_graph_create_i32(int32_t m, int32_t nnz, const int32_t *out_row_offsets, const int32_t *out_column_indices,
+                         const int32_t *in_row_offsets, const int32_t *in_column_indices, gdn_graph **g) {
+  return graph_create_t<int32_t>(m, nnz, out_row_offsets, out_column_indices, in_row_offsets, in_column_indices, 0, m, g);
+}
+
+int gdn_graph_set_out_degree(gdn_graph *g, const int32_t *h_out_degree) {
+  if (!g || !h_out_degree) { set_error("gdn_graph_set_out_degree: null argument"); return GDN_ERR_ARG; }
+  const int64_t rows = g->row_hi - g->row_lo;
+  if (!g->out_degree) {
+    GDN_CUDA(cudaMalloc((void **)&g->out_degree, sizeof(int32_t) * (rows + 1)));
+    g->device_bytes += sizeof(int32_t) * (rows + 1);
+  }
+  GDN_CUDA(cudaMemcpyAsync(g->out_degree, h_out_degree, sizeof(int32_t) * rows, cudaMemcpyHostToDevice, lib().stream));
+  GDN_CUDA(cudaStreamSynchronize(lib().stream));
+  return GDN_OK;
+}
+
+int gdn_graph_destroy(gdn_graph *g) {
+  if (!g) return GDN_OK;
+  if (g->symmetric) { free_csr(g->out); g->in = DevCsr(); }
+  else { free_csr(g->out); free_csr(g->in); }
+  cudaFree(g->contrib[0]); cudaFree(g->contrib[1]); cudaFree(g->out_degree); cudaFree(g->err_partial);
+  cudaFree(g->err_trace); cudaFree(g->pr_done);
+  cudaFree(g->visited); cudaFree(g->front); cudaFree(g->next); cudaFree(g->queue[0]); cudaFree(g->queue[1]);
+  cudaFree(g->heavy_queue); cudaFree(g->counters);
+  cudaGetLastError();
+  delete g;
+  return GDN_OK;
+}
+
+int gdn_graph_info(const gdn_graph *g, int64_t info[8]) {
+  if (!g || !info) return GDN_ERR_ARG;
+  info[0] = g->m; info[1] = (int64_t)g->in.nnz; info[2] = g->row_lo; info[3] = g->row_hi;
+  info[4] = g->in.n_chunks; info[5] = g->in.n_heavy_segs; info[6] = (int64_t)g->device_bytes;
+  info[7] = g->in.off64 ? 64 : 32;
+  return GDN_OK;
+}
+
+int gdn_bfs_resident(gdn_graph *g, int32_t source, int32_t *d_depth, int32_t *d_parent, gdn_stats *st) {
+  if (!g || !d_depth) { set_error("gdn_bfs_resident: null argument"); return GDN_ERR_ARG; }
+  if (st) memset(st, 0, sizeof(*st));
+  return bfs_run(g, source, d_depth, d_parent, st);
+}
+
+int gdn_pagerank_resident(gdn_graph *g, float *d_scores, float damp, double eps, int max_iter, gdn_stats *st) {
+  if (!g || !d_scores || max_iter < 0) { set_error("gdn_pagerank_resident: bad argument"); return GDN_ERR_ARG; }
+  if (!g->has_in) { set_error("PageRank pull needs the in-CSR"); return GDN_ERR_GRAPH; }
+  if (!g->symmetric && !g->out_degree) { set_error("PageRank on a pull-only graph needs gdn_graph_set_out_degree"); return GDN_ERR_GRAPH; }
+  if (st) memset(st, 0, sizeof(*st));
+  return pr_run(g, d_scores, damp, eps, max_iter, st);
+}
+
+int gdn_spmv_resident(gdn_graph *g, const float *d_Ax, const float *d_x, float *d_y, gdn_stats *st) {
+  if (!g || !d_Ax || !d_x || !d_y) { set_error("gdn_spmv_resident: null argument"); return GDN_ERR_ARG; }
+  if (!g->has_in) { set_error("SpMV needs the in-CSR"); return GDN_ERR_GRAPH; }
+  if (st) memset(st, 0, sizeof(*st));
+  return spmv_run(g, d_Ax, d_x, d_y, st);
+}
+
+int gdn_dev_alloc(size_t bytes, void **d_ptr) {
+  GDN_CHECK(ensure_init());
+  GDN_CUDA(cudaMalloc(d_ptr, bytes ? bytes : 16));
+  return GDN_OK;
+}
+int gdn_dev_free(void *d_ptr) { GDN_CUDA(cudaFree(d_ptr)); return GDN_OK; }
+int gdn_memcpy_h2d(void *d, const void *h, size_t bytes) {
+  GDN_CHECK(ensure_init());
+  GDN_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, lib().stream));
+  GDN_CUDA(cudaStreamSynchronize(lib().stream));
+  return GDN_OK;
+}
+int gdn_memcpy_d2h(void *h, const void *d, size_t bytes) {
+  GDN_CHECK(ensure_init());
+  GDN_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, lib().stream));
+  GDN_CUDA(cudaStreamSynchronize(lib().stream));
+  return GDN_OK;
+}
+int gdn_device_sync(void) {
+  GDN_CHECK(ensure_init());
+  GDN_CUDA(cudaDeviceSynchronize());
+  return GDN_OK;
+}
+
+}  // extern "C"

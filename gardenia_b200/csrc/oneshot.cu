@@ -1,0 +1,163 @@
+// oneshot.cu -- the reference-facing one-shot entry points: HOST pointers in,
+// HOST results out; upload, solve, download and free inside the call, exactly
+// the ownership contract of the reference's CUDA solvers
+// (src/pr/base.cu:83-101,133-139; src/bfs/linear_base.cu:34-89;
+// src/spmv/base.cu:28-76).  These are what BFSSolver / PRSolver / SpmvSolver
+// shims bind.
+#include "common.cuh"
+#include <chrono>
+#include <cstring>
+
+using namespace gdn;
+
+namespace {
+double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+struct DevBuf {
+  void *p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  int alloc(size_t bytes) { GDN_CUDA(cudaMalloc(&p, bytes ? bytes : 16)); return GDN_OK; }
+};
+struct GraphGuard {
+  gdn_graph *g = nullptr;
+  ~GraphGuard() { gdn_graph_destroy(g); }
+};
+int h2d(void *d, const void *h, size_t bytes) {
+  GDN_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, lib().stream));
+  return GDN_OK;
+}
+int d2h(void *h, const void *d, size_t bytes) {
+  GDN_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, lib().stream));
+  GDN_CUDA(cudaStreamSynchronize(lib().stream));
+  return GDN_OK;
+}
+
+template <typename OffT>
+int create(int64_t m, int64_t nnz, const OffT *orp, const int32_t *oci, const OffT *irp, const int32_t *ici,
+           gdn_graph **g);
+template <>
+int create<uint64_t>(int64_t m, int64_t nnz, const uint64_t *orp, const int32_t *oci, const uint64_t *irp,
+                     const int32_t *ici, gdn_graph **g) {
+  return gdn_graph_create(m, nnz, orp, oci, irp, ici, 0, m, g);
+}
+template <>
+int create<int32_t>(int64_t m, int64_t nnz, const int32_t *orp, const int32_t *oci, const int32_t *irp,
+                    const int32_t *ici, gdn_graph **g) {
+  return gdn_graph_create_i32((int32_t)m, (int32_t)nnz, orp, oci, irp, ici, g);
+}
+
+template <typename OffT>
+int bfs_oneshot(int64_t m, int64_t nnz, const OffT *orp, const int32_t *oci, const OffT *irp, const int32_t *ici,
+                int32_t source, int32_t *depth_out, int32_t *parent_out, gdn_stats *st) {
+  if (!orp || !oci || !depth_out) { set_error("gdn_bfs: null argument"); return GDN_ERR_ARG; }
+  GDN_CHECK(ensure_init());
+  const double t0 = now_ms();
+  GraphGuard gg;
+  GDN_CHECK(create<OffT>(m, nnz, orp, oci, irp, ici, &gg.g));
+  DevBuf depth, parent;
+  GDN_CHECK(depth.alloc(sizeof(int32_t) * m));
+  if (parent_out) GDN_CHECK(parent.alloc(sizeof(int32_t) * m));
+  const double t1 = now_ms();
+  gdn_stats local;
+  gdn_stats *s = st ? st : &local;
+  GDN_CHECK(gdn_bfs_resident(gg.g, source, (int32_t *)depth.p, (int32_t *)parent.p, s));
+  const double t2 = now_ms();
+  GDN_CHECK(d2h(depth_out, depth.p, sizeof(int32_t) * m));
+  if (parent_out) GDN_CHECK(d2h(parent_out, parent.p, sizeof(int32_t) * m));
+  const double t3 = now_ms();
+  s->h2d_ms = t1 - t0; s->d2h_ms = t3 - t2;
+  s->h2d_bytes = (int64_t)(sizeof(OffT) * (m + 1) + sizeof(int32_t) * nnz) * ((irp && irp != orp) ? 2 : 1);
+  s->d2h_bytes = (int64_t)sizeof(int32_t) * m * (parent_out ? 2 : 1);
+  return GDN_OK;
+}
+
+template <typename OffT>
+int pr_oneshot(int64_t m, int64_t nnz, const OffT *irp, const int32_t *ici, const int32_t *out_degree,
+               float *scores, float damp, double eps, int max_iter, gdn_stats *st) {
+  if (!irp || !ici || !out_degree || !scores) { set_error("gdn_pagerank_pull: null argument"); return GDN_ERR_ARG; }
+  GDN_CHECK(ensure_init());
+  const double t0 = now_ms();
+  GraphGuard gg;
+  GDN_CHECK(create<OffT>(m, nnz, nullptr, nullptr, irp, ici, &gg.g));
+  GDN_CHECK(gdn_graph_set_out_degree(gg.g, out_degree));
+  DevBuf sc;
+  GDN_CHECK(sc.alloc(sizeof(float) * m));
+  GDN_CHECK(h2d(sc.p, scores, sizeof(float) * m));
+  GDN_CUDA(cudaStreamSynchronize(lib().stream));
+  const double t1 = now_ms();
+  gdn_stats local;
+  gdn_stats *s = st ? st : &local;
+  GDN_CHECK(gdn_pagerank_resident(gg.g, (float *)sc.p, damp, eps, max_iter, s));
+  const double t2 = now_ms();
+  GDN_CHECK(d2h(scores, sc.p, sizeof(float) * m));
+  const double t3 = now_ms();
+  s->h2d_ms = t1 - t0; s->d2h_ms = t3 - t2;
+  s->h2d_bytes = (int64_t)(sizeof(OffT) * (m + 1) + sizeof(int32_t) * nnz + 8 * m);
+  s->d2h_bytes = (int64_t)sizeof(float) * m;
+  return GDN_OK;
+}
+
+template <typename OffT>
+int spmv_oneshot(int64_t m, int64_t nnz, const OffT *Ap, const int32_t *Aj, const float *Ax, const float *x,
+                 float *y, gdn_stats *st) {
+  if (!Ap || !Aj || !Ax || !x || !y) { set_error("gdn_spmv_csr: null argument"); return GDN_ERR_ARG; }
+  GDN_CHECK(ensure_init());
+  const double t0 = now_ms();
+  GraphGuard gg;
+  GDN_CHECK(create<OffT>(m, nnz, nullptr, nullptr, Ap, Aj, &gg.g));
+  DevBuf dAx, dx, dy;
+  GDN_CHECK(dAx.alloc(sizeof(float) * nnz + 256));
+  GDN_CHECK(dx.alloc(sizeof(float) * m));
+  GDN_CHECK(dy.alloc(sizeof(float) * m));
+  GDN_CHECK(h2d(dAx.p, Ax, sizeof(float) * nnz));
+  GDN_CHECK(h2d(dx.p, x, sizeof(float) * m));
+  GDN_CHECK(h2d(dy.p, y, sizeof(float) * m));
+  GDN_CUDA(cudaStreamSynchronize(lib().stream));
+  const double t1 = now_ms();
+  gdn_stats local;
+  gdn_stats *s = st ? st : &local;
+  GDN_CHECK(gdn_spmv_resident(gg.g, (const float *)dAx.p, (const float *)dx.p, (float *)dy.p, s));
+  const double t2 = now_ms();
+  GDN_CHECK(d2h(y, dy.p, sizeof(float) * m));
+  const double t3 = now_ms();
+  s->h2d_ms = t1 - t0; s->d2h_ms = t3 - t2;
+  s->h2d_bytes = (int64_t)(sizeof(OffT) * (m + 1) + 8 * nnz + 8 * m);
+  s->d2h_bytes = (int64_t)sizeof(float) * m;
+  return GDN_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int gdn_bfs(int64_t m, int64_t nnz, const uint64_t *out_rowptr, const int32_t *out_colidx,
+            const uint64_t *in_rowptr, const int32_t *in_colidx, int32_t source, int32_t *depth_out,
+            int32_t *parent_out, gdn_stats *st) {
+  return bfs_oneshot<uint64_t>(m, nnz, out_rowptr, out_colidx, in_rowptr, in_colidx, source, depth_out, parent_out, st);
+}
+int gdn_bfs_i32(int32_t m, int32_t nnz, const int32_t *out_row_offsets, const int32_t *out_column_indices,
+                const int32_t *in_row_offsets, const int32_t *in_column_indices, int32_t source,
+                int32_t *depth_out, int32_t *parent_out, gdn_stats *st) {
+  return bfs_oneshot<int32_t>(m, nnz, out_row_offsets, out_column_indices, in_row_offsets, in_column_indices, source,
+                              depth_out, parent_out, st);
+}
+int gdn_pagerank_pull(int64_t m, int64_t nnz, const uint64_t *in_rowptr, const int32_t *in_colidx,
+                      const int32_t *out_degree, float *scores_inout, float damp, double eps, int max_iter,
+                      gdn_stats *st) {
+  return pr_oneshot<uint64_t>(m, nnz, in_rowptr, in_colidx, out_degree, scores_inout, damp, eps, max_iter, st);
+}
+int gdn_pagerank_pull_i32(int32_t m, int32_t nnz, const int32_t *in_row_offsets, const int32_t *in_column_indices,
+                          const int32_t *out_degree, float *scores_inout, float damp, double eps, int max_iter,
+                          gdn_stats *st) {
+  return pr_oneshot<int32_t>(m, nnz, in_row_offsets, in_column_indices, out_degree, scores_inout, damp, eps, max_iter, st);
+}
+int gdn_spmv_csr(int64_t m, int64_t nnz, const uint64_t *Ap, const int32_t *Aj, const float *Ax, const float *x,
+                 float *y_inout, gdn_stats *st) {
+  return spmv_oneshot<uint64_t>(m, nnz, Ap, Aj, Ax, x, y_inout, st);
+}
+int gdn_spmv_csr_i32(int32_t m, int32_t nnz, const int32_t *Ap, const int32_t *Aj, const float *Ax, const float *x,
+                     float *y_inout, gdn_stats *st) {
+  return spmv_oneshot<int32_t>(m, nnz, Ap, Aj, Ax, x, y_inout, st);
+}
+
+}  // extern "C"

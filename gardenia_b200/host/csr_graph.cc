@@ -1,0 +1,278 @@
+// csr_graph.cc -- see csr_graph.hpp.  Reader semantics follow the reference's
+// include/csr_graph.h:55-250 (cited inline); the algorithms are our own.
+#include "csr_graph.hpp"
+#include <omp.h>
+#include <cerrno>
+#include <vector>
+
+namespace gdn {
+
+// Exclusive prefix sum of 64-bit counts, blocked over threads.
+static void prefix_sum(const uint64_t *cnt, int64_t n, uint64_t *out /* n+1 */) {
+  int nt = omp_get_max_threads();
+  std::vector<uint64_t> part(nt + 1, 0);
+#pragma omp parallel num_threads(nt)
+  {
+    int t = omp_get_thread_num();
+    int64_t lo = n * t / nt, hi = n * (t + 1) / nt;
+    uint64_t s = 0;
+    for (int64_t i = lo; i < hi; i++) s += cnt[i];
+    part[t + 1] = s;
+#pragma omp barrier
+#pragma omp single
+    for (int i = 0; i < nt; i++) part[i + 1] += part[i];
+    s = part[t];
+    for (int64_t i = lo; i < hi; i++) { uint64_t c = cnt[i]; out[i] = s; s += c; }
+  }
+  out[n] = part[nt];
+}
+
+VertexId build_csr(int64_t m, const EdgePair32 *edges, int64_t n_edges, bool transpose,
+                   bool remove_self, uint64_t *&rowptr, VertexId *&col, uint64_t &nnz) {
+  std::vector<uint64_t> cnt(m + 1, 0);
+#pragma omp parallel for
+  for (int64_t e = 0; e < n_edges; e++) {
+    VertexId s = transpose ? edges[e].v : edges[e].u;
+#pragma omp atomic
+    cnt[s]++;
+  }
+  std::vector<uint64_t> off(m + 1);
+  prefix_sum(cnt.data(), m, off.data());
+  std::vector<uint64_t> cur(off.begin(), off.end() - 1);
+  VertexId *raw = new VertexId[std::max<uint64_t>(off[m], 1)];
+#pragma omp parallel for
+  for (int64_t e = 0; e < n_edges; e++) {
+    VertexId s = transpose ? edges[e].v : edges[e].u;
+    VertexId d = transpose ? edges[e].u : edges[e].v;
+    uint64_t pos;
+#pragma omp atomic capture
+    pos = cur[s]++;
+    raw[pos] = d;
+  }
+  // sort + unique (+ drop self) each row in place; cnt[] becomes the new degree
+#pragma omp parallel for schedule(dynamic, 1024)
+  for (int64_t v = 0; v < m; v++) {
+    VertexId *b = raw + off[v], *e = raw + off[v + 1];
+    std::sort(b, e);
+    e = std::unique(b, e);
+    if (remove_self) e = std::remove(b, e, (VertexId)v);
+    cnt[v] = (uint64_t)(e - b);
+  }
+  rowptr = new uint64_t[m + 1];
+  prefix_sum(cnt.data(), m, rowptr);
+  nnz = rowptr[m];
+  col = new VertexId[std::max<uint64_t>(nnz, 1)];
+  VertexId maxdeg = 0;
+#pragma omp parallel for schedule(dynamic, 1024) reduction(max : maxdeg)
+  for (int64_t v = 0; v < m; v++) {
+    std::copy(raw + off[v], raw + off[v] + cnt[v], col + rowptr[v]);
+    maxdeg = std::max(maxdeg, (VertexId)cnt[v]);
+  }
+  delete[] raw;
+  return maxdeg;
+}
+
+void transpose_csr(int64_t m, const uint64_t *rowptr, const VertexId *col,
+                   uint64_t *&t_rowptr, VertexId *&t_col) {
+  uint64_t nnz = rowptr[m];
+  std::vector<uint64_t> cnt(m + 1, 0);
+#pragma omp parallel for
+  for (int64_t e = 0; e < (int64_t)nnz; e++) {
+#pragma omp atomic
+    cnt[col[e]]++;
+  }
+  t_rowptr = new uint64_t[m + 1];
+  prefix_sum(cnt.data(), m, t_rowptr);
+  t_col = new VertexId[std::max<uint64_t>(nnz, 1)];
+  // Sources are visited in ascending order inside each destination bucket only
+  // if the fill is sequential per bucket; do a parallel fill and sort rows.
+  std::vector<uint64_t> cur(t_rowptr, t_rowptr + m);
+#pragma omp parallel for schedule(dynamic, 1024)
+  for (int64_t v = 0; v < m; v++)
+    for (uint64_t e = rowptr[v]; e < rowptr[v + 1]; e++) {
+      uint64_t pos;
+#pragma omp atomic capture
+      pos = cur[col[e]]++;
+      t_col[pos] = (VertexId)v;
+    }
+#pragma omp parallel for schedule(dynamic, 1024)
+  for (int64_t v = 0; v < m; v++) std::sort(t_col + t_rowptr[v], t_col + t_rowptr[v + 1]);
+}
+
+void Graph::release() {
+  if (reverse_vertices_ != vertices_) delete[] reverse_vertices_;
+  if (reverse_edges_ != edges_) delete[] reverse_edges_;
+  delete[] vertices_;
+  delete[] edges_;
+  vertices_ = reverse_vertices_ = nullptr;
+  edges_ = reverse_edges_ = nullptr;
+}
+
+// csr_graph.h:234-247: reverse CSR is built only for (!symmetrize && need_reverse);
+// a symmetrized graph aliases the forward arrays.
+void Graph::finish(bool symmetrize, bool need_reverse, bool verbose) {
+  directed_ = false;
+  has_reverse_ = false;
+  if (!symmetrize && need_reverse) {
+    transpose_csr(n_vertices_, vertices_, edges_, reverse_vertices_, reverse_edges_);
+    directed_ = true;
+    has_reverse_ = true;
+    if (verbose) printf("This graph maintains both incomming and outgoing edge-list\n");
+  }
+  if (symmetrize) {
+    if (verbose) printf("This graph is symmetrized\n");
+    reverse_vertices_ = vertices_;
+    reverse_edges_ = edges_;
+    has_reverse_ = true;
+  }
+}
+
+static const char *skip_ws(const char *p, const char *end) {
+  while (p < end && (*p == ' ' || *p == '\t' || *p == '\r')) p++;
+  return p;
+}
+// Parse a decimal integer; returns false if none at p.
+static bool parse_int(const char *&p, const char *end, long &out) {
+  p = skip_ws(p, end);
+  const char *q = p;
+  bool neg = false;
+  if (q < end && (*q == '-' || *q == '+')) { neg = (*q == '-'); q++; }
+  if (q >= end || *q < '0' || *q > '9') return false;
+  long v = 0;
+  while (q < end && *q >= '0' && *q <= '9') { v = v * 10 + (*q - '0'); q++; }
+  out = neg ? -v : v;
+  p = q;
+  return true;
+}
+
+int Graph::load_mtx(const std::string &fname, bool symmetrize, bool need_reverse, bool verbose) {
+  if (verbose) std::cout << "Reading (.mtx) input file " << fname << "\n";
+  std::ifstream in(fname.c_str(), std::ios::binary);
+  if (!in) return kLoadNoFile;
+  std::string buf((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+  const char *p = buf.data(), *end = p + buf.size();
+  auto next_eol = [&](const char *q) { while (q < end && *q != '\n') q++; return q; };
+  // csr_graph.h:86-92: skip header lines whose first character is '%'
+  while (p < end && *p == '%') { p = next_eol(p); if (p < end) p++; }
+  const char *eol = next_eol(p);
+  long m = 0, n = 0, nnz_hdr = 0;
+  {
+    const char *q = p;
+    if (!parse_int(q, eol, m) || !parse_int(q, eol, n)) return kLoadBadHeader;
+    parse_int(q, eol, nnz_hdr);
+  }
+  if (m != n && verbose) printf("Warning, m(%ld) != n(%ld)\n", m, n);
+  p = eol < end ? eol + 1 : end;
+  std::vector<EdgePair32> el;
+  el.reserve(nnz_hdr > 0 ? (size_t)nnz_hdr * (symmetrize ? 2 : 1) : 16);
+  // csr_graph.h:66-73,105-118: skip empty and '#' lines; stop at the first
+  // line that does not start with two integers; weights are ignored.
+  while (p < end) {
+    eol = next_eol(p);
+    const char *q = p;
+    bool blank = (eol == p) || (*p == '#') || (eol - p == 1 && *p == '\r');
+    if (!blank) {
+      long a, b;
+      if (!parse_int(q, eol, a) || !parse_int(q, eol, b)) break;
+      if (a != b) {                                   // self loop dropped, :108
+        if (a < 1 || a > m || b < 1 || b > m) return kLoadBadVertex;
+        el.push_back({(VertexId)(a - 1), (VertexId)(b - 1)});
+        if (symmetrize) el.push_back({(VertexId)(b - 1), (VertexId)(a - 1)});   // :113-116
+      }
+    }
+    p = eol < end ? eol + 1 : end;
+  }
+  n_vertices_ = (VertexId)m;
+  uint64_t raw = el.size();
+  max_degree_ = build_csr(m, el.data(), (int64_t)el.size(), false, false, vertices_, edges_, n_edges_);
+  if (verbose) {
+    printf("Removing redundent edges... %d redundent edges are removed\n", (int)(raw - n_edges_));
+    std::cout << "|V| " << n_vertices_ << " |E| " << n_edges_ << "\n";
+  }
+  finish(symmetrize, need_reverse, verbose);
+  return kLoadOk;
+}
+
+template <typename T>
+static bool read_all(const std::string &fname, T *dst, size_t n) {
+  FILE *f = fopen(fname.c_str(), "rb");
+  if (!f) return false;
+  size_t got = fread(dst, sizeof(T), n, f);
+  fclose(f);
+  return got == n;
+}
+
+// csr_graph.h:218-233
+int Graph::load_bin(const std::string &prefix, bool symmetrize, bool need_reverse, bool verbose) {
+  std::ifstream meta((prefix + ".meta.txt").c_str());
+  if (!meta) return kLoadNoFile;
+  long long nv = 0, ne = 0, maxd = 0;
+  int vid_size = 0;
+  meta >> nv >> ne >> vid_size >> maxd;
+  if (!meta || vid_size != (int)sizeof(VertexId)) return kLoadBadHeader;
+  n_vertices_ = (VertexId)nv;
+  n_edges_ = (uint64_t)ne;
+  max_degree_ = (VertexId)maxd;
+  if (verbose) std::cout << "|V| " << n_vertices_ << " |E| " << n_edges_ << "\n";
+  vertices_ = new uint64_t[nv + 1];
+  edges_ = new VertexId[std::max<long long>(ne, 1)];
+  if (!read_all(prefix + ".vertex.bin", vertices_, (size_t)nv + 1) ||
+      !read_all(prefix + ".edge.bin", edges_, (size_t)ne)) {
+    std::cerr << "Failed to open file: " << prefix << ".{vertex,edge}.bin\n";
+    return kLoadNoFile;
+  }
+  finish(symmetrize, need_reverse, verbose);
+  return kLoadOk;
+}
+
+int Graph::load(const std::string &prefix, const std::string &filetype, bool symmetrize,
+                bool need_reverse, bool verbose) {
+  release();
+  int rc;
+  if (filetype == "mtx") rc = load_mtx(prefix + ".mtx", symmetrize, need_reverse, verbose);
+  else if (filetype == "bin") rc = load_bin(prefix, symmetrize, need_reverse, verbose);
+  else return kLoadBadType;
+  if (rc != kLoadOk) return rc;
+  // csr_graph.h:248
+  if (max_degree_ == 0 || max_degree_ >= n_vertices_) return kLoadDegenerate;
+  return kLoadOk;
+}
+
+Graph::Graph(std::string prefix, std::string filetype, bool symmetrize, bool need_reverse) {
+  int rc = load(prefix, filetype, symmetrize, need_reverse, true);
+  if (rc == kLoadNoFile) { std::cout << "File not available\n"; exit(1); }
+  if (rc != kLoadOk) exit(1);
+}
+
+void Graph::adopt_symmetric(VertexId m, uint64_t nnz, uint64_t *rowptr, VertexId *col, VertexId max_degree) {
+  release();
+  n_vertices_ = m; n_edges_ = nnz; vertices_ = rowptr; edges_ = col; max_degree_ = max_degree;
+  reverse_vertices_ = vertices_; reverse_edges_ = edges_;
+  directed_ = false; has_reverse_ = true;
+}
+
+void Graph::adopt_directed(VertexId m, uint64_t nnz, uint64_t *rowptr, VertexId *col,
+                           uint64_t *t_rowptr, VertexId *t_col, VertexId max_degree) {
+  release();
+  n_vertices_ = m; n_edges_ = nnz; vertices_ = rowptr; edges_ = col; max_degree_ = max_degree;
+  reverse_vertices_ = t_rowptr; reverse_edges_ = t_col;
+  directed_ = true; has_reverse_ = true;
+}
+
+int Graph::write_bin(const std::string &prefix) const {
+  FILE *f = fopen((prefix + ".meta.txt").c_str(), "w");
+  if (!f) return -1;
+  fprintf(f, "%d\n%llu\n%d\n%d\n", n_vertices_, (unsigned long long)n_edges_, (int)sizeof(VertexId), max_degree_);
+  fclose(f);
+  f = fopen((prefix + ".vertex.bin").c_str(), "wb");
+  if (!f) return -1;
+  fwrite(vertices_, sizeof(uint64_t), (size_t)n_vertices_ + 1, f);
+  fclose(f);
+  f = fopen((prefix + ".edge.bin").c_str(), "wb");
+  if (!f) return -1;
+  fwrite(edges_, sizeof(VertexId), n_edges_, f);
+  fclose(f);
+  return 0;
+}
+
+}  // namespace gdn

@@ -1,0 +1,46 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built():
+    """Build libgdn_b200.so + the oracle if they are not there yet (CPU-only work)."""
+    import __graft_entry__ as ge
+    lib = os.path.join(ROOT, "gardenia_b200", "lib", "libgdn_b200.so")
+    orc = os.path.join(ROOT, "oracle", "liboracle.so")
+    if not (os.path.exists(lib) and os.path.exists(orc)):
+        ge.build()
+
+
+GOLDEN_CASES = ["test_pr_dir", "4_sym", "4_dir", "chesapeake_sym", "kron10k16", "urand10k16", "kron12k8"]
+
+
+def load_case(name):
+    csr = dict(np.load(os.path.join(GOLDEN, name + ".csr.npz")))
+    ref = dict(np.load(os.path.join(GOLDEN, name + ".ref.npz")))
+    if "in_rowptr" not in csr:          # symmetrized: reverse aliases forward (csr_graph.h:241-246)
+        csr["in_rowptr"], csr["in_colidx"] = csr["out_rowptr"], csr["out_colidx"]
+        csr["symmetric"] = True
+    else:
+        csr["symmetric"] = False
+    csr["m"] = len(csr["out_rowptr"]) - 1
+    csr["nnz"] = int(csr["out_rowptr"][-1])
+    return csr, ref
+
+
+@pytest.fixture(params=GOLDEN_CASES)
+def case(request):
+    csr, ref = load_case(request.param)
+    return request.param, csr, ref
