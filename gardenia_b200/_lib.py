@@ -39,7 +39,7 @@ class BfsStep(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("iterations", C.c_int32), ("n_steps", C.c_int32),
                 ("solve_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
-                ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+                ("kernel_launches", C.c_int64), ("kernel_ms", C.c_double), ("kernel_calls", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
                 ("edges_reached", C.c_int64), ("vertices_reached", C.c_int64),
                 ("pr_err", C.c_double * GDN_MAX_PR_ITER),
                 ("steps", BfsStep * GDN_MAX_BFS_STEPS)]
@@ -91,6 +91,8 @@ SIGNATURES = {
     "gdn_memcpy_h2d": (C.c_int, [_vp, _vp, C.c_size_t]),
     "gdn_memcpy_d2h": (C.c_int, [_vp, _vp, C.c_size_t]),
     "gdn_device_sync": (C.c_int, []),
+    "gdn_host_pin": (C.c_int, [_vp, C.c_size_t]),
+    "gdn_host_unpin": (C.c_int, [_vp]),
     "gdn_partition_rows": (C.c_int, [_i64, C.c_int, _vp]),
     "gdn_comm_unique_id": (C.c_int, [_vp]),
     "gdn_comm_init": (C.c_int, [C.c_int, C.c_int, _vp]),

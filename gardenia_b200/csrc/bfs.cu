@@ -339,6 +339,7 @@ static int bfs_t(gdn_graph *g, int32_t source, int32_t *d_depth, int32_t *d_pare
   };
   const int sweep_grid = (int)std::max<int64_t>(1, std::min<int64_t>((g->n_words / 32 + 7) / 8, (int64_t)sm * 8));
 
+  kev_reset();
   GDN_CUDA(cudaEventRecord(lib().ev0, s));
   while (n_in > 0) {                                              // omp_beamer.cc:135
     if (scout_count > edges_to_check / kAlpha) {                  // :136
@@ -350,8 +351,10 @@ static int bfs_t(gdn_graph *g, int32_t source, int32_t *d_depth, int32_t *d_pare
         ++iter;
         old_awake = awake;
         GDN_CUDA(cudaMemsetAsync(cnt, 0, sizeof(BfsCounters), s));
+        kev_begin();
         bu_sweep<OffT><<<sweep_grid, 256, 0, s>>>(irp, ci.col, orp, front, next, g->visited, d_depth, d_parent,
                                                   g->n_words, level + 1, cnt);
+        kev_end();
         launches++;
         GDN_CUDA(cudaMemcpyAsync(h, cnt, sizeof(BfsCounters), cudaMemcpyDeviceToHost, s));
         GDN_CUDA(cudaStreamSynchronize(s));
@@ -399,6 +402,7 @@ static int bfs_t(gdn_graph *g, int32_t source, int32_t *d_depth, int32_t *d_pare
     st->kernel_launches = launches;
     st->edges_reached = reached_deg;
     st->vertices_reached = reached;
+    kev_collect(st);
   }
   return GDN_OK;
 }

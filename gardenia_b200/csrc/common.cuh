@@ -19,7 +19,24 @@ struct Lib {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   void *pinned = nullptr;          // small pinned mailbox for per-step counters
   size_t pinned_bytes = 0;
+  // event pairs bracketing each launch of the dominant kernel of a solve
+  static constexpr int kMaxKev = 512;
+  cudaEvent_t kev[2 * kMaxKev] = {};
+  int n_kev = 0;
 };
+Lib &lib();
+// usage: kev_begin(); kernel<<<>>>; kev_end();  ...  after the final sync: kev_collect(st)
+inline void kev_reset() { lib().n_kev = 0; }
+inline void kev_begin() { Lib &l = lib(); if (l.n_kev < Lib::kMaxKev) cudaEventRecord(l.kev[2 * l.n_kev], l.stream); }
+inline void kev_end() { Lib &l = lib(); if (l.n_kev < Lib::kMaxKev) { cudaEventRecord(l.kev[2 * l.n_kev + 1], l.stream); l.n_kev++; } }
+inline void kev_collect(gdn_stats *st) {
+  if (!st) return;
+  Lib &l = lib();
+  double tot = 0;
+  for (int i = 0; i < l.n_kev; i++) { float ms = 0; if (cudaEventElapsedTime(&ms, l.kev[2 * i], l.kev[2 * i + 1]) == cudaSuccess) tot += ms; }
+  st->kernel_ms = tot;
+  st->kernel_calls = l.n_kev;
+}
 Lib &lib();
 int ensure_init();
 

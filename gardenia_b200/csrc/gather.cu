@@ -333,8 +333,11 @@ static int spmv_t(gdn_graph *g, const float *d_Ax, const float *d_x, float *d_y,
   a.Ax = d_Ax; a.vec = d_x; a.y = d_y;
   cudaStream_t s = lib().stream;
   const OffT *rp = (const OffT *)c.rowptr;
+  kev_reset();
   GDN_CUDA(cudaEventRecord(lib().ev0, s));
+  kev_begin();
   gather_kernel<OffT, kModeSpmv><<<gather_grid(c), kThreads, 0, s>>>(rp, c.col, a);
+  kev_end();
   int launches = 1;
   if (c.n_heavy_rows > 0) {
     finalize_heavy<OffT, kModeSpmv><<<heavy_grid(c), kThreads, 0, s>>>(rp, a);
@@ -347,6 +350,7 @@ static int spmv_t(gdn_graph *g, const float *d_Ax, const float *d_x, float *d_y,
     float ms = 0;
     GDN_CUDA(cudaEventElapsedTime(&ms, lib().ev0, lib().ev1));
     st->solve_ms = ms; st->kernel_launches = launches; st->iterations = 1;
+    kev_collect(st);
   }
   return GDN_OK;
 }
@@ -389,6 +393,7 @@ static int pr_t(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
   double *h_err = (double *)lib().pinned;
   int64_t launches = 0;
 
+  kev_reset();
   GDN_CUDA(cudaEventRecord(lib().ev0, s));
   GDN_CUDA(cudaMemsetAsync(g->pr_done, 0, sizeof(int32_t), s));
   const int igrid = (int)std::min<int64_t>((c.rows + 255) / 256 + 1, (int64_t)lib().sm_count * 8);
@@ -400,7 +405,9 @@ static int pr_t(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
     a.vec = g->contrib[cur];
     a.contrib_out = g->contrib[cur ^ 1];
     a.err_slot0 = 0;
+    kev_begin();
     gather_kernel<OffT, kModePr><<<ggrid, kThreads, 0, s>>>(rp, c.col, a);
+    kev_end();
     launches++;
     if (c.n_heavy_rows > 0) {
       a.err_slot0 = ggrid * kWarps;
@@ -426,6 +433,7 @@ static int pr_t(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
     st->solve_ms = ms;
     st->kernel_launches = launches;
     st->iterations = iter + 1;                               // printf("iterations = %d", iter+1), :38
+    kev_collect(st);
   }
   return GDN_OK;
 }

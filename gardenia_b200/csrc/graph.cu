@@ -197,6 +197,7 @@ int gdn_init(int device) {
   GDN_CUDA(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
   GDN_CUDA(cudaEventCreate(&l.ev0));
   GDN_CUDA(cudaEventCreate(&l.ev1));
+  for (int i = 0; i < 2 * Lib::kMaxKev; i++) GDN_CUDA(cudaEventCreate(&l.kev[i]));
   l.pinned_bytes = 4096;
   GDN_CUDA(cudaHostAlloc(&l.pinned, l.pinned_bytes, cudaHostAllocDefault));
   l.inited = true;
@@ -210,6 +211,7 @@ int gdn_finalize(void) {
   cudaStreamDestroy(l.stream);
   cudaEventDestroy(l.ev0);
   cudaEventDestroy(l.ev1);
+  for (int i = 0; i < 2 * Lib::kMaxKev; i++) cudaEventDestroy(l.kev[i]);
   cudaFreeHost(l.pinned);
   l = Lib();
   return GDN_OK;
@@ -296,6 +298,15 @@ int gdn_memcpy_d2h(void *h, const void *d, size_t bytes) {
   GDN_CHECK(ensure_init());
   GDN_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, lib().stream));
   GDN_CUDA(cudaStreamSynchronize(lib().stream));
+  return GDN_OK;
+}
+int gdn_host_pin(void *h_ptr, size_t bytes) {
+  GDN_CHECK(ensure_init());
+  GDN_CUDA(cudaHostRegister(h_ptr, bytes, cudaHostRegisterDefault));
+  return GDN_OK;
+}
+int gdn_host_unpin(void *h_ptr) {
+  GDN_CUDA(cudaHostUnregister(h_ptr));
   return GDN_OK;
 }
 int gdn_device_sync(void) {

@@ -67,6 +67,9 @@ typedef struct {
   double h2d_ms;            /* one-shot entry points: upload (+ preprocessing) wall time */
   double d2h_ms;            /* one-shot entry points: result download */
   int64_t kernel_launches;  /* kernels of ours launched inside the solve region */
+  double kernel_ms;         /* CUDA-event time summed over the launches of the DOMINANT kernel of the solve
+                               (PR/SpMV: gather_kernel; BFS: bu_sweep), measured on the library stream */
+  int64_t kernel_calls;     /* number of launches kernel_ms covers */
   int64_t h2d_bytes, d2h_bytes;
   int64_t edges_reached;    /* BFS: sum of out-degree over reached vertices (directed entries) */
   int64_t vertices_reached; /* BFS */
@@ -151,6 +154,10 @@ int gdn_dev_free(void *d_ptr);
 int gdn_memcpy_h2d(void *d_dst, const void *h_src, size_t bytes);
 int gdn_memcpy_d2h(void *h_dst, const void *d_src, size_t bytes);
 int gdn_device_sync(void);
+/* Page-lock / unlock a caller-owned host range so that the one-shot entry points
+ * copy at full PCIe rate (cudaHostRegister). */
+int gdn_host_pin(void *h_ptr, size_t bytes);
+int gdn_host_unpin(void *h_ptr);
 
 /* ---- 1-D row partition across the GPUs of one box -------------
  * Host-only: splits [0,m) into nparts contiguous, 64-aligned, equal-width
