@@ -210,7 +210,8 @@ def main():
             uid = torch.from_numpy(buf)
         uid = uid.to(dev)
         dist.broadcast(uid, 0)
-        _lib.check(_lib.lib.gdn_comm_init(rank, world, uid.cpu().numpy().ctypes.data))
+        uid_host = np.ascontiguousarray(uid.cpu().numpy())       # keep alive across the C call
+        _lib.check(_lib.lib.gdn_comm_init(rank, world, uid_host.ctypes.data))
 
     def barrier():
         if world > 1:

@@ -31,6 +31,10 @@ struct Nccl {
   int (*CommDestroy)(ncclComm_t) = nullptr;
   int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
   ncclComm_t comm = nullptr;
   int rank = 0, size = 1;
@@ -56,6 +60,10 @@ static int load_nccl() {
   SYM(AllGather, "ncclAllGather")
   SYM(AllReduce, "ncclAllReduce")
   SYM(GetErrorString, "ncclGetErrorString")
+  SYM(Send, "ncclSend")
+  SYM(Recv, "ncclRecv")
+  SYM(GroupStart, "ncclGroupStart")
+  SYM(GroupEnd, "ncclGroupEnd")
 #undef SYM
   return GDN_OK;
 }
@@ -72,10 +80,11 @@ static int load_nccl() {
 int comm_size() { return nccl().size; }
 int comm_rank() { return nccl().rank; }
 
-// Equal-width 64-aligned ranges: width = ceil(m / nparts) rounded up to 64.
+// Equal-width ranges: width = ceil(m / nparts) rounded up to 1024 vertices, so that
+// every slice is a whole number of 32-word bitmap groups (and of 64-bit host words).
 int64_t partition_width(int64_t m, int nparts) {
   int64_t w = (m + nparts - 1) / nparts;
-  return (w + 63) / 64 * 64;
+  return (w + 1023) / 1024 * 1024;
 }
 
 // In-place allgather of this rank's slice of a full-length fp32 vector, plus an
@@ -97,6 +106,45 @@ int bitmap_exchange(gdn_graph *g, uint32_t *bm, long long *counters, int n_count
   const int64_t ww = partition_width(g->m, n.size) / 32;
   if (bm) GDN_NCCL(n.AllGather(bm + (int64_t)n.rank * ww, bm, (size_t)ww, ncclUint32, n.comm, lib().stream));
   if (counters) GDN_NCCL(n.AllReduce(counters, counters, (size_t)n_counters, ncclInt64, ncclSum, n.comm, lib().stream));
+  return GDN_OK;
+}
+
+// own[i] |= OR over the other ranks' copies of this rank's slice
+__global__ void or_merge(uint32_t *__restrict__ own, const uint32_t *__restrict__ xbuf, int64_t ww, int P, int R) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ww; i += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t v = own[i];
+    for (int p = 0; p < P; p++)
+      if (p != R) v |= xbuf[(int64_t)p * ww + i];
+    own[i] = v;
+  }
+}
+
+// Top-down exchange: every rank holds a full-length "discovered" bitmap.  Slice p
+// is sent to rank p (grouped send/recv over NVLink), the owner ORs the P copies,
+// and one allgather republishes the merged slices.  m/8 bytes out, m/8 bytes in.
+int bfs_merge_or(gdn_graph *g, uint32_t *bm, uint32_t *xbuf) {
+  Nccl &n = nccl();
+  if (n.size == 1) return GDN_OK;
+  const int64_t ww = partition_width(g->m, n.size) / 32;
+  GDN_NCCL(n.GroupStart());
+  for (int p = 0; p < n.size; p++) {
+    if (p == n.rank) continue;
+    GDN_NCCL(n.Send(bm + (int64_t)p * ww, (size_t)ww, ncclUint32, p, n.comm, lib().stream));
+    GDN_NCCL(n.Recv(xbuf + (int64_t)p * ww, (size_t)ww, ncclUint32, p, n.comm, lib().stream));
+  }
+  GDN_NCCL(n.GroupEnd());
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((ww + 255) / 256, (int64_t)lib().sm_count * 4));
+  or_merge<<<grid, 256, 0, lib().stream>>>(bm + (int64_t)n.rank * ww, xbuf, ww, n.size, n.rank);
+  GDN_NCCL(n.AllGather(bm + (int64_t)n.rank * ww, bm, (size_t)ww, ncclUint32, n.comm, lib().stream));
+  return GDN_OK;
+}
+
+int bfs_allgather_words(gdn_graph *g, uint32_t *bm) { return bitmap_exchange(g, bm, nullptr, 0); }
+
+int allreduce_i64(long long *d_p, int cnt) {
+  Nccl &n = nccl();
+  if (n.size == 1) return GDN_OK;
+  GDN_NCCL(n.AllReduce(d_p, d_p, (size_t)cnt, ncclInt64, ncclSum, n.comm, lib().stream));
   return GDN_OK;
 }
 

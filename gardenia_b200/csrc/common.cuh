@@ -97,8 +97,10 @@ struct gdn_graph {
   uint32_t *visited = nullptr, *front = nullptr, *next = nullptr;
   int32_t *queue[2] = {nullptr, nullptr};
   int32_t *heavy_queue = nullptr;
+  uint32_t *xbuf = nullptr;          // partitioned BFS: receive buffer of the OR-merge (P bitmap slices)
   void *counters = nullptr;          // BfsCounters on device
   int64_t n_words = 0;               // bitmap words (32-bit), padded to a multiple of 32
+  int64_t bm_alloc_words = 0;        // allocated words per bitmap (>= n_words; room for the allgather slices)
 };
 
 namespace gdn {

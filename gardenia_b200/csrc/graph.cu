@@ -247,7 +247,7 @@ int gdn_graph_destroy(gdn_graph *g) {
   cudaFree(g->contrib[0]); cudaFree(g->contrib[1]); cudaFree(g->out_degree); cudaFree(g->err_partial);
   cudaFree(g->err_trace); cudaFree(g->pr_done);
   cudaFree(g->visited); cudaFree(g->front); cudaFree(g->next); cudaFree(g->queue[0]); cudaFree(g->queue[1]);
-  cudaFree(g->heavy_queue); cudaFree(g->counters);
+  cudaFree(g->heavy_queue); cudaFree(g->counters); cudaFree(g->xbuf);
   cudaGetLastError();
   delete g;
   return GDN_OK;

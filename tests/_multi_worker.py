@@ -1,0 +1,72 @@
+"""Worker for tests/test_gpu_multi.py: one process per GPU (torchrun), 1-D row
+partition, NCCL exchange inside libgdn_b200; rank 0 checks against the oracle."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import gardenia_b200 as gb  # noqa: E402
+from gardenia_b200 import _lib  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    _lib.check(_lib.lib.gdn_init(local))
+    uid = np.zeros(128, dtype=np.uint8)
+    if rank == 0:
+        _lib.check(_lib.lib.gdn_comm_unique_id(uid.ctypes.data))
+    t = torch.from_numpy(uid).to(dev)
+    dist.broadcast(t, 0)
+    uid = t.cpu().numpy()
+    _lib.check(_lib.lib.gdn_comm_init(rank, world, uid.ctypes.data))
+    ok = True
+    for kind, scale in (("g", 16), ("u", 15)):
+        g = gb.Graph.generate(kind, scale, 16)
+        m = g.m
+        b = gb.partition_rows(m, world)
+        lo, hi = int(b[rank]), int(b[rank + 1])
+        w = int(b[1])
+        dg = gb.DeviceGraph(g, lo, hi, device=local)
+        # ---- PageRank
+        scores = torch.full((hi - lo,), float(np.float32(1.0) / np.float32(m)), dtype=torch.float32, device=dev)
+        st = dg.pagerank(scores)
+        full = torch.zeros(w * world, dtype=torch.float32, device=dev)
+        full[lo:hi] = scores
+        dist.all_gather_into_tensor(full, full[rank * w:(rank + 1) * w].clone())
+        # ---- BFS
+        srcs = [int(s) for s in g.pick_sources(3)] + [0]
+        depths = []
+        for s in srcs:
+            depth = torch.empty(m, dtype=torch.int32, device=dev)
+            stb = dg.bfs(s, depth)
+            depths.append((depth.cpu().numpy(), stb.iterations))
+        if rank == 0:
+            from oracle import pyoracle as po
+            rp, ci = g.out_rowptr(), g.out_colidx()
+            oscores, oit, _ = po.pr_pull(m, rp, ci, g.out_degrees())
+            l1 = float(np.abs(full[:m].cpu().numpy().astype(np.float64) - oscores.astype(np.float64)).sum())
+            good = (st.iterations == oit) and l1 <= 1e-6
+            print(f"[multi] {kind}{scale} world={world} PR iters {st.iterations} vs {oit} l1={l1:.3e} {'OK' if good else 'FAIL'}", flush=True)
+            ok &= good
+            for s, (d, it) in zip(srcs, depths):
+                od, oit, _ = po.bfs_do(m, rp, ci, rp, ci, s)
+                good = np.array_equal(d, od) and it == oit
+                print(f"[multi] {kind}{scale} BFS src {s}: iters {it} vs {oit} {'OK' if good else 'FAIL'}", flush=True)
+                ok &= good
+        dg.close()
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.broadcast(flag, 0)
+    _lib.lib.gdn_comm_destroy()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

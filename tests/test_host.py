@@ -1,0 +1,153 @@
+"""Host-side logic and the C-ABI surface, CPU only: readers and generator against
+CSRs produced by the reference's own code (tests/golden/*.csr.npz), the library
+exporting every symbol include/gdn_b200.h declares, and loud failure without a GPU."""
+import ctypes as C
+import hashlib
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import gardenia_b200 as gb
+from gardenia_b200 import _lib
+from conftest import GOLDEN, ROOT, load_case
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_header_symbols_exported():
+    hdr = open(os.path.join(ROOT, "include", "gdn_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(gdn_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 40
+    for name in sorted(declared):
+        assert hasattr(_lib.lib, name), f"{name} declared in gdn_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+
+
+def test_stats_struct_layout_matches_header():
+    # sizeof(gdn_stats): 2*4 + 3*8 + 8 + 8 + 8 + 4*8 + 128*8 + 256*32
+    assert C.sizeof(_lib.Stats) == 8 + 24 + 24 + 32 + 128 * 8 + 256 * 32
+    assert C.sizeof(_lib.BfsStep) == 32
+
+
+@pytest.mark.skipif(_lib.lib.gdn_device_count() > 0, reason="a GPU is present")
+def test_no_gpu_fails_loudly():
+    assert _lib.lib.gdn_init(0) == _lib.GDN_ERR_NO_DEVICE
+    assert "no CPU fallback" in _lib.last_error()
+    g = gb.Graph(os.path.join(GOLDEN, "test_pr"), "mtx", False, True)
+    scores = np.full(g.m, 0.25, dtype=np.float32)
+    with pytest.raises(gb.GdnError) as e:
+        gb.PRSolver(g, scores, verbose=False)
+    assert e.value.code == _lib.GDN_ERR_NO_DEVICE
+    assert np.all(scores == 0.25), "a failed call must not touch the caller's buffer"
+    dist = np.full(g.m, gb.MYINFINITY, dtype=np.int32)
+    with pytest.raises(gb.GdnError):
+        gb.BFSSolver(g, 0, dist, verbose=False)
+
+
+@pytest.mark.parametrize("name,stem,sym,rev", [("test_pr_dir", "test_pr", 0, 1), ("4_sym", "4", 1, 0),
+                                               ("4_dir", "4", 0, 1), ("chesapeake_sym", "chesapeake", 1, 0)])
+def test_mtx_reader_matches_reference(name, stem, sym, rev):
+    csr, _ = load_case(name)
+    g = gb.Graph(os.path.join(GOLDEN, stem), "mtx", bool(sym), bool(rev))
+    assert g.m == csr["m"] and g.nnz == csr["nnz"]
+    assert np.array_equal(g.out_rowptr(), csr["out_rowptr"]) and np.array_equal(g.out_colidx(), csr["out_colidx"])
+    assert g.has_reverse_graph()
+    assert np.array_equal(g.in_rowptr(), csr["in_rowptr"]) and np.array_equal(g.in_colidx(), csr["in_colidx"])
+    assert g.symmetric == bool(sym)
+
+
+def test_no_reverse_graph_is_refused():
+    g = gb.Graph(os.path.join(GOLDEN, "4"), "mtx", False, False)
+    assert not g.has_reverse_graph()
+    with pytest.raises(gb.GdnError):            # src/bfs/omp_beamer.cc:98-102
+        gb.BFSSolver(g, 0, np.zeros(g.m, np.int32), verbose=False)
+
+
+def test_reader_errors():
+    h = C.c_void_p()
+    assert _lib.lib.gdn_read_graph(b"/nonexistent/x", b"mtx", 0, 0, C.byref(h)) == _lib.GDN_ERR_IO
+    assert _lib.lib.gdn_read_graph(b"/nonexistent/x", b"foo", 0, 0, C.byref(h)) == _lib.GDN_ERR_ARG
+    # degenerate graph: max_degree == 0 -> the reference exit(1)s (csr_graph.h:248); we return an error
+    p = os.path.join(GOLDEN, "..", "_tmp_empty")
+    open(p + ".mtx", "w").write("%%MatrixMarket matrix coordinate pattern general\n3 3 1\n2 2\n")
+    try:
+        assert _lib.lib.gdn_read_graph(p.encode(), b"mtx", 0, 0, C.byref(h)) == _lib.GDN_ERR_GRAPH
+    finally:
+        os.remove(p + ".mtx")
+
+
+def test_bin_roundtrip(tmp_path):
+    g = gb.Graph.generate("u", 10, 16)
+    g.write_bin(str(tmp_path / "u10"))
+    meta = open(tmp_path / "u10.meta.txt").read().split()
+    assert [int(x) for x in meta[:3]] == [g.m, g.nnz, 4]       # csr_graph.h:222-226
+    g2 = gb.Graph(str(tmp_path / "u10"), "bin", True, False)
+    assert np.array_equal(g2.out_rowptr(), g.out_rowptr()) and np.array_equal(g2.out_colidx(), g.out_colidx())
+    assert g2.symmetric and g2.has_reverse_graph()
+
+
+def test_gen1_readers_three_encodings():
+    """datasets/4.{mtx,gr} encode the same graph; .graph lists each edge once."""
+    a = gb.Graph.from_file(os.path.join(GOLDEN, "4.mtx"), symmetrize=True)
+    b = gb.Graph.from_file(os.path.join(GOLDEN, "4.gr"), symmetrize=True)     # 0-based ids, tolerated
+    csr, _ = load_case("4_sym")
+    for g in (a, b):
+        assert g.m == 14 and g.nnz == 106
+        assert np.array_equal(g.out_rowptr(), csr["out_rowptr"]) and np.array_equal(g.out_colidx(), csr["out_colidx"])
+    c = gb.Graph.from_file(os.path.join(GOLDEN, "4.graph"))
+    assert c.m == 14 and c.nnz == 53                                          # datasets/4.graph:1
+    d = gb.Graph.from_file(os.path.join(GOLDEN, "4w.mtx"), symmetrize=False)
+    assert d.weights is not None and d.weights.min() >= 1
+
+
+@pytest.mark.parametrize("kind,scale,k,name", [("g", 10, 16, "kron10k16"), ("u", 10, 16, "urand10k16"), ("g", 12, 8, "kron12k8")])
+def test_generator_matches_reference(kind, scale, k, name):
+    csr, _ = load_case(name)
+    g = gb.Graph.generate(kind, scale, k)
+    assert g.m == csr["m"] and g.nnz == csr["nnz"]
+    assert np.array_equal(g.out_rowptr(), csr["out_rowptr"]) and np.array_equal(g.out_colidx(), csr["out_colidx"])
+    assert g.symmetric
+
+
+def test_generator_kats_scale16():
+    """Checksums of the reference generator and hashes recorded by tools/make_golden.py."""
+    big = json.load(open(os.path.join(GOLDEN, "big_hashes.json")))
+    for kind, E, S, d0 in [("g", 909645, 59541140593, 28), ("u", 1048321, 68658945621, 31)]:
+        g = gb.Graph.generate(kind, 16, 16)
+        assert g.m == 65536 and g.nnz == 2 * E
+        assert int(g.out_colidx().astype(np.int64).sum()) == S
+        assert g.get_degree(0) == d0
+        h = big[f"{kind}16"]
+        assert _sha(g.out_rowptr()) == h["rowptr_sha256"] and _sha(g.out_colidx()) == h["colidx_sha256"]
+
+
+def test_generator_thread_count_independent():
+    import subprocess, sys
+    code = ("import sys; sys.path.insert(0, %r); import gardenia_b200 as gb, hashlib, numpy as np;"
+            "g = gb.Graph.generate('g', 14, 16); print(hashlib.sha256(g.out_colidx().tobytes()).hexdigest())") % ROOT
+    outs = set()
+    for t in ("1", "3", "8"):
+        env = dict(os.environ, OMP_NUM_THREADS=t)
+        outs.add(subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout.strip())
+    assert len(outs) == 1
+
+
+def test_fill_uniform_stream():
+    a = gb.fill_uniform(13, 1000)
+    assert a.dtype == np.float32 and 0.0 <= a.min() and a.max() < 1.0
+    # first draw of mt19937(13) is 3340206418 -> >> 8 -> * 2^-24
+    assert a[0] == np.float32((3340206418 >> 8) / 16777216.0)
+    assert np.array_equal(gb.fill_uniform(13, 1500)[:1000], a)
+
+
+def test_pick_sources_skip_isolated():
+    g = gb.Graph.generate("g", 12, 16)
+    s = g.pick_sources(16)
+    deg = g.out_degrees()
+    assert np.all(deg[s] > 0) and np.array_equal(s, g.pick_sources(16))
