@@ -98,6 +98,18 @@ int pr_exchange(gdn_graph *g, float *vec, double *err_slot) {
   return GDN_OK;
 }
 
+// Degree-sorted id space (pull.cu): each rank owns a hot slice [R*Hp, +Hp) and a cold
+// slice [H + R*Wc, +Wc) of contrib -> two in-place allgathers + allreduce of the delta.
+int pull_exchange(gdn_graph *g, float *vec, double *err_slot) {
+  Nccl &n = nccl();
+  if (n.size == 1) return GDN_OK;
+  const PullLayout &L = g->pull;
+  if (L.Hp > 0) GDN_NCCL(n.AllGather(vec + (int64_t)n.rank * L.Hp, vec, (size_t)L.Hp, ncclFloat32, n.comm, lib().stream));
+  if (L.Wc > 0) GDN_NCCL(n.AllGather(vec + L.H + (int64_t)n.rank * L.Wc, vec + L.H, (size_t)L.Wc, ncclFloat32, n.comm, lib().stream));
+  if (err_slot) GDN_NCCL(n.AllReduce(err_slot, err_slot, 1, ncclFloat64, ncclSum, n.comm, lib().stream));
+  return GDN_OK;
+}
+
 // In-place allgather of this rank's slice of a packed bitmap (32-bit words) and
 // allreduce(sum) of n 64-bit counters.
 int bitmap_exchange(gdn_graph *g, uint32_t *bm, long long *counters, int n_counters) {

@@ -77,6 +77,30 @@ struct DevCsr {
   float *heavy_partial = nullptr;  // float[n_heavy_segs]
 };
 
+// Degree-sorted SELL-32 layout of the pull (in-) CSR used by PageRank (pull.cu).
+struct PullLayout {
+  bool prepared = false;       // host part done (orders, ids, slice pointers, work items)
+  bool symmetric_order = true; // row order == column order (row new-ids are two contiguous runs)
+  int P = 1, R = 0;            // communicator size / rank the ids were laid out for
+  int64_t W = 0, H = 0, Hp = 0, Wc = 0, Mp = 0;   // slice width, hot ids (total / per rank), cold width, id space
+  int64_t rows = 0, n_nz_rows = 0;
+  int32_t n_slices = 0;
+  uint64_t n_groups = 0;       // int4 groups in the SELL array
+  int32_t *perm = nullptr;     // [rows]  sorted position -> old local row
+  int32_t *newid = nullptr;    // [m]     old global id -> new global id
+  int32_t *sdeg = nullptr;     // [rows]  length of sorted row j
+  int32_t *sout = nullptr;     // [rows]  out-degree of sorted row j (directed graphs)
+  int32_t *rowid = nullptr;    // [rows]  new global id of sorted row j (only when !symmetric_order)
+  uint32_t *slice_ptr = nullptr;   // [n_slices+1] in int4 groups
+  int4 *sell = nullptr;            // [n_groups]   built lazily on the first PageRank call
+  int32_t n_chunks = 0;
+  int32_t *chunk_slice = nullptr;  // [n_chunks+1]
+  int32_t n_heavy_slices = 0, n_heavy_segs = 0, n_fill_wide = 0;
+  int32_t *heavy_slice = nullptr, *heavy_first = nullptr;
+  int2 *heavy_seg = nullptr;
+  float *partial = nullptr;        // [n_heavy_segs * 32]
+};
+
 }  // namespace gdn
 
 struct gdn_graph {
@@ -93,6 +117,8 @@ struct gdn_graph {
   double *err_trace = nullptr;       // double[GDN_MAX_PR_ITER] on device
   int32_t *pr_done = nullptr;        // device flag: converged
   int n_err_partial = 0;
+  gdn::PullLayout pull;
+  float *scores_sorted = nullptr;    // PR scores in sorted row order during a solve
   // BFS scratch
   uint32_t *visited = nullptr, *front = nullptr, *next = nullptr;
   int32_t *queue[2] = {nullptr, nullptr};
@@ -134,6 +160,14 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
   return p;
+}
+// Streaming 128-bit load with an L2 eviction policy (see l2_policy_evict_first).
+__device__ __forceinline__ int4 ld_stream_v4(const int4 *p, uint64_t pol) {
+  int4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p), "l"(pol));
+  return r;
 }
 // Gathered vector element: read-only path, L1 allocate, L2 evict-last.
 __device__ __forceinline__ float ld_gather_f32(const float *p, uint64_t pol) {

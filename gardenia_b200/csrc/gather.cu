@@ -21,6 +21,7 @@
 //            per row by finalize_heavy in a fixed order.
 // No atomics, deterministic run to run.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace gdn {
 
@@ -438,7 +439,10 @@ static int pr_t(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
   return GDN_OK;
 }
 
+int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_iter, gdn_stats *st);   // pull.cu
+
 int pr_run(gdn_graph *g, float *d_scores, float damp, double eps, int max_iter, gdn_stats *st) {
+  if (g->pull.prepared && !getenv("GDN_PR_CSR")) return pr_run_sell(g, d_scores, damp, eps, max_iter, st);
   return g->in.off64 ? pr_t<uint64_t>(g, d_scores, damp, eps, max_iter, st)
                      : pr_t<uint32_t>(g, d_scores, damp, eps, max_iter, st);
 }

@@ -28,6 +28,8 @@ int ensure_init() {
 }
 
 int build_schedule(gdn_graph *g, DevCsr &c);
+template <typename HostOffT>
+int pull_prepare(gdn_graph *g, const HostOffT *row_off, const HostOffT *key_off);   // pull.cu
 int bfs_run(gdn_graph *g, int32_t source, int32_t *d_depth, int32_t *d_parent, gdn_stats *st);
 int pr_run(gdn_graph *g, float *d_scores, float damp, double eps, int max_iter, gdn_stats *st);
 int spmv_run(gdn_graph *g, const float *d_Ax, const float *d_x, float *d_y, gdn_stats *st);
@@ -153,6 +155,13 @@ static int graph_create_t(int64_t m, int64_t nnz, const HostOffT *out_rowptr, co
       }
     }
   }
+  if (rc == GDN_OK && g->has_in) {
+    // degree-sorted SELL layout for the PageRank pull (host part; the SELL array itself is built on first use)
+    const HostOffT *row_off = (g->symmetric || !in_rowptr) ? out_rowptr : in_rowptr;
+    if (!out_rowptr) row_off = in_rowptr;
+    const HostOffT *key_off = out_rowptr ? out_rowptr : row_off;
+    rc = pull_prepare<HostOffT>(g, row_off, key_off);
+  }
   if (rc != GDN_OK) { gdn_graph_destroy(g); return rc; }
   *out = g;
   return GDN_OK;
@@ -248,6 +257,12 @@ int gdn_graph_destroy(gdn_graph *g) {
   cudaFree(g->err_trace); cudaFree(g->pr_done);
   cudaFree(g->visited); cudaFree(g->front); cudaFree(g->next); cudaFree(g->queue[0]); cudaFree(g->queue[1]);
   cudaFree(g->heavy_queue); cudaFree(g->counters); cudaFree(g->xbuf);
+  {
+    gdn::PullLayout &L = g->pull;
+    cudaFree(L.perm); cudaFree(L.newid); cudaFree(L.sdeg); cudaFree(L.sout); cudaFree(L.rowid); cudaFree(L.slice_ptr);
+    cudaFree(L.sell); cudaFree(L.chunk_slice); cudaFree(L.heavy_slice); cudaFree(L.heavy_first); cudaFree(L.heavy_seg);
+    cudaFree(L.partial); cudaFree(g->scores_sorted);
+  }
   cudaGetLastError();
   delete g;
   return GDN_OK;

@@ -1,0 +1,548 @@
+// pull.cu -- PageRank pull on a degree-sorted SELL-32 layout with a shared-memory
+// hot-vertex table.
+//
+// Why (measured on this B200, profiles/r1_gather_microbench_b200.txt): a random
+// 4-byte gather sustains ~1.0 gather/clk/SM out of L2, ~3/clk/SM out of L1,
+// >=5/clk/SM out of shared memory, and only 40-74 G/s (0.15-0.25/clk/SM) once the
+// gathered vector no longer fits L2 (268 MB at Kronecker scale 26, whose ids the
+// generator permutes at random, include/generator.h:52-62).  The pull gather of
+// src/pr/omp_base.cc:27-33 is therefore bound by WHERE contrib[src] lives, not by
+// the colidx stream.  This file re-lays the problem out for the memory hierarchy
+// once per graph (untimed, like the reference's own segmenting/tiling variants,
+// include/segmenting.h) and never changes the arithmetic:
+//
+//  * vertices are renumbered by (out-)degree, hottest first (host-side stable
+//    counting sort, O(m)); the top H (<= 48 K) contrib values are kept in a
+//    192 KB shared-memory table per SM, the next few million stay L2-resident
+//    because they are now contiguous;
+//  * rows are sorted by length and stored as SELL-32 slices (32 rows per warp,
+//    lane = row, 4 column ids per lane per 128-bit coalesced load), so a lane
+//    sums ITS row in the reference's sequential fp32 order -- rows up to 128
+//    non-zeros are bit-identical to pr_omp_base -- with no staging, no
+//    divergence (rows of a slice have (nearly) equal length) and 8 independent
+//    gathers in flight per lane;
+//  * slices wider than 128 are cut into 128-column segments (one warp each) whose
+//    per-row partials are added in column order by pr_sell_finalize;
+//  * scores live in sorted order during the solve and are permuted back at the end.
+//
+// Multi-GPU: every rank sorts ITS rows; new ids are laid out as
+//   [ hot slice of rank 0 | ... | hot slice of rank P-1 | cold slice of rank 0 | ... ]
+// so the hot table is one contiguous prefix and each rank still owns two
+// contiguous slices of contrib (two in-place NCCL allgathers per iteration).
+#include "common.cuh"
+#include <omp.h>
+#include <algorithm>
+#include <vector>
+
+namespace gdn {
+
+constexpr int kHotMax = 49152;          // fp32 entries in the shared-memory table (192 KB)
+constexpr int kGroupCh = 1024;          // int4 groups per work item (= 4096 column ids)
+constexpr int kSellThreads = 1024;      // one CTA per SM
+
+int comm_size();
+int comm_rank();
+int64_t partition_width(int64_t m, int nparts);
+
+// ------------------------------------------------------------------ host: stable sort by degree, descending
+// perm[j] = index (relative to lo) of the j-th vertex of [lo,hi) in (degree desc, id asc) order.
+static void sort_by_degree(const std::vector<int32_t> &deg, int64_t lo, int64_t hi, int32_t *perm) {
+  const int64_t n = hi - lo;
+  const int DB = 4096;                   // degrees below DB: parallel counting sort; above: std::stable_sort
+  const int T = std::max(1, omp_get_max_threads());
+  std::vector<std::vector<uint32_t>> hist(T, std::vector<uint32_t>(DB, 0));
+  std::vector<std::vector<int32_t>> big(T);
+#pragma omp parallel num_threads(T)
+  {
+    const int t = omp_get_thread_num();
+    const int64_t a = n * t / T, b = n * (t + 1) / T;
+    for (int64_t i = a; i < b; i++) {
+      const int32_t d = deg[lo + i];
+      if (d >= DB) big[t].push_back((int32_t)i); else hist[t][d]++;
+    }
+  }
+  std::vector<int32_t> bigs;
+  for (int t = 0; t < T; t++) bigs.insert(bigs.end(), big[t].begin(), big[t].end());
+  std::stable_sort(bigs.begin(), bigs.end(), [&](int32_t x, int32_t y) { return deg[lo + x] > deg[lo + y]; });
+  std::copy(bigs.begin(), bigs.end(), perm);
+  // start[t][d]: descending degree, then thread order (= ascending id)
+  uint64_t pos = bigs.size();
+  std::vector<std::vector<uint64_t>> start(T, std::vector<uint64_t>(DB));
+  for (int d = DB - 1; d >= 0; d--)
+    for (int t = 0; t < T; t++) { start[t][d] = pos; pos += hist[t][d]; }
+#pragma omp parallel num_threads(T)
+  {
+    const int t = omp_get_thread_num();
+    const int64_t a = n * t / T, b = n * (t + 1) / T;
+    for (int64_t i = a; i < b; i++) {
+      const int32_t d = deg[lo + i];
+      if (d < DB) perm[start[t][d]++] = (int32_t)i;
+    }
+  }
+}
+
+template <typename T>
+static int upload(gdn_graph *g, T **dptr, const T *h, size_t n) {
+  GDN_CUDA(cudaMalloc((void **)dptr, std::max<size_t>(n, 4) * sizeof(T)));
+  g->device_bytes += n * sizeof(T);
+  GDN_CUDA(cudaMemcpyAsync(*dptr, h, n * sizeof(T), cudaMemcpyHostToDevice, lib().stream));
+  return GDN_OK;
+}
+
+// Host part of the layout: orders, new ids, slice pointers, work items.  Runs in
+// gdn_graph_create while the caller's host offsets are still valid.
+//   row_off : offsets of the PULL (in-) CSR, global, host
+//   key_off : offsets whose row lengths rank the COLUMNS by hotness (out-CSR; == row_off when symmetric)
+template <typename HostOffT>
+int pull_prepare(gdn_graph *g, const HostOffT *row_off, const HostOffT *key_off) {
+  PullLayout &L = g->pull;
+  const int P = comm_size(), R = comm_rank();
+  const int64_t m = g->m, lo = g->row_lo, hi = g->row_hi, rows = hi - lo;
+  const int64_t W = (P == 1) ? m : partition_width(m, P);
+  if (lo != std::min<int64_t>((int64_t)R * W, m) || hi != std::min<int64_t>(lo + W, m)) {
+    // a row range that is not this rank's gdn_partition_rows slice: keep the plain CSR path
+    L.prepared = false;
+    return GDN_OK;
+  }
+  L.P = P; L.R = R; L.W = W;
+  L.Hp = std::min<int64_t>(kHotMax / P, W);
+  L.H = L.Hp * P;
+  L.Wc = W - L.Hp;
+  L.Mp = L.H + L.Wc * P;
+  L.rows = rows;
+  L.symmetric_order = (key_off == row_off);
+
+  std::vector<int32_t> rdeg(m), kdeg;
+#pragma omp parallel for
+  for (int64_t v = 0; v < m; v++) rdeg[v] = (int32_t)(row_off[v + 1] - row_off[v]);
+  const std::vector<int32_t> *kd = &rdeg;
+  if (!L.symmetric_order) {
+    kdeg.resize(m);
+#pragma omp parallel for
+    for (int64_t v = 0; v < m; v++) kdeg[v] = (int32_t)(key_off[v + 1] - key_off[v]);
+    kd = &kdeg;
+  }
+  // column order -> new ids for ALL vertices (every rank's slice)
+  std::vector<int32_t> newid(m), tmp(W);
+  for (int q = 0; q < P; q++) {
+    const int64_t qlo = std::min<int64_t>((int64_t)q * W, m), qhi = std::min<int64_t>(qlo + W, m);
+    if (qhi <= qlo) continue;
+    sort_by_degree(*kd, qlo, qhi, tmp.data());
+    const int64_t n = qhi - qlo;
+#pragma omp parallel for
+    for (int64_t j = 0; j < n; j++)
+      newid[qlo + tmp[j]] = (int32_t)(j < L.Hp ? (int64_t)q * L.Hp + j : L.H + (int64_t)q * L.Wc + (j - L.Hp));
+  }
+  // row order of this rank (by row length); identical to the column order when symmetric
+  std::vector<int32_t> perm(std::max<int64_t>(rows, 1));
+  if (rows > 0) sort_by_degree(rdeg, lo, hi, perm.data());
+  std::vector<int32_t> sdeg(std::max<int64_t>(rows, 1)), rowid(std::max<int64_t>(rows, 1));
+  int64_t n_nz = 0;
+#pragma omp parallel for reduction(+ : n_nz)
+  for (int64_t j = 0; j < rows; j++) {
+    sdeg[j] = rdeg[lo + perm[j]];
+    rowid[j] = newid[lo + perm[j]];
+    n_nz += sdeg[j] > 0;
+  }
+  L.n_nz_rows = n_nz;
+  L.n_slices = (int32_t)((n_nz + 31) / 32);
+  // slice pointers in int4 groups: slice s = 32 lanes x ceil(width/4) groups, width = longest (= first) row
+  std::vector<uint32_t> sptr((size_t)L.n_slices + 1);
+  uint64_t tot = 0;
+  for (int32_t s = 0; s < L.n_slices; s++) {
+    sptr[s] = (uint32_t)tot;
+    tot += 32ull * ((sdeg[(int64_t)s * 32] + 3) / 4);
+    if (tot >= 0xffff0000ull) { set_error("pull layout: too many non-zeros for 32-bit group offsets"); return GDN_ERR_ARG; }
+  }
+  sptr[L.n_slices] = (uint32_t)tot;
+  L.n_groups = tot;
+  // work items: chunk k owns the light slices that START in [k*CH,(k+1)*CH); wide slices are cut into segments
+  L.n_chunks = (int32_t)(tot / kGroupCh + 1);
+  std::vector<int32_t> chunk((size_t)L.n_chunks + 1);
+  {
+    int32_t s = 0;
+    for (int32_t k = 0; k < L.n_chunks; k++) {
+      while (s < L.n_slices && sptr[s] < (uint64_t)k * kGroupCh) s++;
+      chunk[k] = s;
+    }
+    chunk[L.n_chunks] = L.n_slices;
+  }
+  std::vector<int32_t> hslice, hfirst;
+  std::vector<int2> hseg;
+  for (int32_t s = 0; s < L.n_slices; s++) {
+    const uint32_t sz = sptr[s + 1] - sptr[s];
+    if (sz <= (uint32_t)kGroupCh) break;                 // widths are non-increasing
+    hslice.push_back(s);
+    hfirst.push_back((int32_t)hseg.size());
+    for (uint32_t q = 0; q < (sz + kGroupCh - 1) / kGroupCh; q++) hseg.push_back(make_int2(s, (int)q));
+  }
+  hfirst.push_back((int32_t)hseg.size());
+  L.n_heavy_slices = (int32_t)hslice.size();
+  L.n_heavy_segs = (int32_t)hseg.size();
+  // wide slices for the fill kernel: the whole grid strides their column tiles
+  L.n_fill_wide = 0;
+  for (int32_t s = 0; s < L.n_slices && sdeg[(int64_t)s * 32] > 2048; s++) L.n_fill_wide++;
+
+  GDN_CHECK(upload(g, &L.perm, perm.data(), (size_t)rows));
+  GDN_CHECK(upload(g, &L.newid, newid.data(), (size_t)m));
+  GDN_CHECK(upload(g, &L.sdeg, sdeg.data(), (size_t)rows));
+  if (!L.symmetric_order) GDN_CHECK(upload(g, &L.rowid, rowid.data(), (size_t)rows));
+  GDN_CHECK(upload(g, &L.slice_ptr, sptr.data(), sptr.size()));
+  GDN_CHECK(upload(g, &L.chunk_slice, chunk.data(), chunk.size()));
+  if (L.n_heavy_slices) {
+    GDN_CHECK(upload(g, &L.heavy_slice, hslice.data(), hslice.size()));
+    GDN_CHECK(upload(g, &L.heavy_first, hfirst.data(), hfirst.size()));
+    GDN_CHECK(upload(g, &L.heavy_seg, hseg.data(), hseg.size()));
+    GDN_CUDA(cudaMalloc((void **)&L.partial, sizeof(float) * 32 * (size_t)L.n_heavy_segs));
+    g->device_bytes += sizeof(float) * 32 * (size_t)L.n_heavy_segs;
+  }
+  GDN_CUDA(cudaStreamSynchronize(lib().stream));      // host vectors die here
+  L.prepared = true;
+  return GDN_OK;
+}
+template int pull_prepare<uint64_t>(gdn_graph *, const uint64_t *, const uint64_t *);
+template int pull_prepare<int32_t>(gdn_graph *, const int32_t *, const int32_t *);
+
+// ------------------------------------------------------------------ device: fill the SELL array
+// One warp per slice; 32x32 tiles are read row-wise (coalesced along a CSR row),
+// renumbered through newid[], transposed in shared memory and written lane = row
+// (coalesced 512-byte stores).  Padding is -1.
+template <typename OffT>
+__device__ __forceinline__ void fill_tile(const int32_t *__restrict__ col, const int32_t *__restrict__ newid,
+                                          int (*tile)[33], OffT b_l, uint32_t d_l, uint32_t k0, uint32_t ngk,
+                                          int4 *__restrict__ dst, int lane) {
+  for (int rr = 0; rr < 32; rr++) {
+    const OffT b = __shfl_sync(kFull, b_l, rr);
+    const uint32_t d = __shfl_sync(kFull, d_l, rr);
+    int c = -1;
+    if (k0 + lane < d) c = newid[col[b + k0 + lane]];
+    tile[rr][lane] = c;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int gq = 0; gq < 8; gq++) {
+    const uint32_t kk = k0 / 4 + gq;
+    if (kk < ngk) dst[(size_t)kk * 32 + lane] = make_int4(tile[lane][4 * gq], tile[lane][4 * gq + 1], tile[lane][4 * gq + 2], tile[lane][4 * gq + 3]);
+  }
+  __syncwarp();
+}
+
+template <typename OffT>
+__global__ void __launch_bounds__(256, 4)
+sell_fill(const OffT *__restrict__ rowptr, const int32_t *__restrict__ col, const int32_t *__restrict__ perm,
+          const int32_t *__restrict__ newid, const uint32_t *__restrict__ slice_ptr, int32_t n_slices, int64_t n_nz_rows,
+          int32_t n_wide, int4 *__restrict__ sell) {
+  __shared__ int tiles[8][32][33];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t warp = (int64_t)blockIdx.x * 8 + wib, nwarps = (int64_t)gridDim.x * 8;
+  // wide slices: all warps of the grid share the column tiles of one slice at a time
+  for (int32_t s = 0; s < n_wide; s++) {
+    const int64_t j = (int64_t)s * 32 + lane;
+    OffT b_l = 0; uint32_t d_l = 0;
+    if (j < n_nz_rows) { const int32_t old = perm[j]; b_l = rowptr[old]; d_l = (uint32_t)(rowptr[old + 1] - b_l); }
+    const uint32_t w = __shfl_sync(kFull, d_l, 0), ngk = (w + 3) / 4;
+    for (uint64_t k0 = (uint64_t)warp * 32; k0 < w; k0 += (uint64_t)nwarps * 32)
+      fill_tile<OffT>(col, newid, tiles[wib], b_l, d_l, (uint32_t)k0, ngk, sell + slice_ptr[s], lane);
+  }
+  for (int64_t s = n_wide + warp; s < n_slices; s += nwarps) {
+    const int64_t j = s * 32 + lane;
+    OffT b_l = 0; uint32_t d_l = 0;
+    if (j < n_nz_rows) { const int32_t old = perm[j]; b_l = rowptr[old]; d_l = (uint32_t)(rowptr[old + 1] - b_l); }
+    const uint32_t w = __shfl_sync(kFull, d_l, 0), ngk = (w + 3) / 4;
+    for (uint32_t k0 = 0; k0 < w; k0 += 32)
+      fill_tile<OffT>(col, newid, tiles[wib], b_l, d_l, k0, ngk, sell + slice_ptr[s], lane);
+  }
+}
+
+int pull_build_sell(gdn_graph *g) {
+  PullLayout &L = g->pull;
+  if (L.sell || !L.prepared) return GDN_OK;
+  const DevCsr &c = g->in;
+  GDN_CUDA(cudaMalloc((void **)&L.sell, sizeof(int4) * std::max<uint64_t>(L.n_groups, 1) + 256));
+  g->device_bytes += sizeof(int4) * L.n_groups;
+  if (L.n_slices > 0) {
+    const int grid = lib().sm_count * 8;
+    if (c.off64)
+      sell_fill<uint64_t><<<grid, 256, 0, lib().stream>>>((const uint64_t *)c.rowptr, c.col, L.perm, L.newid, L.slice_ptr,
+                                                          L.n_slices, L.n_nz_rows, L.n_fill_wide, L.sell);
+    else
+      sell_fill<uint32_t><<<grid, 256, 0, lib().stream>>>((const uint32_t *)c.rowptr, c.col, L.perm, L.newid, L.slice_ptr,
+                                                          L.n_slices, L.n_nz_rows, L.n_fill_wide, L.sell);
+  }
+  GDN_CUDA(cudaStreamSynchronize(lib().stream));
+  GDN_CUDA(cudaGetLastError());
+  return GDN_OK;
+}
+
+// ------------------------------------------------------------------ device: the PageRank iteration
+struct SellArgs {
+  const int4 *sell;
+  const uint32_t *slice_ptr;
+  const int32_t *chunk_slice;
+  int32_t n_chunks;
+  const int2 *heavy_seg;
+  const int32_t *heavy_slice, *heavy_first;
+  int32_t n_heavy_segs, n_heavy_slices;
+  float *partial;
+  const float *contrib_in;     // indexed by NEW global id, length Mp
+  float *contrib_out;
+  float *scores;               // sorted local order
+  const int32_t *sdeg;         // row length of sorted row j
+  const int32_t *sout;         // out-degree of sorted row j (nullptr: = sdeg)
+  const int32_t *rowid;        // new global id of sorted row j (nullptr: formula below)
+  int64_t n_nz_rows, rows;
+  int32_t H;
+  int64_t Hp, Wc;
+  int32_t rank;
+  float base, damp;
+  double *err_partial;
+  const int32_t *done;
+  int32_t err_slot0;
+};
+
+__device__ __forceinline__ int64_t row_newid(const SellArgs &a, int64_t j) {
+  if (a.rowid) return a.rowid[j];
+  return j < a.Hp ? (int64_t)a.rank * a.Hp + j : (int64_t)a.H + (int64_t)a.rank * a.Wc + (j - a.Hp);
+}
+
+// scores[dst] = base + damp * sum; error += |new - old|; next contrib   (src/pr/omp_base.cc:24-25,31-33)
+__device__ __forceinline__ void pr_epilogue(const SellArgs &a, int64_t j, float acc, double &err) {
+  const float old_score = a.scores[j];
+  const float nw = __fadd_rn(a.base, __fmul_rn(a.damp, acc));
+  a.scores[j] = nw;
+  err += (double)fabsf(__fsub_rn(nw, old_score));
+  const int32_t deg = a.sout ? a.sout[j] : a.sdeg[j];
+  a.contrib_out[row_newid(a, j)] = __fdiv_rn(nw, (float)deg);
+}
+
+__device__ __forceinline__ float pull_one(const SellArgs &a, const float *s_hot, int c) {
+  float v = 0.f;
+  if ((unsigned)c < (unsigned)a.H) v = s_hot[c];
+  else if (c >= 0) v = __ldg(a.contrib_in + c);
+  return v;
+}
+
+// Sum groups [g0, g1) (multiples of 32 groups; lane = row) sequentially per lane.
+__device__ __forceinline__ float sell_sum(const SellArgs &a, const float *s_hot, uint32_t g0, uint32_t g1, int lane,
+                                          float acc, uint64_t pol) {
+  uint32_t g = g0 + lane;
+  for (; g + 32 < g1; g += 64) {           // two groups per trip: 8 gathers in flight per lane
+    const int4 c0 = ld_stream_v4(a.sell + g, pol);
+    const int4 c1 = ld_stream_v4(a.sell + g + 32, pol);
+    const float v0 = pull_one(a, s_hot, c0.x), v1 = pull_one(a, s_hot, c0.y), v2 = pull_one(a, s_hot, c0.z),
+                v3 = pull_one(a, s_hot, c0.w), v4 = pull_one(a, s_hot, c1.x), v5 = pull_one(a, s_hot, c1.y),
+                v6 = pull_one(a, s_hot, c1.z), v7 = pull_one(a, s_hot, c1.w);
+    acc = __fadd_rn(acc, v0); acc = __fadd_rn(acc, v1); acc = __fadd_rn(acc, v2); acc = __fadd_rn(acc, v3);
+    acc = __fadd_rn(acc, v4); acc = __fadd_rn(acc, v5); acc = __fadd_rn(acc, v6); acc = __fadd_rn(acc, v7);
+  }
+  if (g < g1) {
+    const int4 c0 = ld_stream_v4(a.sell + g, pol);
+    const float v0 = pull_one(a, s_hot, c0.x), v1 = pull_one(a, s_hot, c0.y), v2 = pull_one(a, s_hot, c0.z),
+                v3 = pull_one(a, s_hot, c0.w);
+    acc = __fadd_rn(acc, v0); acc = __fadd_rn(acc, v1); acc = __fadd_rn(acc, v2); acc = __fadd_rn(acc, v3);
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(kSellThreads, 1)
+pr_sell_kernel(SellArgs a) {
+  extern __shared__ float s_hot[];
+  if (*a.done) return;
+  for (int i = threadIdx.x; i < a.H; i += kSellThreads) s_hot[i] = a.contrib_in[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (kSellThreads / 32) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (kSellThreads / 32);
+  const int64_t n_items = (int64_t)a.n_chunks + a.n_heavy_segs;
+  const uint64_t pol = l2_policy_evict_first();
+  double err = 0.0;
+  // heavy segments first (they are the longest items), then the chunks
+  for (int64_t item = warp; item < n_items; item += nwarps) {
+    if (item < a.n_heavy_segs) {
+      const int2 hs = a.heavy_seg[item];
+      const uint32_t s0 = a.slice_ptr[hs.x], s1 = a.slice_ptr[hs.x + 1];
+      const uint32_t g0 = s0 + (uint32_t)hs.y * kGroupCh;
+      const uint32_t g1 = (s1 - g0 > (uint32_t)kGroupCh) ? g0 + kGroupCh : s1;
+      a.partial[(size_t)item * 32 + lane] = sell_sum(a, s_hot, g0, g1, lane, 0.f, pol);
+    } else {
+      const int64_t k = item - a.n_heavy_segs;
+      const int32_t sa = a.chunk_slice[k], sb = a.chunk_slice[k + 1];
+      for (int32_t s = sa; s < sb; s++) {
+        const uint32_t g0 = a.slice_ptr[s], g1 = a.slice_ptr[s + 1];
+        if (g1 - g0 > (uint32_t)kGroupCh) continue;          // wide slice: handled as segments
+        const float acc = sell_sum(a, s_hot, g0, g1, lane, 0.f, pol);
+        const int64_t j = (int64_t)s * 32 + lane;
+        if (j < a.n_nz_rows) pr_epilogue(a, j, acc, err);
+      }
+    }
+  }
+  err = warp_sum(err);
+  if (lane == 0) a.err_partial[a.err_slot0 + warp] = err;
+}
+
+// wide slices: one warp per slice adds the per-row partials of its segments in column order
+__global__ void __launch_bounds__(256, 4)
+pr_sell_finalize(SellArgs a) {
+  if (*a.done) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * 8;
+  double err = 0.0;
+  for (int64_t h = warp; h < a.n_heavy_slices; h += nwarps) {
+    const int32_t s = a.heavy_slice[h];
+    const int32_t f0 = a.heavy_first[h], f1 = a.heavy_first[h + 1];
+    float acc = 0.f;
+    for (int32_t q = f0; q < f1; q++) acc = __fadd_rn(acc, a.partial[(size_t)q * 32 + lane]);
+    const int64_t j = (int64_t)s * 32 + lane;
+    if (j < a.n_nz_rows) pr_epilogue(a, j, acc, err);
+  }
+  err = warp_sum(err);
+  if (lane == 0) a.err_partial[a.err_slot0 + warp] = err;
+}
+
+// rows without in-edges: score = base (src/pr/omp_base.cc:28-32 with an empty sum)
+__global__ void __launch_bounds__(256, 4)
+pr_sell_isolated(SellArgs a) {
+  if (*a.done) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  double err = 0.0;
+  for (int64_t j = a.n_nz_rows + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < a.rows; j += (int64_t)gridDim.x * blockDim.x)
+    pr_epilogue(a, j, 0.f, err);
+  err = warp_sum(err);
+  if (lane == 0) a.err_partial[a.err_slot0 + warp] = err;
+}
+
+__global__ void pr_sell_load(const float *__restrict__ scores_user, const int32_t *__restrict__ perm, SellArgs a) {
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < a.rows; j += (int64_t)gridDim.x * blockDim.x) {
+    const float sc = scores_user[perm[j]];
+    a.scores[j] = sc;
+    const int32_t deg = a.sout ? a.sout[j] : a.sdeg[j];
+    a.contrib_out[row_newid(a, j)] = __fdiv_rn(sc, (float)deg);      // src/pr/omp_base.cc:24-25
+  }
+}
+__global__ void pr_sell_store(float *__restrict__ scores_user, const int32_t *__restrict__ perm,
+                              const float *__restrict__ scores_sorted, int64_t rows) {
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < rows; j += (int64_t)gridDim.x * blockDim.x)
+    scores_user[perm[j]] = scores_sorted[j];
+}
+__global__ void gather_i32(const int32_t *__restrict__ src, const int32_t *__restrict__ perm, int32_t *__restrict__ dst, int64_t n) {
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) dst[j] = src[perm[j]];
+}
+
+__global__ void __launch_bounds__(256)
+pr_reduce_err2(const double *__restrict__ partial, int n, double *err_trace, int iter, double eps, int32_t *done) {
+  __shared__ double s[256];
+  if (*done) return;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) acc += partial[i];
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    err_trace[iter] = s[0];
+    if (s[0] < eps) *done = iter + 1;
+  }
+}
+
+int pull_exchange(gdn_graph *g, float *contrib, double *err_slot);   // comm.cu
+
+int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_iter, gdn_stats *st) {
+  PullLayout &L = g->pull;
+  GDN_CHECK(pull_build_sell(g));
+  cudaStream_t s = lib().stream;
+  const int sm = lib().sm_count;
+  const int wpc = kSellThreads / 32;
+  const int fgrid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)L.n_heavy_slices + 7) / 8, (int64_t)sm * 4));
+  const int igrid = (int)std::max<int64_t>(1, std::min<int64_t>((L.rows - L.n_nz_rows + 255) / 256, (int64_t)sm * 8));
+  const int n_partial = sm * wpc + fgrid * 8 + igrid * 8;
+  if (!g->contrib[0]) {
+    GDN_CUDA(cudaMalloc((void **)&g->contrib[0], sizeof(float) * (L.Mp + 64)));
+    GDN_CUDA(cudaMalloc((void **)&g->contrib[1], sizeof(float) * (L.Mp + 64)));
+    GDN_CUDA(cudaMalloc((void **)&g->scores_sorted, sizeof(float) * std::max<int64_t>(L.rows, 1)));
+    GDN_CUDA(cudaMalloc((void **)&g->err_trace, sizeof(double) * GDN_MAX_PR_ITER));
+    GDN_CUDA(cudaMalloc((void **)&g->pr_done, sizeof(int32_t)));
+    GDN_CUDA(cudaMemsetAsync(g->contrib[0], 0, sizeof(float) * (L.Mp + 64), s));
+    GDN_CUDA(cudaMemsetAsync(g->contrib[1], 0, sizeof(float) * (L.Mp + 64), s));
+    g->device_bytes += sizeof(float) * (2 * L.Mp + L.rows);
+    if (g->out_degree) {                       // directed graph: out-degree in sorted row order
+      GDN_CUDA(cudaMalloc((void **)&L.sout, sizeof(int32_t) * std::max<int64_t>(L.rows, 1)));
+      gather_i32<<<sm * 8, 256, 0, s>>>(g->out_degree, L.perm, L.sout, L.rows);
+    }
+  }
+  if (g->n_err_partial < n_partial) {
+    if (g->err_partial) GDN_CUDA(cudaFree(g->err_partial));
+    GDN_CUDA(cudaMalloc((void **)&g->err_partial, sizeof(double) * n_partial));
+    g->n_err_partial = n_partial;
+  }
+  if (max_iter > GDN_MAX_PR_ITER - 1) max_iter = GDN_MAX_PR_ITER - 1;
+  const size_t smem = sizeof(float) * (size_t)L.H;
+  GDN_CUDA(cudaFuncSetAttribute(pr_sell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+  SellArgs a = {};
+  a.sell = L.sell; a.slice_ptr = L.slice_ptr; a.chunk_slice = L.chunk_slice; a.n_chunks = L.n_chunks;
+  a.heavy_seg = L.heavy_seg; a.heavy_slice = L.heavy_slice; a.heavy_first = L.heavy_first;
+  a.n_heavy_segs = L.n_heavy_segs; a.n_heavy_slices = L.n_heavy_slices; a.partial = L.partial;
+  a.scores = g->scores_sorted; a.sdeg = L.sdeg; a.sout = L.sout; a.rowid = L.rowid;
+  a.n_nz_rows = L.n_nz_rows; a.rows = L.rows; a.H = (int32_t)L.H; a.Hp = L.Hp; a.Wc = L.Wc; a.rank = L.R;
+  a.base = (1.0f - damp) / (float)(int32_t)g->m;            // src/pr/omp_base.cc:16
+  a.damp = damp; a.err_partial = g->err_partial; a.done = g->pr_done;
+  double *h_err = (double *)lib().pinned;
+  int64_t launches = 0;
+  const bool multi = L.P > 1;
+
+  kev_reset();
+  GDN_CUDA(cudaEventRecord(lib().ev0, s));
+  GDN_CUDA(cudaMemsetAsync(g->pr_done, 0, sizeof(int32_t), s));
+  GDN_CUDA(cudaMemsetAsync(g->err_partial, 0, sizeof(double) * n_partial, s));
+  a.contrib_out = g->contrib[0];
+  pr_sell_load<<<sm * 8, 256, 0, s>>>(d_scores, L.perm, a);
+  launches++;
+  GDN_CHECK(pull_exchange(g, g->contrib[0], nullptr));
+  int iter, cur = 0;
+  for (iter = 0; iter < max_iter; iter++) {
+    a.contrib_in = g->contrib[cur];
+    a.contrib_out = g->contrib[cur ^ 1];
+    a.err_slot0 = 0;
+    kev_begin();
+    pr_sell_kernel<<<sm, kSellThreads, smem, s>>>(a);
+    kev_end();
+    launches++;
+    if (L.n_heavy_slices > 0) {
+      a.err_slot0 = sm * wpc;
+      pr_sell_finalize<<<fgrid, 256, 0, s>>>(a);
+      launches++;
+    }
+    if (L.rows > L.n_nz_rows) {
+      a.err_slot0 = sm * wpc + fgrid * 8;
+      pr_sell_isolated<<<igrid, 256, 0, s>>>(a);
+      launches++;
+    }
+    pr_reduce_err2<<<1, 256, 0, s>>>(g->err_partial, n_partial, g->err_trace, iter, multi ? -1.0 : eps, g->pr_done);
+    launches++;
+    GDN_CHECK(pull_exchange(g, g->contrib[cur ^ 1], g->err_trace + iter));
+    GDN_CUDA(cudaMemcpyAsync(h_err, g->err_trace + iter, sizeof(double), cudaMemcpyDeviceToHost, s));
+    GDN_CUDA(cudaStreamSynchronize(s));
+    if (st) st->pr_err[iter] = *h_err;
+    cur ^= 1;
+    if (*h_err < eps) break;                                 // src/pr/omp_base.cc:36
+  }
+  pr_sell_store<<<sm * 8, 256, 0, s>>>(d_scores, L.perm, g->scores_sorted, L.rows);
+  launches++;
+  GDN_CUDA(cudaEventRecord(lib().ev1, s));
+  GDN_CUDA(cudaStreamSynchronize(s));
+  GDN_CUDA(cudaGetLastError());
+  if (st) {
+    float ms = 0;
+    GDN_CUDA(cudaEventElapsedTime(&ms, lib().ev0, lib().ev1));
+    st->solve_ms = ms;
+    st->kernel_launches = launches;
+    st->iterations = iter + 1;                               // printf("iterations = %d", iter+1), :38
+    kev_collect(st);
+  }
+  return GDN_OK;
+}
+
+}  // namespace gdn
