@@ -20,10 +20,14 @@
 //    packed edge-by-edge onto lanes via a warp prefix sum; queue appends are
 //    warp-aggregated (one atomicAdd per warp per round).
 #include "common.cuh"
+#include <cstdlib>
+#include <algorithm>
 
 namespace gdn {
 
-constexpr int kTdHeavy = 8192;     // rows at least this long are expanded by the whole grid
+constexpr int kTdHeavy = 8192;     // largest row a single warp strip-mines; the host lowers the cut for small frontiers
+constexpr int kTdPiece = 128;      // edges per work piece of a deferred ("heavy") row
+constexpr int kBuReorderMax = 16384;   // rows longer than this keep their order in the hubs-first copy
 constexpr int kBuSerial = 8;       // in-neighbours a lane probes alone before the warp helps
 constexpr int kAlpha = 15, kBeta = 18;   // src/bfs/omp_beamer.cc:111
 
@@ -32,7 +36,10 @@ struct BfsCounters {
   long long awake;      // BU: vertices discovered (omp_beamer.cc:23)
   long long degsum;     // BU: sum of out-degree of discovered vertices (TEPS accounting)
   int tail;             // next-queue length
-  int heavy_tail;       // heavy-queue length
+  int pad;
+  long long bu_edges;   // BU: in-edges probed; TD: edges of the frontier (roofline accounting)
+  long long bu_scanned; // BU: unvisited vertices swept
+  unsigned long long heavy_pack;   // high 32: deferred rows, low 32: their 128-edge pieces (ONE atomic allocates both)
 };
 
 struct BfsState {
@@ -85,20 +92,23 @@ __device__ __forceinline__ long long td_visit(const OffT *__restrict__ rowptr, c
 template <typename OffT>
 __global__ void __launch_bounds__(256, 4)
 td_expand(const OffT *__restrict__ rowptr, const int32_t *__restrict__ col, const int32_t *__restrict__ q_in,
-          int n_in, BfsState s, int32_t *heavy_q, int level) {
+          int n_in, BfsState s, int32_t *heavy_q, uint32_t *heavy_off, uint32_t heavy_cut, int level) {
   if (n_in < 0) n_in = s.cnt->tail;       // partitioned mode: queue length lives on the device
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  long long scout = 0;
+  long long scout = 0, edges = 0;
   for (int base = warp * 32; base < n_in; base += nwarps * 32) {
     const int idx = base + lane;
     int v = -1;
     OffT b = 0, e = 0;
     if (idx < n_in) { v = q_in[idx]; b = rowptr[v - s.row_lo]; e = rowptr[v - s.row_lo + 1]; }
     uint32_t deg = (uint32_t)(e - b);
-    if (deg >= (uint32_t)kTdHeavy) {                    // tier 1: defer to td_heavy
-      heavy_q[atomicAdd(&s.cnt->heavy_tail, 1)] = v;
+    edges += deg;
+    if (deg >= heavy_cut) {                              // tier 1: defer to td_heavy (flattened piece list)
+      const unsigned long long old = atomicAdd(&s.cnt->heavy_pack, (1ull << 32) | (unsigned long long)((deg + kTdPiece - 1) / kTdPiece));
+      heavy_q[old >> 32] = v;
+      heavy_off[old >> 32] = (uint32_t)old;
       deg = 0;
     }
     unsigned med = __ballot_sync(kFull, deg >= 32u);     // tier 2: warp strip-mines the row
@@ -140,104 +150,273 @@ td_expand(const OffT *__restrict__ rowptr, const int32_t *__restrict__ col, cons
     }
   }
   scout = warp_sum(scout);
+  edges = warp_sum(edges);
   if (lane == 0 && scout) atomicAdd((unsigned long long *)&s.cnt->scout, (unsigned long long)scout);
+  if (lane == 0 && edges) atomicAdd((unsigned long long *)&s.cnt->bu_edges, (unsigned long long)edges);
 }
 
-// Rows >= kTdHeavy: every warp of the grid takes 32-edge pieces of the row.
+// Deferred rows: the (row, 128-edge piece) pairs form one flat list (heavy_off[slot] = first piece of
+// row slot, monotone in slot because slot and pieces come from the same 64-bit atomic).  Every warp
+// takes a contiguous range of pieces: one binary search, then a walk.  A frontier of five hubs is
+// expanded by the whole grid instead of five warps.
 template <typename OffT>
 __global__ void __launch_bounds__(256, 4)
 td_heavy(const OffT *__restrict__ rowptr, const int32_t *__restrict__ col, BfsState s,
-         const int32_t *__restrict__ heavy_q, int level) {
+         const int32_t *__restrict__ heavy_q, const uint32_t *__restrict__ heavy_off, int level) {
+  const unsigned long long pack = s.cnt->heavy_pack;
+  const uint32_t nh = (uint32_t)(pack >> 32), np = (uint32_t)pack;
+  if (nh == 0) return;
   const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int nh = s.cnt->heavy_tail;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t per = (np + nwarps - 1) / nwarps;
+  const uint64_t p0_ = (uint64_t)warp * per;
+  if (p0_ >= np) return;
+  uint32_t p = (uint32_t)p0_;
+  const uint32_t p1 = (uint32_t)min((uint64_t)np, p0_ + per);
+  uint32_t lo = 0, hi = nh;                              // heavy_off[lo] <= p < heavy_off[hi]
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (heavy_off[mid] <= p) lo = mid; else hi = mid;
+  }
   long long scout = 0;
-  for (int h = 0; h < nh; h++) {
-    const int src = heavy_q[h];
+  for (uint32_t slot = lo; p < p1; slot++) {
+    const int src = heavy_q[slot];
     const OffT b = rowptr[src - s.row_lo], e = rowptr[src - s.row_lo + 1];
-    for (OffT i = b + (OffT)warp * 32; i < e; i += (OffT)nwarps * 32) {
-      const OffT k = i + lane;
-      const int dst = (k < e) ? col[k] : -1;
-      scout += td_visit(rowptr, s, dst, src, level, lane);
+    const uint32_t first = heavy_off[slot];
+    const uint32_t pend = min(p1, (slot + 1 < nh) ? heavy_off[slot + 1] : np);
+    for (; p < pend; p++) {
+      const OffT i0 = b + (OffT)(p - first) * kTdPiece;
+      const OffT i1 = (e - i0 > (OffT)kTdPiece) ? i0 + kTdPiece : e;
+      for (OffT i = i0; i < i1; i += 32) {
+        const OffT k = i + lane;
+        const int dst = (k < i1) ? col[k] : -1;
+        scout += td_visit(rowptr, s, dst, src, level, lane);
+      }
     }
   }
   scout = warp_sum(scout);
   if (lane == 0 && scout) atomicAdd((unsigned long long *)&s.cnt->scout, (unsigned long long)scout);
 }
 
-// BUStep, src/bfs/omp_beamer.cc:13-32.  One warp sweeps 32 bitmap words
-// (1024 vertices) at a time; lane L owns vertex bit L of the current word.
+// Hubs-first copy of the bottom-up CSR.  BFS depths (and the alpha/beta schedule, which only counts
+// vertices) do not depend on the order in which a row's in-neighbours are probed, but the COST of
+// BUStep does: the sweep stops at the first neighbour found in the frontier (src/bfs/omp_beamer.cc:19-25)
+// and on a skewed graph that is almost always a hub.  Every row of at most kBuReorderMax entries is
+// stably partitioned by the log-scale degree class of the neighbour (deg_class, 0 = hub); longer rows
+// (hubs themselves, discovered in the first top-down steps) are copied unchanged.  One warp per row.
+template <typename OffT>
+__global__ void __launch_bounds__(256, 4)
+hubs_first(const OffT *__restrict__ rowptr, const int32_t *__restrict__ col, const uint8_t *__restrict__ cls,
+           int32_t *__restrict__ out, int64_t rows) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    const OffT b = rowptr[r], e = rowptr[r + 1];
+    const OffT len = e - b;
+    if (len > (OffT)kBuReorderMax || len <= 1) {
+      for (OffT i = b + lane; i < e; i += 32) out[i] = col[i];
+      continue;
+    }
+    // pass 1: entries per class -> lane j holds the running write offset of class j
+    uint32_t mycount = 0;
+    if (len > 32) {
+      for (OffT i = b; i < e; i += 32) {
+        const OffT k = i + lane;
+        const int kc = (k < e) ? (int)cls[col[k]] : 99;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const unsigned mj = __ballot_sync(kFull, kc == j);
+          if (lane == j) mycount += __popc(mj);
+        }
+      }
+    }
+    uint32_t start = mycount;                             // exclusive scan over lanes 0..7
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      const uint32_t n = __shfl_up_sync(kFull, start, o);
+      if (lane >= o) start += n;
+    }
+    start -= mycount;
+    // pass 2: stable scatter
+    for (OffT i = b; i < e; i += 32) {
+      const OffT k = i + lane;
+      const int c = (k < e) ? col[k] : -1;
+      const int kc = (k < e) ? (int)cls[c] : 99;
+      unsigned mk = 0;
+      uint32_t add = 0;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const unsigned mj = __ballot_sync(kFull, kc == j);
+        if (kc == j) mk = mj;
+        if (lane == j) add = __popc(mj);
+      }
+      if (len <= 32) {                                    // single chunk: class starts from this chunk's counts
+        uint32_t st1 = add;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+          const uint32_t n = __shfl_up_sync(kFull, st1, o);
+          if (lane >= o) st1 += n;
+        }
+        start = st1 - add;
+      }
+      const uint32_t base = __shfl_sync(kFull, start, kc & 7);
+      if (k < e) out[b + base + __popc(mk & lt)] = c;
+      start += add;
+    }
+  }
+}
+
+// BUStep, src/bfs/omp_beamer.cc:13-32.  One warp sweeps 32 bitmap words (1024 vertices) at a time.
+// The unvisited vertices of the group are first compacted into a shared-memory list (popc + warp scan),
+// so that every lane works on a live vertex -- on a Kronecker graph half of the ids are isolated
+// (pre-marked in `visited`, see iso_bitmap) and after the first sweep most of the rest are visited --
+// and each lane follows TWO vertices at once: the sweep is a chain of dependent loads
+// (offsets -> column -> frontier bit), so its speed is the number of chains in flight.
+// A lane probes up to kBuSerial in-neighbours alone; rows that have not hit by then are scanned by the
+// whole warp with a ballot early exit.  `next` is assembled in shared memory; no global atomics.
+template <typename OffT>
+__device__ __forceinline__ int bu_warp_scan(const int32_t *__restrict__ col, const uint32_t *__restrict__ front,
+                                            OffT bb, OffT ee, int lane, long long &probed) {
+  for (OffT i = bb; i < ee; i += 32) {
+    const OffT k = i + lane;
+    int src = -1;
+    bool ok = false;
+    if (k < ee) { src = col[k]; ok = (front[(uint32_t)src >> 5] >> (src & 31)) & 1u; probed++; }
+    const unsigned bal = __ballot_sync(kFull, ok);
+    if (bal) return __shfl_sync(kFull, src, __ffs(bal) - 1);
+  }
+  return -1;
+}
+
 template <typename OffT>
 __global__ void __launch_bounds__(256, 4)
 bu_sweep(const OffT *__restrict__ rowptr, const int32_t *__restrict__ col, const OffT *__restrict__ out_rowptr,
          const uint32_t *__restrict__ front, uint32_t *__restrict__ next, uint32_t *visited, int32_t *depth,
          int32_t *parent, int64_t word_lo, int64_t word_hi, int64_t row_lo, bool update_visited, int level,
          BfsCounters *cnt) {
-  const int lane = threadIdx.x & 31;
+  __shared__ uint16_t s_list[8][1024];
+  __shared__ uint32_t s_next[8][32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int64_t g_lo = word_lo >> 5, g_hi = word_hi >> 5;   // word ranges are multiples of 32
   rowptr -= row_lo;                                          // rows are addressed by global vertex id
   out_rowptr -= row_lo;
-  long long awake = 0, degsum = 0;
+  uint16_t *list = s_list[wib];
+  uint32_t *nx = s_next[wib];
+  long long awake = 0, degsum = 0, probed = 0, swept = 0;
   for (int64_t g = g_lo + warp; g < g_hi; g += nwarps) {
     const int64_t widx = g * 32 + lane;
     const uint32_t vis = visited[widx];
-    uint32_t nxt = 0;
-    if (__ballot_sync(kFull, vis != 0xffffffffu) != 0) {
-      for (int w = 0; w < 32; w++) {
-        const uint32_t word = __shfl_sync(kFull, vis, w);
-        if (word == 0xffffffffu) continue;               // warp-uniform
-        const int64_t v = (g * 32 + w) * 32 + lane;
-        const bool active = !((word >> lane) & 1u);
-        bool found = false;
-        int par = -1;
-        OffT lim = 0, e = 0;
-        if (active) {
-          const OffT b = rowptr[v];
-          e = rowptr[v + 1];
-          lim = (e - b > (OffT)kBuSerial) ? b + kBuSerial : e;
-          for (OffT i = b; i < lim; i++) {
-            const int src = col[i];
-            if ((front[(uint32_t)src >> 5] >> (src & 31)) & 1u) { found = true; par = src; break; }
-          }
-        }
-        // long rows that have not hit yet: the whole warp scans the remainder
-        unsigned rest = __ballot_sync(kFull, active && !found && lim < e);
-        while (rest) {
-          const int l = __ffs(rest) - 1;
-          rest &= rest - 1;
-          const OffT bb = __shfl_sync(kFull, lim, l), ee = __shfl_sync(kFull, e, l);
-          int hit = -1;
-          for (OffT i = bb; i < ee; i += 32) {
-            const OffT k = i + lane;
-            int src = -1;
-            bool ok = false;
-            if (k < ee) { src = col[k]; ok = (front[(uint32_t)src >> 5] >> (src & 31)) & 1u; }
-            const unsigned bal = __ballot_sync(kFull, ok);
-            if (bal) { hit = __shfl_sync(kFull, src, __ffs(bal) - 1); break; }
-          }
-          if (lane == l && hit >= 0) { found = true; par = hit; }
-        }
-        const unsigned fmask = __ballot_sync(kFull, found);
-        if (found) {
-          depth[v] = level;
-          if (parent) parent[v] = par;
-          degsum += (long long)(out_rowptr[v + 1] - out_rowptr[v]);
-        }
-        if (lane == w) nxt = fmask;
-        if (lane == 0) awake += __popc(fmask);
-      }
+    uint32_t act = ~vis;
+    const int c = __popc(act);
+    int off = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int n = __shfl_up_sync(kFull, off, o);
+      if (lane >= o) off += n;
     }
+    const int total = __shfl_sync(kFull, off, 31);
+    if (total == 0) { next[widx] = 0; continue; }
+    swept += c;
+    nx[lane] = 0;
+    off -= c;
+    while (act) {
+      const int bit = __ffs(act) - 1;
+      act &= act - 1;
+      list[off++] = (uint16_t)((lane << 5) | bit);
+    }
+    __syncwarp();
+    const int64_t vbase = g * 1024;
+    for (int i0 = 0; i0 < total; i0 += 64) {
+      const bool on_a = i0 + lane < total, on_b = i0 + 32 + lane < total;
+      const int la = on_a ? list[i0 + lane] : 0, lb = on_b ? list[i0 + 32 + lane] : 0;
+      const int64_t va = vbase + la, vb = vbase + lb;
+      OffT ia = 0, ea = 0, ib = 0, eb = 0;
+      if (on_a) { ia = rowptr[va]; ea = rowptr[va + 1]; }
+      if (on_b) { ib = rowptr[vb]; eb = rowptr[vb + 1]; }
+      const OffT lima = (ea - ia > (OffT)kBuSerial) ? ia + kBuSerial : ea;
+      const OffT limb = (eb - ib > (OffT)kBuSerial) ? ib + kBuSerial : eb;
+      int pa = -1, pb = -1;
+#pragma unroll 1
+      for (int p = 0; p < kBuSerial; p++) {
+        const bool ga = pa < 0 && ia < lima, gb = pb < 0 && ib < limb;
+        if (!__any_sync(kFull, ga || gb)) break;
+        const int sa = ga ? col[ia] : 0, sb = gb ? col[ib] : 0;
+        const uint32_t wa = ga ? front[(uint32_t)sa >> 5] : 0u, wb = gb ? front[(uint32_t)sb >> 5] : 0u;
+        if (ga && ((wa >> (sa & 31)) & 1u)) pa = sa;
+        if (gb && ((wb >> (sb & 31)) & 1u)) pb = sb;
+        probed += (int)ga + (int)gb;
+        ia++; ib++;
+      }
+      // long rows that have not hit yet: the whole warp scans the remainder
+      unsigned rest = __ballot_sync(kFull, on_a && pa < 0 && lima < ea);
+      while (rest) {
+        const int l = __ffs(rest) - 1;
+        rest &= rest - 1;
+        const int hit = bu_warp_scan<OffT>(col, front, __shfl_sync(kFull, lima, l), __shfl_sync(kFull, ea, l), lane, probed);
+        if (lane == l) pa = hit;
+      }
+      rest = __ballot_sync(kFull, on_b && pb < 0 && limb < eb);
+      while (rest) {
+        const int l = __ffs(rest) - 1;
+        rest &= rest - 1;
+        const int hit = bu_warp_scan<OffT>(col, front, __shfl_sync(kFull, limb, l), __shfl_sync(kFull, eb, l), lane, probed);
+        if (lane == l) pb = hit;
+      }
+      if (pa >= 0) {
+        depth[va] = level;
+        if (parent) parent[va] = pa;
+        degsum += (long long)(out_rowptr[va + 1] - out_rowptr[va]);
+        atomicOr(&nx[la >> 5], 1u << (la & 31));
+      }
+      if (pb >= 0) {
+        depth[vb] = level;
+        if (parent) parent[vb] = pb;
+        degsum += (long long)(out_rowptr[vb + 1] - out_rowptr[vb]);
+        atomicOr(&nx[lb >> 5], 1u << (lb & 31));
+      }
+      const unsigned fa = __ballot_sync(kFull, pa >= 0), fb = __ballot_sync(kFull, pb >= 0);
+      if (lane == 0) awake += __popc(fa) + __popc(fb);
+    }
+    __syncwarp();
+    const uint32_t nxt = nx[lane];
     next[widx] = nxt;
     if (nxt && update_visited) visited[widx] = vis | nxt;
+    __syncwarp();
   }
   awake = warp_sum(awake);
   degsum = warp_sum(degsum);
+  probed = warp_sum(probed);
+  swept = warp_sum(swept);
+  if (lane == 0 && swept) {
+    atomicAdd((unsigned long long *)&cnt->bu_edges, (unsigned long long)probed);
+    atomicAdd((unsigned long long *)&cnt->bu_scanned, (unsigned long long)swept);
+  }
   if (lane == 0 && awake) {
     atomicAdd((unsigned long long *)&cnt->awake, (unsigned long long)awake);
     atomicAdd((unsigned long long *)&cnt->degsum, (unsigned long long)degsum);
+  }
+}
+
+// Vertices without in-edges can never be discovered (omp_beamer.cc:17-26 finds no neighbour, TDStep never
+// sees them as a destination): their bits are pre-set in `visited` so that the sweeps skip them.  Static per
+// graph; a row partition marks its own rows only (the only ones it sweeps).
+template <typename OffT>
+__global__ void iso_bitmap(const OffT *__restrict__ in_rowptr, int64_t row_lo, int64_t row_hi, int64_t m, int64_t n_words,
+                           uint32_t *__restrict__ iso) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t w = warp; w < n_words; w += nwarps) {
+    const int64_t v = w * 32 + lane;
+    bool z = v >= m;                                       // pad bits count as visited
+    if (v >= row_lo && v < row_hi) z = in_rowptr[v - row_lo + 1] == in_rowptr[v - row_lo];
+    const unsigned mask = __ballot_sync(kFull, z);
+    if (lane == 0) iso[w] = mask;
   }
 }
 
@@ -283,7 +462,7 @@ template <typename OffT>
 __global__ void bfs_init(const OffT *__restrict__ out_rowptr, int32_t *depth, int32_t *parent, uint32_t *visited,
                          int64_t m, int64_t n_words, int source, int32_t *queue0, BfsCounters *cnt,
                          uint32_t *front /* partitioned mode: bitmap holding just the source */, int64_t row_lo,
-                         int64_t row_hi) {
+                         int64_t row_hi, const uint32_t *__restrict__ iso) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nth = (int64_t)gridDim.x * blockDim.x;
   for (int64_t v = tid; v < m; v += nth) {
@@ -291,9 +470,7 @@ __global__ void bfs_init(const OffT *__restrict__ out_rowptr, int32_t *depth, in
     if (parent) parent[v] = (v == source) ? source : -1;
   }
   for (int64_t w = tid; w < n_words; w += nth) {
-    uint32_t word = 0;
-    const int64_t lo = w * 32;
-    if (lo + 32 > m) word = (lo >= m) ? 0xffffffffu : ~((1u << (int)(m - lo)) - 1u);   // pad bits: "visited"
+    uint32_t word = iso[w];                                 // isolated vertices + pad bits: "visited"
     if ((int64_t)(source >> 5) == w) word |= 1u << (source & 31);
     visited[w] = word;
     if (front) front[w] = ((int64_t)(source >> 5) == w) ? (1u << (source & 31)) : 0u;
@@ -302,7 +479,7 @@ __global__ void bfs_init(const OffT *__restrict__ out_rowptr, int32_t *depth, in
     queue0[0] = source;
     const bool own = source >= row_lo && source < row_hi;
     cnt->scout = own ? (long long)(out_rowptr[source - row_lo + 1] - out_rowptr[source - row_lo]) : 0;   // degrees[source], omp_beamer.cc:130
-    cnt->awake = 0; cnt->degsum = 0; cnt->tail = 0; cnt->heavy_tail = 0;
+    cnt->awake = 0; cnt->degsum = 0; cnt->tail = 0; cnt->pad = 0; cnt->bu_edges = 0; cnt->bu_scanned = 0; cnt->heavy_pack = 0;
   }
 }
 
@@ -353,36 +530,70 @@ static int bfs_alloc(gdn_graph *g) {
   const int64_t need = std::max<int64_t>(g->n_words, partition_width(g->m, comm_size()) / 32 * comm_size());
   if (g->visited && g->bm_alloc_words >= need) return GDN_OK;
   if (g->visited) {
-    cudaFree(g->visited); cudaFree(g->front); cudaFree(g->next); cudaFree(g->xbuf);
-    g->visited = g->front = g->next = g->xbuf = nullptr;
+    cudaFree(g->visited); cudaFree(g->front); cudaFree(g->next); cudaFree(g->xbuf); cudaFree(g->iso);
+    g->visited = g->front = g->next = g->xbuf = g->iso = nullptr;
   }
   const size_t bm = sizeof(uint32_t) * need;
   GDN_CUDA(cudaMalloc((void **)&g->visited, bm));
   GDN_CUDA(cudaMalloc((void **)&g->front, bm));
   GDN_CUDA(cudaMalloc((void **)&g->next, bm));
+  GDN_CUDA(cudaMalloc((void **)&g->iso, bm));
+  {
+    const DevCsr &ci = g->symmetric ? g->out : g->in;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((g->n_words + 7) / 8, (int64_t)lib().sm_count * 8));
+    if (ci.off64) iso_bitmap<uint64_t><<<grid, 256, 0, lib().stream>>>((const uint64_t *)ci.rowptr, g->row_lo, g->row_hi, g->m, g->n_words, g->iso);
+    else iso_bitmap<uint32_t><<<grid, 256, 0, lib().stream>>>((const uint32_t *)ci.rowptr, g->row_lo, g->row_hi, g->m, g->n_words, g->iso);
+  }
   GDN_CUDA(cudaMemsetAsync(g->front, 0, bm, lib().stream));
   GDN_CUDA(cudaMemsetAsync(g->next, 0, bm, lib().stream));
   g->bm_alloc_words = need;
-  g->device_bytes += 3 * bm;
+  g->device_bytes += 4 * bm;
   if (!g->queue[0]) {
     GDN_CUDA(cudaMalloc((void **)&g->queue[0], sizeof(int32_t) * std::max<int64_t>(g->m, 1)));
     GDN_CUDA(cudaMalloc((void **)&g->queue[1], sizeof(int32_t) * std::max<int64_t>(g->m, 1)));
-    const int64_t hq = (int64_t)(g->out.nnz / kTdHeavy) + 2;
+    // deferred rows have >= 32 entries (td_cut), so there are at most nnz/32 of them in one step
+    const int64_t hq = std::min<int64_t>(g->row_hi - g->row_lo, (int64_t)(g->out.nnz / 32)) + 2;
     GDN_CUDA(cudaMalloc((void **)&g->heavy_queue, sizeof(int32_t) * hq));
+    GDN_CUDA(cudaMalloc((void **)&g->heavy_off, sizeof(uint32_t) * hq));
+    g->heavy_cap = hq;
     GDN_CUDA(cudaMalloc((void **)&g->counters, sizeof(BfsCounters)));
-    g->device_bytes += 2 * sizeof(int32_t) * g->m + sizeof(int32_t) * hq + sizeof(BfsCounters);
+    g->device_bytes += 2 * sizeof(int32_t) * g->m + 2 * sizeof(int32_t) * hq + sizeof(BfsCounters);
   }
+  return GDN_OK;
+}
+
+// Rows at least this long are deferred to td_heavy.  `edges` = scout_count = the number of edges this
+// top-down step scans (known exactly from the previous step, omp_beamer.cc:155): aim at equal work per
+// warp of a full grid, never below one warp-width and never above what one warp should strip-mine.
+static uint32_t td_cut(int64_t edges, int sm) {
+  const int64_t per_warp = edges / ((int64_t)sm * 4 * 8);
+  return (uint32_t)std::max<int64_t>(32, std::min<int64_t>(kTdHeavy, per_warp));
+}
+
+// Build the hubs-first copy of the bottom-up columns on first use (8 bytes... 4 bytes per edge, ~50 ms at Kron-26).
+template <typename OffT>
+static int bfs_prepare(gdn_graph *g) {
+  if (g->col_bu || !g->deg_class || g->one_shot || getenv("GDN_BFS_NO_REORDER")) return GDN_OK;
+  const DevCsr &ci = g->symmetric ? g->out : g->in;
+  if (ci.nnz == 0) return GDN_OK;
+  GDN_CUDA(cudaMalloc((void **)&g->col_bu, sizeof(int32_t) * ci.nnz + 256));
+  g->device_bytes += sizeof(int32_t) * ci.nnz;
+  hubs_first<OffT><<<lib().sm_count * 8, 256, 0, lib().stream>>>((const OffT *)ci.rowptr, ci.col, g->deg_class, g->col_bu, ci.rows);
+  GDN_CUDA(cudaStreamSynchronize(lib().stream));
+  GDN_CUDA(cudaGetLastError());
   return GDN_OK;
 }
 
 template <typename OffT>
 static int bfs_t(gdn_graph *g, int32_t source, int32_t *d_depth, int32_t *d_parent, gdn_stats *st) {
   GDN_CHECK(bfs_alloc(g));
+  GDN_CHECK(bfs_prepare<OffT>(g));
   cudaStream_t s = lib().stream;
   const DevCsr &co = g->out;
   const DevCsr &ci = g->symmetric ? g->out : g->in;
   const OffT *orp = (const OffT *)co.rowptr;
   const OffT *irp = (const OffT *)ci.rowptr;
+  const int32_t *bu_col = g->col_bu ? g->col_bu : ci.col;
   BfsCounters *cnt = (BfsCounters *)g->counters;
   BfsCounters *h = (BfsCounters *)lib().pinned;
   const int64_t m = g->m;
@@ -391,7 +602,7 @@ static int bfs_t(gdn_graph *g, int32_t source, int32_t *d_depth, int32_t *d_pare
 
   const int init_grid = (int)std::min<int64_t>((m + 255) / 256, (int64_t)sm * 8);
   bfs_init<OffT><<<init_grid, 256, 0, s>>>(orp, d_depth, d_parent, g->visited, m, g->n_words, source, g->queue[0], cnt,
-                                           nullptr, 0, m);
+                                           nullptr, 0, m, g->iso);
   GDN_CUDA(cudaMemcpyAsync(h, cnt, sizeof(BfsCounters), cudaMemcpyDeviceToHost, s));
   GDN_CUDA(cudaStreamSynchronize(s));
   GDN_CUDA(cudaGetLastError());
@@ -402,10 +613,10 @@ static int bfs_t(gdn_graph *g, int32_t source, int32_t *d_depth, int32_t *d_pare
   int64_t n_in = 1;
   int cur = 0, level = 0, iter = 0, n_steps = 0;
   uint32_t *front = g->front, *next = g->next;
-  auto record = [&](int dir, int64_t frontier, int64_t disc, int64_t sc) {
+  auto record = [&](int dir, int64_t frontier, int64_t disc, int64_t sc, int64_t edges, int64_t scanned) {
     if (st && n_steps < GDN_MAX_BFS_STEPS) {
       gdn_bfs_step &b = st->steps[n_steps];
-      b.dir = dir; b.pad = 0; b.frontier = frontier; b.discovered = disc; b.scout = sc;
+      b.dir = dir; b.pad = 0; b.frontier = frontier; b.discovered = disc; b.scout = sc; b.edges = edges; b.scanned = scanned;
     }
     n_steps++;
   };
@@ -424,7 +635,7 @@ static int bfs_t(gdn_graph *g, int32_t source, int32_t *d_depth, int32_t *d_pare
         old_awake = awake;
         GDN_CUDA(cudaMemsetAsync(cnt, 0, sizeof(BfsCounters), s));
         kev_begin();
-        bu_sweep<OffT><<<sweep_grid, 256, 0, s>>>(irp, ci.col, orp, front, next, g->visited, d_depth, d_parent,
+        bu_sweep<OffT><<<sweep_grid, 256, 0, s>>>(irp, bu_col, orp, front, next, g->visited, d_depth, d_parent,
                                                   0, g->n_words, 0, true, level + 1, cnt);
         kev_end();
         launches++;
@@ -434,7 +645,7 @@ static int bfs_t(gdn_graph *g, int32_t source, int32_t *d_depth, int32_t *d_pare
         reached += awake; reached_deg += h->degsum;
         level++;
         std::swap(front, next);                                   // front.swap(curr), :145
-        record(1, old_awake, awake, awake);
+        record(1, old_awake, awake, awake, h->bu_edges, h->bu_scanned);
       } while ((awake >= old_awake) || (awake > m / kBeta));      // :148-149
       GDN_CUDA(cudaMemsetAsync(cnt, 0, sizeof(BfsCounters), s));
       bitmap_to_queue<<<sweep_grid, 256, 0, s>>>(front, 0, g->n_words, g->queue[cur], cnt);
@@ -449,13 +660,14 @@ static int bfs_t(gdn_graph *g, int32_t source, int32_t *d_depth, int32_t *d_pare
       GDN_CUDA(cudaMemsetAsync(cnt, 0, sizeof(BfsCounters), s));
       BfsState bs = {g->visited, d_depth, d_parent, g->queue[cur ^ 1], cnt, nullptr, 0};
       const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_in + 255) / 256, (int64_t)sm * 8));
-      td_expand<OffT><<<grid, 256, 0, s>>>(orp, co.col, g->queue[cur], (int)n_in, bs, g->heavy_queue, level + 1);
-      td_heavy<OffT><<<sm * 4, 256, 0, s>>>(orp, co.col, bs, g->heavy_queue, level + 1);
+      td_expand<OffT><<<grid, 256, 0, s>>>(orp, co.col, g->queue[cur], (int)n_in, bs, g->heavy_queue, g->heavy_off,
+                                           td_cut(scout_count, sm), level + 1);
+      td_heavy<OffT><<<sm * 4, 256, 0, s>>>(orp, co.col, bs, g->heavy_queue, g->heavy_off, level + 1);
       launches += 2;
       GDN_CUDA(cudaMemcpyAsync(h, cnt, sizeof(BfsCounters), cudaMemcpyDeviceToHost, s));
       GDN_CUDA(cudaStreamSynchronize(s));
       scout_count = h->scout;                                     // :155
-      record(0, n_in, h->tail, scout_count);
+      record(0, n_in, h->tail, scout_count, h->bu_edges, 0);
       reached += h->tail; reached_deg += scout_count;
       n_in = h->tail;
       cur ^= 1;
@@ -496,6 +708,7 @@ int allreduce_i64(long long *d_p, int n);                              // comm.c
 template <typename OffT>
 static int bfs_multi_t(gdn_graph *g, int32_t source, int32_t *d_depth, gdn_stats *st) {
   GDN_CHECK(bfs_alloc(g));
+  GDN_CHECK(bfs_prepare<OffT>(g));
   cudaStream_t s = lib().stream;
   const DevCsr &co = g->out;
   const DevCsr &ci = g->symmetric ? g->out : g->in;
@@ -518,7 +731,7 @@ static int bfs_multi_t(gdn_graph *g, int32_t source, int32_t *d_depth, gdn_stats
 
   const int init_grid = (int)std::min<int64_t>((m + 255) / 256, (int64_t)sm * 8);
   bfs_init<OffT><<<init_grid, 256, 0, s>>>(orp, d_depth, nullptr, g->visited, m, g->n_words, source, g->queue[0], cnt,
-                                           front, g->row_lo, g->row_hi);
+                                           front, g->row_lo, g->row_hi, g->iso);
   // global E and degrees[source]: two all-reduced scalars
   long long *d_tmp = (long long *)&cnt->awake;                  // reuse: awake <- local nnz
   long long local_nnz = (long long)co.nnz;
@@ -533,10 +746,10 @@ static int bfs_multi_t(gdn_graph *g, int32_t source, int32_t *d_depth, gdn_stats
   int64_t reached_deg = scout_count, reached = 1;
   int64_t n_front = 1;
   int level = 0, iter = 0, n_steps = 0;
-  auto record = [&](int dir, int64_t frontier, int64_t disc, int64_t sc) {
+  auto record = [&](int dir, int64_t frontier, int64_t disc, int64_t sc, int64_t edges, int64_t scanned) {
     if (st && n_steps < GDN_MAX_BFS_STEPS) {
       gdn_bfs_step &b = st->steps[n_steps];
-      b.dir = dir; b.pad = 0; b.frontier = frontier; b.discovered = disc; b.scout = sc;
+      b.dir = dir; b.pad = 0; b.frontier = frontier; b.discovered = disc; b.scout = sc; b.edges = edges; b.scanned = scanned;
     }
     n_steps++;
   };
@@ -562,7 +775,7 @@ static int bfs_multi_t(gdn_graph *g, int32_t source, int32_t *d_depth, gdn_stats
         old_awake = awake;
         GDN_CUDA(cudaMemsetAsync(cnt, 0, sizeof(BfsCounters), s));
         kev_begin();
-        bu_sweep<OffT><<<own_grid, 256, 0, s>>>(irp, ci.col, orp, front, next, g->visited, d_depth, nullptr, own_lo,
+        bu_sweep<OffT><<<own_grid, 256, 0, s>>>(irp, g->col_bu ? g->col_bu : ci.col, orp, front, next, g->visited, d_depth, nullptr, own_lo,
                                                 own_hi, g->row_lo, false, level + 1, cnt);
         kev_end();
         launches++;
@@ -572,7 +785,7 @@ static int bfs_multi_t(gdn_graph *g, int32_t source, int32_t *d_depth, gdn_stats
         awake = h->awake;
         reached += awake; reached_deg += h->scout;
         level++;
-        record(1, old_awake, awake, awake);
+        record(1, old_awake, awake, awake, 0, 0);
       } while ((awake >= old_awake) || (awake > m / kBeta));      // :148-149
       n_front = awake;
       scout_count = 1;                                            // :151
@@ -583,14 +796,15 @@ static int bfs_multi_t(gdn_graph *g, int32_t source, int32_t *d_depth, gdn_stats
       GDN_CUDA(cudaMemsetAsync(next, 0, sizeof(uint32_t) * g->n_words, s));
       bitmap_to_queue<<<own_grid, 256, 0, s>>>(front, own_lo, own_hi, g->queue[0], cnt);
       BfsState bs = {g->visited, d_depth, nullptr, nullptr, cnt, next, g->row_lo};
-      td_expand<OffT><<<sm * 4, 256, 0, s>>>(orp, co.col, g->queue[0], -1, bs, g->heavy_queue, level + 1);
-      td_heavy<OffT><<<sm * 4, 256, 0, s>>>(orp, co.col, bs, g->heavy_queue, level + 1);
+      td_expand<OffT><<<sm * 4, 256, 0, s>>>(orp, co.col, g->queue[0], -1, bs, g->heavy_queue, g->heavy_off,
+                                             td_cut(scout_count / P, sm), level + 1);
+      td_heavy<OffT><<<sm * 4, 256, 0, s>>>(orp, co.col, bs, g->heavy_queue, g->heavy_off, level + 1);
       launches += 3;
       GDN_CHECK(bfs_merge_or(g, next, g->xbuf));
       GDN_CUDA(cudaMemsetAsync(cnt, 0, sizeof(BfsCounters), s));
       GDN_CHECK(absorb());
       scout_count = h->scout;                                     // :155
-      record(0, n_front, h->awake, scout_count);
+      record(0, n_front, h->awake, scout_count, 0, 0);
       reached += h->awake; reached_deg += scout_count;
       n_front = h->awake;
       level++;

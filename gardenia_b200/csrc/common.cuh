@@ -121,8 +121,14 @@ struct gdn_graph {
   float *scores_sorted = nullptr;    // PR scores in sorted row order during a solve
   // BFS scratch
   uint32_t *visited = nullptr, *front = nullptr, *next = nullptr;
+  uint32_t *iso = nullptr;           // static: vertices without in-edges (+ pad bits), pre-set in `visited`
   int32_t *queue[2] = {nullptr, nullptr};
-  int32_t *heavy_queue = nullptr;
+  int32_t *heavy_queue = nullptr;     // top-down: rows deferred to td_heavy ...
+  uint32_t *heavy_off = nullptr;      // ... and the first 128-edge piece of each (flattened work list)
+  int64_t heavy_cap = 0;
+  uint8_t *deg_class = nullptr;       // uint8[m]: log-scale out-degree class of every vertex, 0 = hub (host-built at create)
+  bool one_shot = false;              // graph lives for ONE solve (oneshot.cu): skip layouts that only pay off when amortised
+  int32_t *col_bu = nullptr;          // bottom-up copy of the in-CSR columns, every row reordered hubs-first
   uint32_t *xbuf = nullptr;          // partitioned BFS: receive buffer of the OR-merge (P bitmap slices)
   void *counters = nullptr;          // BfsCounters on device
   int64_t n_words = 0;               // bitmap words (32-bit), padded to a multiple of 32

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <chrono>
 #include <vector>
+#include <algorithm>
 
 namespace gdn {
 
@@ -155,6 +156,25 @@ static int graph_create_t(int64_t m, int64_t nnz, const HostOffT *out_rowptr, co
       }
     }
   }
+  if (rc == GDN_OK && out_rowptr && g->has_in) {
+    // log-scale out-degree class of EVERY vertex (the host still has the full offsets here; a row
+    // partition only keeps its own rows on the device): class 0 = hubs ... 7 = leaves, thresholds
+    // avg_degree * 4^j.  bfs.cu orders each bottom-up row hubs-first with it.
+    std::vector<uint8_t> cls((size_t)m);
+    const double avg = std::max(1.0, (double)nnz / (double)m);
+#pragma omp parallel for
+    for (int64_t v = 0; v < m; v++) {
+      const double d = (double)(out_rowptr[v + 1] - out_rowptr[v]) / avg;
+      int c = 7;
+      for (double t = 0.25; c > 0 && d >= t; t *= 4.0) c--;
+      cls[v] = (uint8_t)c;
+    }
+    if (cudaMalloc((void **)&g->deg_class, (size_t)m + 16) != cudaSuccess) { cudaGetLastError(); set_error("out of device memory"); rc = GDN_ERR_NOMEM; }
+    else {
+      g->device_bytes += (size_t)m;
+      if (cudaMemcpy(g->deg_class, cls.data(), (size_t)m, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("deg_class upload failed"); rc = GDN_ERR_CUDA; }
+    }
+  }
   if (rc == GDN_OK && g->has_in) {
     // degree-sorted SELL layout for the PageRank pull (host part; the SELL array itself is built on first use)
     const HostOffT *row_off = (g->symmetric || !in_rowptr) ? out_rowptr : in_rowptr;
@@ -255,8 +275,9 @@ int gdn_graph_destroy(gdn_graph *g) {
   else { free_csr(g->out); free_csr(g->in); }
   cudaFree(g->contrib[0]); cudaFree(g->contrib[1]); cudaFree(g->out_degree); cudaFree(g->err_partial);
   cudaFree(g->err_trace); cudaFree(g->pr_done);
-  cudaFree(g->visited); cudaFree(g->front); cudaFree(g->next); cudaFree(g->queue[0]); cudaFree(g->queue[1]);
-  cudaFree(g->heavy_queue); cudaFree(g->counters); cudaFree(g->xbuf);
+  cudaFree(g->visited); cudaFree(g->front); cudaFree(g->next); cudaFree(g->iso); cudaFree(g->queue[0]); cudaFree(g->queue[1]);
+  cudaFree(g->heavy_queue); cudaFree(g->heavy_off); cudaFree(g->deg_class); cudaFree(g->col_bu);
+  cudaFree(g->counters); cudaFree(g->xbuf);
   {
     gdn::PullLayout &L = g->pull;
     cudaFree(L.perm); cudaFree(L.newid); cudaFree(L.sdeg); cudaFree(L.sout); cudaFree(L.rowid); cudaFree(L.slice_ptr);

@@ -55,6 +55,7 @@ int bfs_oneshot(int64_t m, int64_t nnz, const OffT *orp, const int32_t *oci, con
   const double t0 = now_ms();
   GraphGuard gg;
   GDN_CHECK(create<OffT>(m, nnz, orp, oci, irp, ici, &gg.g));
+  gg.g->one_shot = true;
   DevBuf depth, parent;
   GDN_CHECK(depth.alloc(sizeof(int32_t) * m));
   if (parent_out) GDN_CHECK(parent.alloc(sizeof(int32_t) * m));

@@ -31,6 +31,7 @@
 // contiguous slices of contrib (two in-place NCCL allgathers per iteration).
 #include "common.cuh"
 #include <omp.h>
+#include <cstdlib>
 #include <algorithm>
 #include <vector>
 
@@ -298,6 +299,7 @@ struct SellArgs {
   double *err_partial;
   const int32_t *done;
   int32_t err_slot0;
+  int32_t warm;                // new ids below this are kept L2-resident; colder ids are gathered evict-first
 };
 
 __device__ __forceinline__ int64_t row_newid(const SellArgs &a, int64_t j) {
@@ -307,43 +309,80 @@ __device__ __forceinline__ int64_t row_newid(const SellArgs &a, int64_t j) {
 
 // scores[dst] = base + damp * sum; error += |new - old|; next contrib   (src/pr/omp_base.cc:24-25,31-33)
 __device__ __forceinline__ void pr_epilogue(const SellArgs &a, int64_t j, float acc, double &err) {
-  const float old_score = a.scores[j];
+  // scores / sdeg are touched once per iteration: streaming (evict-first) accesses keep them from
+  // displacing the warm part of contrib in L2; the new contrib of a warm id is stored normally (it is
+  // gathered in the next iteration), a cold one streaming.
+  const float old_score = __ldcs(a.scores + j);
   const float nw = __fadd_rn(a.base, __fmul_rn(a.damp, acc));
-  a.scores[j] = nw;
+  __stcs(a.scores + j, nw);
   err += (double)fabsf(__fsub_rn(nw, old_score));
-  const int32_t deg = a.sout ? a.sout[j] : a.sdeg[j];
-  a.contrib_out[row_newid(a, j)] = __fdiv_rn(nw, (float)deg);
+  const int32_t deg = a.sout ? __ldcs(a.sout + j) : __ldcs(a.sdeg + j);
+  const int64_t id = row_newid(a, j);
+  const float cv = __fdiv_rn(nw, (float)deg);
+  if (id < a.warm) a.contrib_out[id] = cv; else __stcs(a.contrib_out + id, cv);
 }
 
-__device__ __forceinline__ float pull_one(const SellArgs &a, const float *s_hot, int c) {
+// One gathered contrib value.  Three tiers (profiles/r1_gather_microbench_b200.txt): ids < H come from the
+// shared-memory table; ids < warm are the part of contrib that fits the 126 MB L2 and are loaded with an
+// L2 evict-last hint; colder ids (a few % of the edges of a Kronecker graph) are loaded evict-first so that
+// their one-touch sectors do not push the warm part out of L2.
+template <int POLICY>
+__device__ __forceinline__ float pull_one(const SellArgs &a, const float *s_hot, int c, uint64_t pol_first, uint64_t pol_last) {
   float v = 0.f;
-  if ((unsigned)c < (unsigned)a.H) v = s_hot[c];
-  else if (c >= 0) v = __ldg(a.contrib_in + c);
+  if ((unsigned)c < (unsigned)a.H) {
+    v = s_hot[c];
+  } else if (c >= 0) {
+    const float *p = a.contrib_in + c;
+    if (POLICY == 0) {
+      v = __ldg(p);
+    } else if (c < a.warm) {
+      if (POLICY == 1) v = ld_gather_f32(p, pol_last);
+      else v = __ldg(p);
+    } else {
+      asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol_first));
+    }
+  }
   return v;
 }
 
-// Sum groups [g0, g1) (multiples of 32 groups; lane = row) sequentially per lane.
+// Sum groups [g0, g1) (multiples of 32 groups; lane = row) sequentially per lane, in column order.
+// Software-pipelined: the NEXT four index groups are requested before the current 16 gathers are
+// issued, so a lane keeps 16 gathers + 4 index loads in flight (the kernel is latency-bound otherwise:
+// ncu r1 showed 90 % of issue slots with no eligible warp at 8 dependent gathers per trip).
+// Missing groups are padded with -1 = "add 0.0f", which leaves the fp32 sum bit-identical.
+template <int POLICY>
 __device__ __forceinline__ float sell_sum(const SellArgs &a, const float *s_hot, uint32_t g0, uint32_t g1, int lane,
-                                          float acc, uint64_t pol) {
-  uint32_t g = g0 + lane;
-  for (; g + 32 < g1; g += 64) {           // two groups per trip: 8 gathers in flight per lane
-    const int4 c0 = ld_stream_v4(a.sell + g, pol);
-    const int4 c1 = ld_stream_v4(a.sell + g + 32, pol);
-    const float v0 = pull_one(a, s_hot, c0.x), v1 = pull_one(a, s_hot, c0.y), v2 = pull_one(a, s_hot, c0.z),
-                v3 = pull_one(a, s_hot, c0.w), v4 = pull_one(a, s_hot, c1.x), v5 = pull_one(a, s_hot, c1.y),
-                v6 = pull_one(a, s_hot, c1.z), v7 = pull_one(a, s_hot, c1.w);
-    acc = __fadd_rn(acc, v0); acc = __fadd_rn(acc, v1); acc = __fadd_rn(acc, v2); acc = __fadd_rn(acc, v3);
-    acc = __fadd_rn(acc, v4); acc = __fadd_rn(acc, v5); acc = __fadd_rn(acc, v6); acc = __fadd_rn(acc, v7);
-  }
-  if (g < g1) {
-    const int4 c0 = ld_stream_v4(a.sell + g, pol);
-    const float v0 = pull_one(a, s_hot, c0.x), v1 = pull_one(a, s_hot, c0.y), v2 = pull_one(a, s_hot, c0.z),
-                v3 = pull_one(a, s_hot, c0.w);
-    acc = __fadd_rn(acc, v0); acc = __fadd_rn(acc, v1); acc = __fadd_rn(acc, v2); acc = __fadd_rn(acc, v3);
+                                          float acc, uint64_t pol, uint64_t pol_last) {
+  const int4 *p = a.sell + g0 + lane;
+  const int n = (int)((g1 - g0) >> 5);            // groups per lane (warp-uniform)
+  const int4 none = make_int4(-1, -1, -1, -1);
+  int4 c0 = 0 < n ? ld_stream_v4(p, pol) : none;
+  int4 c1 = 1 < n ? ld_stream_v4(p + 32, pol) : none;
+  int4 c2 = 2 < n ? ld_stream_v4(p + 64, pol) : none;
+  int4 c3 = 3 < n ? ld_stream_v4(p + 96, pol) : none;
+  for (int k = 0; k < n; k += 4) {
+    p += 128;
+    const int4 n0 = k + 4 < n ? ld_stream_v4(p, pol) : none;
+    const int4 n1 = k + 5 < n ? ld_stream_v4(p + 32, pol) : none;
+    const int4 n2 = k + 6 < n ? ld_stream_v4(p + 64, pol) : none;
+    const int4 n3 = k + 7 < n ? ld_stream_v4(p + 96, pol) : none;
+    float v[16];
+    v[0] = pull_one<POLICY>(a, s_hot, c0.x, pol, pol_last); v[1] = pull_one<POLICY>(a, s_hot, c0.y, pol, pol_last);
+    v[2] = pull_one<POLICY>(a, s_hot, c0.z, pol, pol_last); v[3] = pull_one<POLICY>(a, s_hot, c0.w, pol, pol_last);
+    v[4] = pull_one<POLICY>(a, s_hot, c1.x, pol, pol_last); v[5] = pull_one<POLICY>(a, s_hot, c1.y, pol, pol_last);
+    v[6] = pull_one<POLICY>(a, s_hot, c1.z, pol, pol_last); v[7] = pull_one<POLICY>(a, s_hot, c1.w, pol, pol_last);
+    v[8] = pull_one<POLICY>(a, s_hot, c2.x, pol, pol_last); v[9] = pull_one<POLICY>(a, s_hot, c2.y, pol, pol_last);
+    v[10] = pull_one<POLICY>(a, s_hot, c2.z, pol, pol_last); v[11] = pull_one<POLICY>(a, s_hot, c2.w, pol, pol_last);
+    v[12] = pull_one<POLICY>(a, s_hot, c3.x, pol, pol_last); v[13] = pull_one<POLICY>(a, s_hot, c3.y, pol, pol_last);
+    v[14] = pull_one<POLICY>(a, s_hot, c3.z, pol, pol_last); v[15] = pull_one<POLICY>(a, s_hot, c3.w, pol, pol_last);
+#pragma unroll
+    for (int q = 0; q < 16; q++) acc = __fadd_rn(acc, v[q]);
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
   }
   return acc;
 }
 
+template <int POLICY>
 __global__ void __launch_bounds__(kSellThreads, 1)
 pr_sell_kernel(SellArgs a) {
   extern __shared__ float s_hot[];
@@ -354,7 +393,7 @@ pr_sell_kernel(SellArgs a) {
   const int64_t warp = (int64_t)blockIdx.x * (kSellThreads / 32) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (kSellThreads / 32);
   const int64_t n_items = (int64_t)a.n_chunks + a.n_heavy_segs;
-  const uint64_t pol = l2_policy_evict_first();
+  const uint64_t pol = l2_policy_evict_first(), pol_last = l2_policy_evict_last();
   double err = 0.0;
   // heavy segments first (they are the longest items), then the chunks
   for (int64_t item = warp; item < n_items; item += nwarps) {
@@ -363,14 +402,14 @@ pr_sell_kernel(SellArgs a) {
       const uint32_t s0 = a.slice_ptr[hs.x], s1 = a.slice_ptr[hs.x + 1];
       const uint32_t g0 = s0 + (uint32_t)hs.y * kGroupCh;
       const uint32_t g1 = (s1 - g0 > (uint32_t)kGroupCh) ? g0 + kGroupCh : s1;
-      a.partial[(size_t)item * 32 + lane] = sell_sum(a, s_hot, g0, g1, lane, 0.f, pol);
+      a.partial[(size_t)item * 32 + lane] = sell_sum<POLICY>(a, s_hot, g0, g1, lane, 0.f, pol, pol_last);
     } else {
       const int64_t k = item - a.n_heavy_segs;
       const int32_t sa = a.chunk_slice[k], sb = a.chunk_slice[k + 1];
       for (int32_t s = sa; s < sb; s++) {
         const uint32_t g0 = a.slice_ptr[s], g1 = a.slice_ptr[s + 1];
         if (g1 - g0 > (uint32_t)kGroupCh) continue;          // wide slice: handled as segments
-        const float acc = sell_sum(a, s_hot, g0, g1, lane, 0.f, pol);
+        const float acc = sell_sum<POLICY>(a, s_hot, g0, g1, lane, 0.f, pol, pol_last);
         const int64_t j = (int64_t)s * 32 + lane;
         if (j < a.n_nz_rows) pr_epilogue(a, j, acc, err);
       }
@@ -479,7 +518,12 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
   }
   if (max_iter > GDN_MAX_PR_ITER - 1) max_iter = GDN_MAX_PR_ITER - 1;
   const size_t smem = sizeof(float) * (size_t)L.H;
-  GDN_CUDA(cudaFuncSetAttribute(pr_sell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // L2 residency tiers of the gathered vector (see pull_one); tunables for the profiling scripts
+  const char *e_pol = getenv("GDN_PR_POLICY"), *e_warm = getenv("GDN_PR_WARM_MB");
+  const int policy = e_pol ? atoi(e_pol) : 1;
+  const int64_t warm_ids = (int64_t)(e_warm ? atoi(e_warm) : 64) * (1 << 20) / 4;
+  void (*kern)(SellArgs) = policy == 0 ? pr_sell_kernel<0> : policy == 1 ? pr_sell_kernel<1> : pr_sell_kernel<2>;
+  GDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
   SellArgs a = {};
   a.sell = L.sell; a.slice_ptr = L.slice_ptr; a.chunk_slice = L.chunk_slice; a.n_chunks = L.n_chunks;
@@ -489,6 +533,7 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
   a.n_nz_rows = L.n_nz_rows; a.rows = L.rows; a.H = (int32_t)L.H; a.Hp = L.Hp; a.Wc = L.Wc; a.rank = L.R;
   a.base = (1.0f - damp) / (float)(int32_t)g->m;            // src/pr/omp_base.cc:16
   a.damp = damp; a.err_partial = g->err_partial; a.done = g->pr_done;
+  a.warm = (int32_t)std::min<int64_t>(warm_ids, 0x7fffffff);
   double *h_err = (double *)lib().pinned;
   int64_t launches = 0;
   const bool multi = L.P > 1;
@@ -507,7 +552,7 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
     a.contrib_out = g->contrib[cur ^ 1];
     a.err_slot0 = 0;
     kev_begin();
-    pr_sell_kernel<<<sm, kSellThreads, smem, s>>>(a);
+    kern<<<sm, kSellThreads, smem, s>>>(a);
     kev_end();
     launches++;
     if (L.n_heavy_slices > 0) {
@@ -515,10 +560,15 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
       pr_sell_finalize<<<fgrid, 256, 0, s>>>(a);
       launches++;
     }
-    if (L.rows > L.n_nz_rows) {
+    if (L.rows > L.n_nz_rows && iter < 2) {
+      // rows without in-edges reach their fixed point base (+0 error) in the first iteration; the second
+      // pass only writes their (constant) contrib into the other buffer.  Later iterations skip them:
+      // their L1 delta is exactly 0 and both contrib buffers already hold base/out_degree.
       a.err_slot0 = sm * wpc + fgrid * 8;
       pr_sell_isolated<<<igrid, 256, 0, s>>>(a);
       launches++;
+    } else if (L.rows > L.n_nz_rows && iter == 2) {
+      GDN_CUDA(cudaMemsetAsync(g->err_partial + sm * wpc + fgrid * 8, 0, sizeof(double) * igrid * 8, s));
     }
     pr_reduce_err2<<<1, 256, 0, s>>>(g->err_partial, n_partial, g->err_trace, iter, multi ? -1.0 : eps, g->pr_done);
     launches++;

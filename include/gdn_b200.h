@@ -58,6 +58,8 @@ typedef struct {
   int64_t frontier;     /* |frontier| expanded by this step */
   int64_t discovered;   /* vertices that received a depth */
   int64_t scout;        /* TD: scout_count, BU: awake_count */
+  int64_t edges;        /* edges examined: TD = sum of out-degree over the frontier, BU = in-edges probed until the first hit */
+  int64_t scanned;      /* BU: unvisited vertices swept (0 for TD) */
 } gdn_bfs_step;
 
 typedef struct {

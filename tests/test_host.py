@@ -30,9 +30,9 @@ def test_header_symbols_exported():
 
 
 def test_stats_struct_layout_matches_header():
-    # sizeof(gdn_stats): 2*4 + 3*8 + 8 + 8 + 8 + 4*8 + 128*8 + 256*32
-    assert C.sizeof(_lib.Stats) == 8 + 24 + 24 + 32 + 128 * 8 + 256 * 32
-    assert C.sizeof(_lib.BfsStep) == 32
+    # sizeof(gdn_stats): 2*4 + 3*8 + 8 + 8 + 8 + 4*8 + 128*8 + 256*48
+    assert C.sizeof(_lib.Stats) == 8 + 24 + 24 + 32 + 128 * 8 + 256 * 48
+    assert C.sizeof(_lib.BfsStep) == 48
 
 
 @pytest.mark.skipif(_lib.lib.gdn_device_count() > 0, reason="a GPU is present")
