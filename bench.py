@@ -226,11 +226,15 @@ def main():
         return float(t.item())
 
     # ---------------------------------------------------------------- graph
+    # torchrun exports OMP_NUM_THREADS=1; the host side (generator, layout preprocessing) is OpenMP code
+    ncpu = os.cpu_count() or 1
     if rank == 0:
+        _lib.lib.gdn_set_host_threads(ncpu)                  # the other ranks wait at the barrier
         pre, g = load_graph("g", args.scale)
     barrier()
     if rank != 0:
         pre, g = load_graph("g", args.scale)
+    _lib.lib.gdn_set_host_threads(max(1, ncpu // world))
     m, nnz = g.m, g.nnz
     bounds = gb.partition_rows(m, world)
     lo, hi = int(bounds[rank]), int(bounds[rank + 1])
@@ -283,6 +287,7 @@ def main():
     h_scores = torch.empty(rows, dtype=torch.float32).pin_memory()
     for a in (g.out_rowptr(), g.out_colidx()):
         _lib.lib.gdn_host_pin(a.ctypes.data, a.nbytes)       # page-lock the caller's CSR once (untimed)
+    g.out_degrees()                                          # the caller's degree array (graph_io.h read_graph returns it), built once
     dg.close()
     barrier()
     e0 = time.time()
@@ -311,7 +316,7 @@ def main():
 
     also = {}
     if world == 1 and not args.no_also:
-        also = side_metrics(args, g, local_rank, peak)
+        also = side_metrics(args, g, local_rank, peak, pre)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -336,7 +341,7 @@ def main():
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "gather_kernel<PR>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "pr_sell_kernel (one launch = one PageRank iteration over all rows)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_kernel_ms,
                          "launches_timed": int(kern_calls),
@@ -353,7 +358,26 @@ def main():
     return 0
 
 
-def side_metrics(args, g, device, peak):
+def bfs_algorithmic_bytes(m, steps):
+    """SURVEY §8(d) byte model evaluated over the schedule this BFS actually ran (gdn_stats.steps):
+    TD  4|F| (queue) + 8|F| (offsets) + 4 E_td (columns) + 4 new (depth) + 4 new (queue)
+    BU  3 m/8 (visited, front read; next write) + 8 V_bu (offsets) + 4 E_bu (columns probed) + 4 new (depth)
+    conversions Q->B: 4|F| + m/8, B->Q: m/8 + 4|F|.  Bitmap probes per edge count as 0 (L2-resident)."""
+    total, prev = 0, None
+    for s in steps:
+        if s["dir"] == 0:
+            if prev == 1:
+                total += m // 8 + 4 * s["frontier"]
+            total += 12 * s["frontier"] + 4 * s["edges"] + 8 * s["discovered"]
+        else:
+            if prev != 1:
+                total += 4 * s["frontier"] + m // 8
+            total += 3 * (m // 8) + 8 * s["scanned"] + 4 * s["edges"] + 4 * s["discovered"]
+        prev = s["dir"]
+    return total
+
+
+def side_metrics(args, g, device, peak, pre):
     """BFS GTEPS on the same Kronecker graph and SpMV GFLOP/s on urand (N=1 only)."""
     import numpy as np
     import torch
@@ -364,22 +388,39 @@ def side_metrics(args, g, device, peak):
     dg = gb.DeviceGraph(g, device=device)
     depth = torch.empty(m, dtype=torch.int32, device=dev)
     sources = [int(s) for s in g.pick_sources(16)]
-    dg.bfs(sources[0], depth)                         # warm-up
+    for s in sources[:3]:
+        dg.bfs(s, depth)                              # warm-up (first call also builds the hubs-first copy)
     tot_ms = tot_edges = kern_ms = 0.0
     launches = 0
+    alg = 0
     per = []
     for s in sources:
         st = dg.bfs(s, depth)
         tot_ms += st.solve_ms; tot_edges += st.edges_reached / 2; kern_ms += st.kernel_ms; launches += st.kernel_launches
+        alg += bfs_algorithmic_bytes(m, st.bfs_steps())
         per.append(st.edges_reached / 2 / (st.solve_ms / 1e3) / 1e9)
+    achieved = alg / (tot_ms / 1e3) / 1e9
     out["bfs"] = {"metric": "bfs_gteps", "value": tot_edges / (tot_ms / 1e3) / 1e9, "unit": "GTEPS",
-                  "workload": f"direction-optimizing BFS, Kronecker scale-{args.scale}, 16 GAP-style sources",
+                  "workload": f"direction-optimizing BFS, Kronecker scale-{args.scale}, 16 GAP-style sources, undirected edges of the reached component / solve time",
                   "sources": sources, "median_gteps": float(np.median(per)), "ms_per_bfs": tot_ms / len(sources),
-                  "bu_sweep_share": kern_ms / tot_ms, "gpu_launches": int(launches)}
+                  "bu_sweep_share": kern_ms / tot_ms, "gpu_launches": int(launches),
+                  "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                               "algorithmic_bytes_per_bfs": alg / len(sources),
+                               "note": "bytes of SURVEY 8(d) over the schedule actually run (hubs-first rows probe fewer in-edges than the oracle order); whole BFS incl. per-level host syncs"}}
+    if not args.no_cpu:
+        try:
+            drv = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+            ms, iters, _ = run_reference_binary([drv, "bfs", "bin", pre, "1", "0", str(sources[0]), os.path.join(CACHE_DIR, "ref_depth.i32"), "3"], os.cpu_count() or 1)
+            ref_ms = min(ms)
+            st = dg.bfs(sources[0], depth)
+            out["bfs"]["cpu_baseline"] = {"value": st.edges_reached / 2 / (ref_ms / 1e3) / 1e9, "unit": "GTEPS", "cores": os.cpu_count() or 1, "kind": "reference",
+                                          "sample": f"bfs_omp_beamer, source {sources[0]}, best of 3, {ref_ms:.1f} ms"}
+        except Exception as e:  # noqa: BLE001
+            out["bfs"]["cpu_baseline"] = {"value": None, "sample": f"failed: {e}"}
     dg.close()
     del depth
     # SpMV on urand
-    _, gu = load_graph("u", args.spmv_scale)
+    upre, gu = load_graph("u", args.spmv_scale)
     dgu = gb.DeviceGraph(gu, device=device)
     Ax = torch.from_numpy(gb.fill_uniform(13, gu.nnz)).to(dev)
     x = torch.from_numpy(gb.fill_uniform(14, gu.m)).to(dev)
@@ -399,6 +440,16 @@ def side_metrics(args, g, device, peak):
                    "roofline": {"bound": "hbm", "achieved": alg / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                                 "frac": alg / (ms / 1e3) / 1e9 / peak, "algorithmic_bytes_per_launch": alg}}
     dgu.close()
+    del Ax, x, y
+    if not args.no_cpu:
+        try:
+            drv = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+            rms, _, _ = run_reference_binary([drv, "spmv", "bin", upre, "1", "0", "13", os.path.join(CACHE_DIR, "ref_y.f32"), "3"], os.cpu_count() or 1)
+            ref_ms = min(rms)
+            out["spmv"]["cpu_baseline"] = {"value": 2.0 * gu.nnz / (ref_ms / 1e3) / 1e9, "unit": "GFLOP/s", "cores": os.cpu_count() or 1, "kind": "reference",
+                                           "sample": f"spmv_omp_base, best of 3, {ref_ms:.1f} ms"}
+        except Exception as e:  # noqa: BLE001
+            out["spmv"]["cpu_baseline"] = {"value": None, "sample": f"failed: {e}"}
     return out
 
 

@@ -88,6 +88,69 @@ __device__ __forceinline__ long long td_visit(const OffT *__restrict__ rowptr, c
   return deg;
 }
 
+// Four 32-edge groups at once (td_heavy): the visited probes, the claims and the degree look-ups of the
+// four destinations are independent, so their latencies overlap.  Claimed vertices are staged in a
+// per-warp shared-memory buffer and appended to the next queue kTdStage at a time: one reservation
+// (atomicAdd on the single queue tail) per ~30 pieces instead of one per piece -- with a million pieces
+// in the largest top-down step of a Kron-26 BFS the same-address atomic was the bottleneck.
+constexpr int kTdStage = 512;
+__device__ __forceinline__ void td_flush(const BfsState &s, const int *buf, int &nbuf, int lane) {
+  if (nbuf == 0) return;
+  int base = 0;
+  if (lane == 0) base = atomicAdd(&s.cnt->tail, nbuf);
+  base = __shfl_sync(kFull, base, 0);
+  __syncwarp();
+  for (int i = lane; i < nbuf; i += 32) s.q_out[base + i] = buf[i];
+  __syncwarp();
+  nbuf = 0;
+}
+
+template <typename OffT>
+__device__ __forceinline__ long long td_visit4(const OffT *__restrict__ rowptr, const BfsState &s, const int (&dst)[4], int src,
+                                               int level, int lane, int *buf, int &nbuf) {
+  if (s.mark) {
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (dst[u] >= 0) {
+        const uint32_t w = (uint32_t)dst[u] >> 5, bit = 1u << (dst[u] & 31);
+        if (!(s.visited[w] & bit) && !(s.mark[w] & bit)) atomicOr(&s.mark[w], bit);
+      }
+    }
+    return 0;
+  }
+  uint32_t word[4];
+#pragma unroll
+  for (int u = 0; u < 4; u++) word[u] = dst[u] >= 0 ? s.visited[(uint32_t)dst[u] >> 5] : 0xffffffffu;
+  bool claimed[4];
+#pragma unroll
+  for (int u = 0; u < 4; u++) {
+    const uint32_t bit = 1u << (dst[u] & 31);
+    claimed[u] = false;
+    if (!(word[u] & bit)) claimed[u] = !(atomicOr(&s.visited[(uint32_t)dst[u] >> 5], bit) & bit);
+  }
+  unsigned cm[4];
+  int total = 0;
+#pragma unroll
+  for (int u = 0; u < 4; u++) { cm[u] = __ballot_sync(kFull, claimed[u]); total += __popc(cm[u]); }
+  long long deg = 0;
+  if (total) {
+    if (nbuf + total > kTdStage) td_flush(s, buf, nbuf, lane);
+    int base = nbuf;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (claimed[u]) {
+        buf[base + __popc(cm[u] & ((1u << lane) - 1))] = dst[u];
+        s.depth[dst[u]] = level;
+        if (s.parent) s.parent[dst[u]] = src;
+        deg += (long long)(rowptr[dst[u] + 1] - rowptr[dst[u]]);
+      }
+      base += __popc(cm[u]);
+    }
+    nbuf += total;
+  }
+  return deg;
+}
+
 // TDStep, src/bfs/omp_beamer.cc:35-58.
 template <typename OffT>
 __global__ void __launch_bounds__(256, 4)
@@ -163,10 +226,13 @@ template <typename OffT>
 __global__ void __launch_bounds__(256, 4)
 td_heavy(const OffT *__restrict__ rowptr, const int32_t *__restrict__ col, BfsState s,
          const int32_t *__restrict__ heavy_q, const uint32_t *__restrict__ heavy_off, int level) {
+  __shared__ int s_stage[8][kTdStage];
   const unsigned long long pack = s.cnt->heavy_pack;
   const uint32_t nh = (uint32_t)(pack >> 32), np = (uint32_t)pack;
   if (nh == 0) return;
   const int lane = threadIdx.x & 31;
+  int *buf = s_stage[threadIdx.x >> 5];
+  int nbuf = 0;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t per = (np + nwarps - 1) / nwarps;
@@ -188,13 +254,16 @@ td_heavy(const OffT *__restrict__ rowptr, const int32_t *__restrict__ col, BfsSt
     for (; p < pend; p++) {
       const OffT i0 = b + (OffT)(p - first) * kTdPiece;
       const OffT i1 = (e - i0 > (OffT)kTdPiece) ? i0 + kTdPiece : e;
-      for (OffT i = i0; i < i1; i += 32) {
-        const OffT k = i + lane;
-        const int dst = (k < i1) ? col[k] : -1;
-        scout += td_visit(rowptr, s, dst, src, level, lane);
+      int dst[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const OffT k = i0 + (OffT)(u * 32 + lane);
+        dst[u] = (k < i1) ? col[k] : -1;
       }
+      scout += td_visit4(rowptr, s, dst, src, level, lane, buf, nbuf);
     }
   }
+  if (!s.mark) td_flush(s, buf, nbuf, lane);
   scout = warp_sum(scout);
   if (lane == 0 && scout) atomicAdd((unsigned long long *)&s.cnt->scout, (unsigned long long)scout);
 }
@@ -566,8 +635,9 @@ static int bfs_alloc(gdn_graph *g) {
 // top-down step scans (known exactly from the previous step, omp_beamer.cc:155): aim at equal work per
 // warp of a full grid, never below one warp-width and never above what one warp should strip-mine.
 static uint32_t td_cut(int64_t edges, int sm) {
-  const int64_t per_warp = edges / ((int64_t)sm * 4 * 8);
-  return (uint32_t)std::max<int64_t>(32, std::min<int64_t>(kTdHeavy, per_warp));
+  // a warp of td_expand owns 32 frontier rows: bound the ROW length by 1/32 of the per-warp share
+  const int64_t per_row = edges / ((int64_t)sm * 4 * 8 * 32);
+  return (uint32_t)std::max<int64_t>(32, std::min<int64_t>(kTdHeavy, per_row));
 }
 
 // Build the hubs-first copy of the bottom-up columns on first use (8 bytes... 4 bytes per edge, ~50 ms at Kron-26).

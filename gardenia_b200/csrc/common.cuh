@@ -39,6 +39,8 @@ inline void kev_collect(gdn_stats *st) {
 }
 Lib &lib();
 int ensure_init();
+// GDN_TRACE=1: wall-clock stage timings of the upload / preprocessing path on stderr
+void trace(const char *label);
 
 #define GDN_CUDA(call)                                                                  \
   do {                                                                                  \

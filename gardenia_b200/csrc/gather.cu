@@ -64,7 +64,7 @@ template <int MODE>
 __device__ __forceinline__ void row_epilogue(const GatherArgs &a, int64_t r, float acc, int32_t row_len,
                                              double &err) {
   if (MODE == kModeSpmv) {
-    a.y[r] = acc;                                      // acc started from y[r], omp_base.cc:25,32
+    __stcs(a.y + r, acc);                              // acc started from y[r], omp_base.cc:25,32; streaming: y is touched once
   } else {
     const float old_score = a.scores[r];
     const float nw = __fadd_rn(a.base, __fmul_rn(a.damp, acc));   // pr/omp_base.cc:32, no FMA contraction
@@ -130,8 +130,8 @@ gather_kernel(const OffT *__restrict__ rowptr, const int32_t *__restrict__ col, 
   for (int64_t item = warp; item < n_items; item += nwarps) {
     if (item < a.n_chunks) {
       // ---- light block: whole rows [r0, r1)
-      const int32_t r0 = a.chunk_row[item];
-      int32_t r1 = a.chunk_row[item + 1];
+      const int32_t r0 = __ldcs(a.chunk_row + item);
+      int32_t r1 = __ldcs(a.chunk_row + item + 1);
       if (r1 > r0) {
         const OffT lb = rowptr[r1 - 1], le = rowptr[r1];
         if (le - lb > (OffT)kChunk) r1--;               // heavy last row: handled as segments
@@ -143,7 +143,7 @@ gather_kernel(const OffT *__restrict__ rowptr, const int32_t *__restrict__ col, 
       __syncwarp();
       for (int32_t r = r0 + lane; r < r1; r += 32) {
         const int32_t s = (int32_t)(rowptr[r] - a0), t = (int32_t)(rowptr[r + 1] - a0);
-        float acc = (MODE == kModeSpmv) ? a.y[r] : 0.f;
+        float acc = (MODE == kModeSpmv) ? __ldcs(a.y + r) : 0.f;
         for (int32_t j = s; j < t; j++) acc = __fadd_rn(acc, sv[j]);
         row_epilogue<MODE>(a, r, acc, t - s, err);
       }
@@ -502,7 +502,7 @@ static int spmv_t(gdn_graph *g, const float *d_Ax, const float *d_x, float *d_y,
   // The TMA-staged variant is correct but measured 2.6x SLOWER than the register-staged kernel on urand-24
   // (8.4 vs 3.2 ms, profiles/r1_ncu_summary.md): 12 warps/SM of per-warp 1 K-entry items cannot cover the
   // describe -> copy -> gather -> row-sum chain.  Kept selectable for the next round's rework.
-  static const bool legacy = getenv("GDN_SPMV_TMA") == nullptr;
+  const bool legacy = getenv("GDN_SPMV_TMA") == nullptr;
   const size_t tma_smem = sizeof(TmaStage) * 2 * kTmaWarps + sizeof(uint64_t) * 2 * kTmaWarps;
   kev_begin();
   if (legacy) {

@@ -7,6 +7,7 @@
 // narrows uint64 -> int unconditionally), column indices stay global.
 #include "common.cuh"
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <chrono>
 #include <vector>
@@ -22,6 +23,15 @@ void set_error(const char *fmt, ...) {
   va_end(ap);
 }
 Lib &lib() { static Lib l; return l; }
+
+void trace(const char *label) {
+  static const bool on = getenv("GDN_TRACE") != nullptr;
+  if (!on) return;
+  static double last = 0;
+  const double now = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  fprintf(stderr, "[gdn trace] %-28s +%9.2f ms\n", label, last == 0 ? 0.0 : now - last);
+  last = now;
+}
 
 int ensure_init() {
   if (lib().inited) return GDN_OK;
@@ -63,9 +73,19 @@ __global__ void validate_csr(const OffT *__restrict__ rp, const int32_t *__restr
   }
 }
 
+// Upload of one CSR in two halves so that host-side preprocessing can run while the (pinned) column
+// array is still crossing PCIe: upload_csr_begin queues the copies and the validation kernel on the
+// library stream, upload_csr_end waits, checks the verdict and builds the row-block schedule.
+struct PendingUpload {
+  void *tmp = nullptr;
+  int *flag = nullptr;
+  int *h_flag = nullptr;      // slot in the pinned mailbox
+  bool want_schedule = false;
+};
+
 template <typename HostOffT>
-static int upload_csr(gdn_graph *g, DevCsr &c, const HostOffT *h_rowptr, const int32_t *h_col, int64_t row_lo,
-                      int64_t row_hi, bool want_schedule) {
+static int upload_csr_begin(gdn_graph *g, DevCsr &c, const HostOffT *h_rowptr, const int32_t *h_col, int64_t row_lo,
+                            int64_t row_hi, bool want_schedule, int slot, PendingUpload &pu) {
   cudaStream_t st = lib().stream;
   c.rows = row_hi - row_lo;
   const uint64_t base = (uint64_t)h_rowptr[row_lo];
@@ -79,29 +99,38 @@ static int upload_csr(gdn_graph *g, DevCsr &c, const HostOffT *h_rowptr, const i
   // offsets: stage the host-typed slice, narrow/rebase on the device
   HostOffT *tmp = nullptr;
   GDN_CUDA(cudaMalloc((void **)&tmp, sizeof(HostOffT) * (c.rows + 1)));
+  pu.tmp = tmp;
   GDN_CUDA(cudaMemcpyAsync(tmp, h_rowptr + row_lo, sizeof(HostOffT) * (c.rows + 1), cudaMemcpyHostToDevice, st));
   const int grid = (int)std::min<int64_t>((c.rows + 256) / 256, (int64_t)lib().sm_count * 8);
   if (c.off64) convert_offsets<HostOffT, uint64_t><<<grid, 256, 0, st>>>(tmp, (uint64_t *)c.rowptr, c.rows + 1, base);
   else convert_offsets<HostOffT, uint32_t><<<grid, 256, 0, st>>>(tmp, (uint32_t *)c.rowptr, c.rows + 1, base);
   GDN_CUDA(cudaMemcpyAsync(c.col, h_col + base, sizeof(int32_t) * c.nnz, cudaMemcpyHostToDevice, st));
   GDN_CUDA(cudaMemsetAsync((char *)c.col + sizeof(int32_t) * c.nnz, 0, 256, st));
-  int *flag = nullptr;
-  GDN_CUDA(cudaMalloc((void **)&flag, sizeof(int)));
-  GDN_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
+  GDN_CUDA(cudaMalloc((void **)&pu.flag, sizeof(int)));
+  GDN_CUDA(cudaMemsetAsync(pu.flag, 0, sizeof(int), st));
   const int vgrid = lib().sm_count * 8;
-  if (c.off64) validate_csr<uint64_t><<<vgrid, 256, 0, st>>>((const uint64_t *)c.rowptr, c.col, c.rows, c.nnz, g->m, flag);
-  else validate_csr<uint32_t><<<vgrid, 256, 0, st>>>((const uint32_t *)c.rowptr, c.col, c.rows, c.nnz, g->m, flag);
-  int hflag = 0;
-  GDN_CUDA(cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
-  GDN_CUDA(cudaStreamSynchronize(st));
-  GDN_CUDA(cudaFree(tmp));
-  GDN_CUDA(cudaFree(flag));
+  if (c.off64) validate_csr<uint64_t><<<vgrid, 256, 0, st>>>((const uint64_t *)c.rowptr, c.col, c.rows, c.nnz, g->m, pu.flag);
+  else validate_csr<uint32_t><<<vgrid, 256, 0, st>>>((const uint32_t *)c.rowptr, c.col, c.rows, c.nnz, g->m, pu.flag);
+  pu.h_flag = (int *)((char *)lib().pinned + 1024) + slot;
+  *pu.h_flag = 0;
+  GDN_CUDA(cudaMemcpyAsync(pu.h_flag, pu.flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  pu.want_schedule = want_schedule;
+  return GDN_OK;
+}
+
+static int upload_csr_end(gdn_graph *g, DevCsr &c, PendingUpload &pu) {
+  if (!pu.flag) return GDN_OK;
+  GDN_CUDA(cudaStreamSynchronize(lib().stream));
+  const int hflag = *pu.h_flag;
+  cudaFree(pu.tmp);
+  cudaFree(pu.flag);
+  pu.tmp = nullptr; pu.flag = nullptr;
   GDN_CUDA(cudaGetLastError());
   if (hflag) {
     set_error("malformed CSR (%s)", hflag == 1 ? "row offsets not monotone" : hflag == 2 ? "offset ends" : "column index out of range");
     return GDN_ERR_GRAPH;
   }
-  if (want_schedule) GDN_CHECK(build_schedule(g, c));
+  if (pu.want_schedule) GDN_CHECK(build_schedule(g, c));
   return GDN_OK;
 }
 
@@ -125,37 +154,24 @@ static int graph_create_t(int64_t m, int64_t nnz, const HostOffT *out_rowptr, co
   gdn_graph *g = new gdn_graph();
   g->m = m; g->row_lo = row_lo; g->row_hi = row_hi;
   int rc = GDN_OK;
-  if (out_rowptr && (!in_rowptr || (in_rowptr == out_rowptr && in_colidx == out_colidx))) {
+  trace("graph_create: begin");
+  PendingUpload pu_out, pu_in;
+  const bool sym = out_rowptr && (!in_rowptr || (in_rowptr == out_rowptr && in_colidx == out_colidx));
+  if (sym) {
     // one CSR serves both directions (symmetrized graph, include/csr_graph.h:241-246)
-    rc = upload_csr(g, g->out, out_rowptr, out_colidx, row_lo, row_hi, true);
+    rc = upload_csr_begin(g, g->out, out_rowptr, out_colidx, row_lo, row_hi, true, 0, pu_out);
     g->symmetric = true;
     g->has_out = g->has_in = true;
-    g->in = g->out;      // shallow alias; freed once
   } else if (!out_rowptr) {
     // pull-only graph: PageRank additionally needs gdn_graph_set_out_degree
-    rc = upload_csr(g, g->in, in_rowptr, in_colidx, row_lo, row_hi, true);
+    rc = upload_csr_begin(g, g->in, in_rowptr, in_colidx, row_lo, row_hi, true, 1, pu_in);
     g->has_in = true;
   } else {
-    rc = upload_csr(g, g->out, out_rowptr, out_colidx, row_lo, row_hi, false);
-    if (rc == GDN_OK) rc = upload_csr(g, g->in, in_rowptr, in_colidx, row_lo, row_hi, true);
+    rc = upload_csr_begin(g, g->out, out_rowptr, out_colidx, row_lo, row_hi, false, 0, pu_out);
+    if (rc == GDN_OK) rc = upload_csr_begin(g, g->in, in_rowptr, in_colidx, row_lo, row_hi, true, 1, pu_in);
     g->has_out = g->has_in = true;
-    if (rc == GDN_OK) {
-      // PageRank divides by the OUT degree (src/pr/omp_base.cc:25)
-      cudaStream_t st = lib().stream;
-      const int64_t rows = row_hi - row_lo;
-      if (cudaMalloc((void **)&g->out_degree, sizeof(int32_t) * (rows + 1)) != cudaSuccess) {
-        cudaGetLastError();
-        set_error("out of device memory");
-        rc = GDN_ERR_NOMEM;
-      } else {
-        g->device_bytes += sizeof(int32_t) * (rows + 1);
-        const int grid = (int)std::min<int64_t>((rows + 256) / 256, (int64_t)lib().sm_count * 8);
-        if (g->out.off64) row_lengths<uint64_t><<<grid, 256, 0, st>>>((const uint64_t *)g->out.rowptr, g->out_degree, rows);
-        else row_lengths<uint32_t><<<grid, 256, 0, st>>>((const uint32_t *)g->out.rowptr, g->out_degree, rows);
-        if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("row_lengths failed"); rc = GDN_ERR_CUDA; }
-      }
-    }
   }
+  trace("graph_create: CSR uploaded");
   if (rc == GDN_OK && out_rowptr && g->has_in) {
     // log-scale out-degree class of EVERY vertex (the host still has the full offsets here; a row
     // partition only keeps its own rows on the device): class 0 = hubs ... 7 = leaves, thresholds
@@ -175,6 +191,7 @@ static int graph_create_t(int64_t m, int64_t nnz, const HostOffT *out_rowptr, co
       if (cudaMemcpy(g->deg_class, cls.data(), (size_t)m, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("deg_class upload failed"); rc = GDN_ERR_CUDA; }
     }
   }
+  trace("graph_create: degree classes");
   if (rc == GDN_OK && g->has_in) {
     // degree-sorted SELL layout for the PageRank pull (host part; the SELL array itself is built on first use)
     const HostOffT *row_off = (g->symmetric || !in_rowptr) ? out_rowptr : in_rowptr;
@@ -182,6 +199,30 @@ static int graph_create_t(int64_t m, int64_t nnz, const HostOffT *out_rowptr, co
     const HostOffT *key_off = out_rowptr ? out_rowptr : row_off;
     rc = pull_prepare<HostOffT>(g, row_off, key_off);
   }
+  trace("graph_create: pull layout");
+  // the copies queued by upload_csr_begin have been running under the host work above
+  {
+    const int r1 = upload_csr_end(g, g->out, pu_out), r2 = upload_csr_end(g, g->in, pu_in);
+    if (rc == GDN_OK) rc = r1 != GDN_OK ? r1 : r2;
+  }
+  if (rc == GDN_OK && sym) g->in = g->out;      // shallow alias; freed once
+  if (rc == GDN_OK && !sym && out_rowptr) {
+    // PageRank divides by the OUT degree (src/pr/omp_base.cc:25)
+    cudaStream_t st = lib().stream;
+    const int64_t rows = row_hi - row_lo;
+    if (cudaMalloc((void **)&g->out_degree, sizeof(int32_t) * (rows + 1)) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("out of device memory");
+      rc = GDN_ERR_NOMEM;
+    } else {
+      g->device_bytes += sizeof(int32_t) * (rows + 1);
+      const int grid = (int)std::min<int64_t>((rows + 256) / 256, (int64_t)lib().sm_count * 8);
+      if (g->out.off64) row_lengths<uint64_t><<<grid, 256, 0, st>>>((const uint64_t *)g->out.rowptr, g->out_degree, rows);
+      else row_lengths<uint32_t><<<grid, 256, 0, st>>>((const uint32_t *)g->out.rowptr, g->out_degree, rows);
+      if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("row_lengths failed"); rc = GDN_ERR_CUDA; }
+    }
+  }
+  trace("graph_create: uploads finished");
   if (rc != GDN_OK) { gdn_graph_destroy(g); return rc; }
   *out = g;
   return GDN_OK;

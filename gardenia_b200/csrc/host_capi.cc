@@ -89,6 +89,12 @@ int gdn_host_graph_write_bin(const gdn_host_graph *hg, const char *prefix) {
   return hg->g.write_bin(prefix) == 0 ? GDN_OK : GDN_ERR_IO;
 }
 
+int gdn_set_host_threads(int n) {
+  if (n < 1) return GDN_ERR_ARG;
+  omp_set_num_threads(n);
+  return GDN_OK;
+}
+
 int gdn_fill_uniform(uint32_t seed, int64_t n, float *out) {
   if (!out || n < 0) return GDN_ERR_ARG;
   std::mt19937 rng(seed);

@@ -89,10 +89,13 @@ int pr_oneshot(int64_t m, int64_t nnz, const OffT *irp, const int32_t *ici, cons
   const double t1 = now_ms();
   gdn_stats local;
   gdn_stats *s = st ? st : &local;
+  trace("pr_oneshot: inputs resident");
   GDN_CHECK(gdn_pagerank_resident(gg.g, (float *)sc.p, damp, eps, max_iter, s));
+  trace("pr_oneshot: solved");
   const double t2 = now_ms();
   GDN_CHECK(d2h(scores, sc.p, sizeof(float) * m));
   const double t3 = now_ms();
+  trace("pr_oneshot: downloaded");
   s->h2d_ms = t1 - t0; s->d2h_ms = t3 - t2;
   s->h2d_bytes = (int64_t)(sizeof(OffT) * (m + 1) + sizeof(int32_t) * nnz + 8 * m);
   s->d2h_bytes = (int64_t)sizeof(float) * m;

@@ -47,7 +47,22 @@ int64_t partition_width(int64_t m, int nparts);
 
 // ------------------------------------------------------------------ host: stable sort by degree, descending
 // perm[j] = index (relative to lo) of the j-th vertex of [lo,hi) in (degree desc, id asc) order.
-static void sort_by_degree(const std::vector<int32_t> &deg, int64_t lo, int64_t hi, int32_t *perm) {
+// 268 MB work arrays: uninitialised (std::vector would zero them on ONE thread: ~60 ms each at Kron-26) and
+// first-touched inside the parallel loops.
+template <typename T>
+struct RawBuf {
+  T *p = nullptr;
+  explicit RawBuf(size_t n = 0) { if (n) p = (T *)malloc(n * sizeof(T)); }
+  ~RawBuf() { free(p); }
+  RawBuf(const RawBuf &) = delete;
+  RawBuf &operator=(const RawBuf &) = delete;
+  void alloc(size_t n) { free(p); p = (T *)malloc(std::max<size_t>(n, 1) * sizeof(T)); }
+  T &operator[](size_t i) { return p[i]; }
+  const T &operator[](size_t i) const { return p[i]; }
+  T *data() { return p; }
+};
+
+static void sort_by_degree(const int32_t *deg, int64_t lo, int64_t hi, int32_t *perm, int32_t *sorted_deg = nullptr) {
   const int64_t n = hi - lo;
   const int DB = 4096;                   // degrees below DB: parallel counting sort; above: std::stable_sort
   const int T = std::max(1, omp_get_max_threads());
@@ -66,6 +81,7 @@ static void sort_by_degree(const std::vector<int32_t> &deg, int64_t lo, int64_t 
   for (int t = 0; t < T; t++) bigs.insert(bigs.end(), big[t].begin(), big[t].end());
   std::stable_sort(bigs.begin(), bigs.end(), [&](int32_t x, int32_t y) { return deg[lo + x] > deg[lo + y]; });
   std::copy(bigs.begin(), bigs.end(), perm);
+  if (sorted_deg) for (size_t i = 0; i < bigs.size(); i++) sorted_deg[i] = deg[lo + bigs[i]];
   // start[t][d]: descending degree, then thread order (= ascending id)
   uint64_t pos = bigs.size();
   std::vector<std::vector<uint64_t>> start(T, std::vector<uint64_t>(DB));
@@ -77,7 +93,11 @@ static void sort_by_degree(const std::vector<int32_t> &deg, int64_t lo, int64_t 
     const int64_t a = n * t / T, b = n * (t + 1) / T;
     for (int64_t i = a; i < b; i++) {
       const int32_t d = deg[lo + i];
-      if (d < DB) perm[start[t][d]++] = (int32_t)i;
+      if (d < DB) {
+        const uint64_t pos = start[t][d]++;
+        perm[pos] = (int32_t)i;
+        if (sorted_deg) sorted_deg[pos] = d;
+      }
     }
   }
 }
@@ -94,6 +114,18 @@ static int upload(gdn_graph *g, T **dptr, const T *h, size_t n) {
 // gdn_graph_create while the caller's host offsets are still valid.
 //   row_off : offsets of the PULL (in-) CSR, global, host
 //   key_off : offsets whose row lengths rank the COLUMNS by hotness (out-CSR; == row_off when symmetric)
+// device halves of the layout (one GPU, symmetric order): new ids and sorted row lengths from the order
+__global__ void newid_from_perm(const int32_t *__restrict__ perm, int32_t *__restrict__ newid, int64_t n) {
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) newid[perm[j]] = (int32_t)j;
+}
+template <typename OffT>
+__global__ void sdeg_from_perm(const OffT *__restrict__ rowptr, const int32_t *__restrict__ perm, int32_t *__restrict__ sdeg, int64_t n) {
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t r = perm[j];
+    sdeg[j] = (int32_t)(rowptr[r + 1] - rowptr[r]);
+  }
+}
+
 template <typename HostOffT>
 int pull_prepare(gdn_graph *g, const HostOffT *row_off, const HostOffT *key_off) {
   PullLayout &L = g->pull;
@@ -113,46 +145,70 @@ int pull_prepare(gdn_graph *g, const HostOffT *row_off, const HostOffT *key_off)
   L.rows = rows;
   L.symmetric_order = (key_off == row_off);
 
-  std::vector<int32_t> rdeg(m), kdeg;
-#pragma omp parallel for
-  for (int64_t v = 0; v < m; v++) rdeg[v] = (int32_t)(row_off[v + 1] - row_off[v]);
-  const std::vector<int32_t> *kd = &rdeg;
+  trace("pull_prepare: begin");
+  RawBuf<int32_t> rdeg(m), kdeg;
+  if (!rdeg.p) { set_error("out of host memory"); return GDN_ERR_NOMEM; }
+  int64_t bad = 0;          // the device-side validation of these offsets is still in flight: do not index with garbage
+#pragma omp parallel for reduction(+ : bad)
+  for (int64_t v = 0; v < m; v++) {
+    rdeg[v] = (int32_t)(row_off[v + 1] - row_off[v]);
+    bad += row_off[v + 1] < row_off[v];
+  }
+  const int32_t *kd = rdeg.data();
   if (!L.symmetric_order) {
-    kdeg.resize(m);
-#pragma omp parallel for
-    for (int64_t v = 0; v < m; v++) kdeg[v] = (int32_t)(key_off[v + 1] - key_off[v]);
-    kd = &kdeg;
+    kdeg.alloc(m);
+#pragma omp parallel for reduction(+ : bad)
+    for (int64_t v = 0; v < m; v++) {
+      kdeg[v] = (int32_t)(key_off[v + 1] - key_off[v]);
+      bad += key_off[v + 1] < key_off[v];
+    }
+    kd = kdeg.data();
   }
-  // column order -> new ids for ALL vertices (every rank's slice)
-  std::vector<int32_t> newid(m), tmp(W);
-  for (int q = 0; q < P; q++) {
-    const int64_t qlo = std::min<int64_t>((int64_t)q * W, m), qhi = std::min<int64_t>(qlo + W, m);
-    if (qhi <= qlo) continue;
-    sort_by_degree(*kd, qlo, qhi, tmp.data());
-    const int64_t n = qhi - qlo;
+  if (bad) { L.prepared = false; return GDN_OK; }      // upload_csr_end reports the malformed CSR
+  // on one GPU of a symmetric graph the row order IS the column order: one sort, and newid / sdeg are
+  // derived from it on the device (no 268 MB host scatter, no upload)
+  const bool one_sort = L.symmetric_order && P == 1;
+  RawBuf<int32_t> perm(std::max<int64_t>(rows, 1)), newid, tmp, sdeg, rowid;
+  if (one_sort) {
+    sort_by_degree(kd, 0, m, perm.data());
+  } else {
+    newid.alloc(m); tmp.alloc(W); sdeg.alloc(std::max<int64_t>(rows, 1));
+    for (int q = 0; q < P; q++) {
+      const int64_t qlo = std::min<int64_t>((int64_t)q * W, m), qhi = std::min<int64_t>(qlo + W, m);
+      if (qhi <= qlo) continue;
+      sort_by_degree(kd, qlo, qhi, tmp.data());
+      const int64_t n = qhi - qlo;
 #pragma omp parallel for
-    for (int64_t j = 0; j < n; j++)
-      newid[qlo + tmp[j]] = (int32_t)(j < L.Hp ? (int64_t)q * L.Hp + j : L.H + (int64_t)q * L.Wc + (j - L.Hp));
+      for (int64_t j = 0; j < n; j++)
+        newid[qlo + tmp[j]] = (int32_t)(j < L.Hp ? (int64_t)q * L.Hp + j : L.H + (int64_t)q * L.Wc + (j - L.Hp));
+    }
+    if (rows > 0) sort_by_degree(rdeg.data(), lo, hi, perm.data(), sdeg.data());
+    if (!L.symmetric_order) {
+      rowid.alloc(std::max<int64_t>(rows, 1));
+#pragma omp parallel for
+      for (int64_t j = 0; j < rows; j++) rowid[j] = newid[lo + perm[j]];
+    }
   }
-  // row order of this rank (by row length); identical to the column order when symmetric
-  std::vector<int32_t> perm(std::max<int64_t>(rows, 1));
-  if (rows > 0) sort_by_degree(rdeg, lo, hi, perm.data());
-  std::vector<int32_t> sdeg(std::max<int64_t>(rows, 1)), rowid(std::max<int64_t>(rows, 1));
+  trace("pull_prepare: orders");
+  auto len_of = [&](int64_t j) -> int32_t { return rdeg[lo + perm[j]]; };     // length of sorted row j
   int64_t n_nz = 0;
-#pragma omp parallel for reduction(+ : n_nz)
-  for (int64_t j = 0; j < rows; j++) {
-    sdeg[j] = rdeg[lo + perm[j]];
-    rowid[j] = newid[lo + perm[j]];
-    n_nz += sdeg[j] > 0;
+  {
+    // rows are sorted by length, descending: the non-empty ones are a prefix
+    int64_t a = 0, b = rows;
+    while (a < b) { const int64_t mid = (a + b) >> 1; if (len_of(mid) > 0) a = mid + 1; else b = mid; }
+    n_nz = a;
   }
   L.n_nz_rows = n_nz;
   L.n_slices = (int32_t)((n_nz + 31) / 32);
   // slice pointers in int4 groups: slice s = 32 lanes x ceil(width/4) groups, width = longest (= first) row
   std::vector<uint32_t> sptr((size_t)L.n_slices + 1);
+  std::vector<int32_t> width((size_t)L.n_slices + 1);
+#pragma omp parallel for
+  for (int32_t s = 0; s < L.n_slices; s++) width[s] = len_of((int64_t)s * 32);
   uint64_t tot = 0;
   for (int32_t s = 0; s < L.n_slices; s++) {
     sptr[s] = (uint32_t)tot;
-    tot += 32ull * ((sdeg[(int64_t)s * 32] + 3) / 4);
+    tot += 32ull * ((width[s] + 3) / 4);
     if (tot >= 0xffff0000ull) { set_error("pull layout: too many non-zeros for 32-bit group offsets"); return GDN_ERR_ARG; }
   }
   sptr[L.n_slices] = (uint32_t)tot;
@@ -182,12 +238,26 @@ int pull_prepare(gdn_graph *g, const HostOffT *row_off, const HostOffT *key_off)
   L.n_heavy_segs = (int32_t)hseg.size();
   // wide slices for the fill kernel: the whole grid strides their column tiles
   L.n_fill_wide = 0;
-  for (int32_t s = 0; s < L.n_slices && sdeg[(int64_t)s * 32] > 2048; s++) L.n_fill_wide++;
+  for (int32_t s = 0; s < L.n_slices && width[s] > 2048; s++) L.n_fill_wide++;
 
+  trace("pull_prepare: slices");
+  cudaStream_t st = lib().stream;
   GDN_CHECK(upload(g, &L.perm, perm.data(), (size_t)rows));
-  GDN_CHECK(upload(g, &L.newid, newid.data(), (size_t)m));
-  GDN_CHECK(upload(g, &L.sdeg, sdeg.data(), (size_t)rows));
-  if (!L.symmetric_order) GDN_CHECK(upload(g, &L.rowid, rowid.data(), (size_t)rows));
+  if (one_sort) {
+    // the device offsets were queued on this stream by upload_csr_begin, so they are ready for sdeg_from_perm
+    GDN_CUDA(cudaMalloc((void **)&L.newid, sizeof(int32_t) * std::max<int64_t>(m, 4)));
+    GDN_CUDA(cudaMalloc((void **)&L.sdeg, sizeof(int32_t) * std::max<int64_t>(rows, 4)));
+    g->device_bytes += sizeof(int32_t) * (m + rows);
+    const DevCsr &c = g->symmetric ? g->out : g->in;
+    const int grid = lib().sm_count * 8;
+    newid_from_perm<<<grid, 256, 0, st>>>(L.perm, L.newid, rows);
+    if (c.off64) sdeg_from_perm<uint64_t><<<grid, 256, 0, st>>>((const uint64_t *)c.rowptr, L.perm, L.sdeg, rows);
+    else sdeg_from_perm<uint32_t><<<grid, 256, 0, st>>>((const uint32_t *)c.rowptr, L.perm, L.sdeg, rows);
+  } else {
+    GDN_CHECK(upload(g, &L.newid, newid.data(), (size_t)m));
+    GDN_CHECK(upload(g, &L.sdeg, sdeg.data(), (size_t)rows));
+    if (!L.symmetric_order) GDN_CHECK(upload(g, &L.rowid, rowid.data(), (size_t)rows));
+  }
   GDN_CHECK(upload(g, &L.slice_ptr, sptr.data(), sptr.size()));
   GDN_CHECK(upload(g, &L.chunk_slice, chunk.data(), chunk.size()));
   if (L.n_heavy_slices) {
@@ -197,7 +267,9 @@ int pull_prepare(gdn_graph *g, const HostOffT *row_off, const HostOffT *key_off)
     GDN_CUDA(cudaMalloc((void **)&L.partial, sizeof(float) * 32 * (size_t)L.n_heavy_segs));
     g->device_bytes += sizeof(float) * 32 * (size_t)L.n_heavy_segs;
   }
-  GDN_CUDA(cudaStreamSynchronize(lib().stream));      // host vectors die here
+  GDN_CUDA(cudaStreamSynchronize(st));      // host buffers die here
+  GDN_CUDA(cudaGetLastError());
+  trace("pull_prepare: uploaded");
   L.prepared = true;
   return GDN_OK;
 }
@@ -272,6 +344,7 @@ int pull_build_sell(gdn_graph *g) {
   }
   GDN_CUDA(cudaStreamSynchronize(lib().stream));
   GDN_CUDA(cudaGetLastError());
+  trace("pull_build_sell: done");
   return GDN_OK;
 }
 
@@ -325,23 +398,31 @@ __device__ __forceinline__ void pr_epilogue(const SellArgs &a, int64_t j, float 
 // One gathered contrib value.  Three tiers (profiles/r1_gather_microbench_b200.txt): ids < H come from the
 // shared-memory table; ids < warm are the part of contrib that fits the 126 MB L2 and are loaded with an
 // L2 evict-last hint; colder ids (a few % of the edges of a Kronecker graph) are loaded evict-first so that
-// their one-touch sectors do not push the warm part out of L2.
+// their one-touch sectors do not push the warm part out of L2.  Written as three PREDICATED loads (no
+// branches): the compiler's branchy version spent a fifth of its issue slots on reconvergence and left
+// the 16 loads of a trip interleaved with them (ncu r1: stall_mio 18 %, short scoreboard 30 %).
 template <int POLICY>
-__device__ __forceinline__ float pull_one(const SellArgs &a, const float *s_hot, int c, uint64_t pol_first, uint64_t pol_last) {
+__device__ __forceinline__ float pull_one(const SellArgs &a, uint32_t s_hot_addr, const float *s_hot, int c, uint64_t pol_first, uint64_t pol_last) {
   float v = 0.f;
-  if ((unsigned)c < (unsigned)a.H) {
-    v = s_hot[c];
-  } else if (c >= 0) {
-    const float *p = a.contrib_in + c;
-    if (POLICY == 0) {
-      v = __ldg(p);
-    } else if (c < a.warm) {
-      if (POLICY == 1) v = ld_gather_f32(p, pol_last);
-      else v = __ldg(p);
-    } else {
-      asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol_first));
-    }
+  if (POLICY == 0) {
+    if ((unsigned)c < (unsigned)a.H) v = s_hot[c];
+    else if (c >= 0) v = __ldg(a.contrib_in + c);
+    return v;
   }
+  const float *p = a.contrib_in + c;
+  uint64_t pol_norm = 0;
+  if (POLICY == 2) asm volatile("createpolicy.fractional.L2::evict_unchanged.b64 %0, 1.0;" : "=l"(pol_norm));
+  asm volatile(
+      "{\n\t.reg .pred ph, pw, pc;\n\t"
+      "setp.lt.u32 ph, %1, %2;\n\t"               // hot: 0 <= c < H   (c = -1 is 0xffffffff: never hot)
+      "setp.ge.s32 pw, %1, %2;\n\t"               // not hot and not padding
+      "setp.ge.s32 pc, %1, %3;\n\t"               // cold
+      "and.pred pw, pw, !pc;\n\t"
+      "@ph ld.shared.f32 %0, [%4];\n\t"
+      "@pw ld.global.nc.L2::cache_hint.f32 %0, [%5], %6;\n\t"
+      "@pc ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%5], %7;\n\t}"
+      : "+f"(v)
+      : "r"(c), "r"(a.H), "r"(a.warm), "r"(s_hot_addr + 4u * (uint32_t)c), "l"(p), "l"(POLICY == 2 ? pol_norm : pol_last), "l"(pol_first));
   return v;
 }
 
@@ -354,6 +435,7 @@ template <int POLICY>
 __device__ __forceinline__ float sell_sum(const SellArgs &a, const float *s_hot, uint32_t g0, uint32_t g1, int lane,
                                           float acc, uint64_t pol, uint64_t pol_last) {
   const int4 *p = a.sell + g0 + lane;
+  const uint32_t s_hot_addr = (uint32_t)__cvta_generic_to_shared(s_hot);
   const int n = (int)((g1 - g0) >> 5);            // groups per lane (warp-uniform)
   const int4 none = make_int4(-1, -1, -1, -1);
   int4 c0 = 0 < n ? ld_stream_v4(p, pol) : none;
@@ -367,14 +449,14 @@ __device__ __forceinline__ float sell_sum(const SellArgs &a, const float *s_hot,
     const int4 n2 = k + 6 < n ? ld_stream_v4(p + 64, pol) : none;
     const int4 n3 = k + 7 < n ? ld_stream_v4(p + 96, pol) : none;
     float v[16];
-    v[0] = pull_one<POLICY>(a, s_hot, c0.x, pol, pol_last); v[1] = pull_one<POLICY>(a, s_hot, c0.y, pol, pol_last);
-    v[2] = pull_one<POLICY>(a, s_hot, c0.z, pol, pol_last); v[3] = pull_one<POLICY>(a, s_hot, c0.w, pol, pol_last);
-    v[4] = pull_one<POLICY>(a, s_hot, c1.x, pol, pol_last); v[5] = pull_one<POLICY>(a, s_hot, c1.y, pol, pol_last);
-    v[6] = pull_one<POLICY>(a, s_hot, c1.z, pol, pol_last); v[7] = pull_one<POLICY>(a, s_hot, c1.w, pol, pol_last);
-    v[8] = pull_one<POLICY>(a, s_hot, c2.x, pol, pol_last); v[9] = pull_one<POLICY>(a, s_hot, c2.y, pol, pol_last);
-    v[10] = pull_one<POLICY>(a, s_hot, c2.z, pol, pol_last); v[11] = pull_one<POLICY>(a, s_hot, c2.w, pol, pol_last);
-    v[12] = pull_one<POLICY>(a, s_hot, c3.x, pol, pol_last); v[13] = pull_one<POLICY>(a, s_hot, c3.y, pol, pol_last);
-    v[14] = pull_one<POLICY>(a, s_hot, c3.z, pol, pol_last); v[15] = pull_one<POLICY>(a, s_hot, c3.w, pol, pol_last);
+    v[0] = pull_one<POLICY>(a, s_hot_addr, s_hot, c0.x, pol, pol_last); v[1] = pull_one<POLICY>(a, s_hot_addr, s_hot, c0.y, pol, pol_last);
+    v[2] = pull_one<POLICY>(a, s_hot_addr, s_hot, c0.z, pol, pol_last); v[3] = pull_one<POLICY>(a, s_hot_addr, s_hot, c0.w, pol, pol_last);
+    v[4] = pull_one<POLICY>(a, s_hot_addr, s_hot, c1.x, pol, pol_last); v[5] = pull_one<POLICY>(a, s_hot_addr, s_hot, c1.y, pol, pol_last);
+    v[6] = pull_one<POLICY>(a, s_hot_addr, s_hot, c1.z, pol, pol_last); v[7] = pull_one<POLICY>(a, s_hot_addr, s_hot, c1.w, pol, pol_last);
+    v[8] = pull_one<POLICY>(a, s_hot_addr, s_hot, c2.x, pol, pol_last); v[9] = pull_one<POLICY>(a, s_hot_addr, s_hot, c2.y, pol, pol_last);
+    v[10] = pull_one<POLICY>(a, s_hot_addr, s_hot, c2.z, pol, pol_last); v[11] = pull_one<POLICY>(a, s_hot_addr, s_hot, c2.w, pol, pol_last);
+    v[12] = pull_one<POLICY>(a, s_hot_addr, s_hot, c3.x, pol, pol_last); v[13] = pull_one<POLICY>(a, s_hot_addr, s_hot, c3.y, pol, pol_last);
+    v[14] = pull_one<POLICY>(a, s_hot_addr, s_hot, c3.z, pol, pol_last); v[15] = pull_one<POLICY>(a, s_hot_addr, s_hot, c3.w, pol, pol_last);
 #pragma unroll
     for (int q = 0; q < 16; q++) acc = __fadd_rn(acc, v[q]);
     c0 = n0; c1 = n1; c2 = n2; c3 = n3;
@@ -430,7 +512,15 @@ pr_sell_finalize(SellArgs a) {
     const int32_t s = a.heavy_slice[h];
     const int32_t f0 = a.heavy_first[h], f1 = a.heavy_first[h + 1];
     float acc = 0.f;
-    for (int32_t q = f0; q < f1; q++) acc = __fadd_rn(acc, a.partial[(size_t)q * 32 + lane]);
+    int32_t q = f0;
+    for (; q + 8 <= f1; q += 8) {                   // 8 independent loads, then the adds in segment order
+      float t[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) t[u] = __ldcs(a.partial + (size_t)(q + u) * 32 + lane);
+#pragma unroll
+      for (int u = 0; u < 8; u++) acc = __fadd_rn(acc, t[u]);
+    }
+    for (; q < f1; q++) acc = __fadd_rn(acc, __ldcs(a.partial + (size_t)q * 32 + lane));
     const int64_t j = (int64_t)s * 32 + lane;
     if (j < a.n_nz_rows) pr_epilogue(a, j, acc, err);
   }
@@ -438,15 +528,28 @@ pr_sell_finalize(SellArgs a) {
   if (lane == 0) a.err_partial[a.err_slot0 + warp] = err;
 }
 
-// rows without in-edges: score = base (src/pr/omp_base.cc:28-32 with an empty sum)
+// rows without in-edges: score = base (src/pr/omp_base.cc:28-32 with an empty sum).  They reach that
+// fixed point in the first iteration and never move again (L1 delta exactly 0), so this runs ONCE per
+// solve and writes their constant contrib into both buffers.
 __global__ void __launch_bounds__(256, 4)
-pr_sell_isolated(SellArgs a) {
+pr_sell_isolated(SellArgs a, float *contrib_other) {
   if (*a.done) return;
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   double err = 0.0;
-  for (int64_t j = a.n_nz_rows + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < a.rows; j += (int64_t)gridDim.x * blockDim.x)
-    pr_epilogue(a, j, 0.f, err);
+  const float nw = __fadd_rn(a.base, __fmul_rn(a.damp, 0.f));
+  for (int64_t j = a.n_nz_rows + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < a.rows; j += (int64_t)gridDim.x * blockDim.x) {
+    const float old_score = __ldcs(a.scores + j);
+    __stcs(a.scores + j, nw);
+    err += (double)fabsf(__fsub_rn(nw, old_score));
+    const int32_t deg = a.sout ? __ldcs(a.sout + j) : __ldcs(a.sdeg + j);
+    // x / 0 without the division slow path (symmetric graphs: every such row has out-degree 0 too)
+    const float cv = deg != 0 ? __fdiv_rn(nw, (float)deg)
+                              : (nw > 0.f ? __int_as_float(0x7f800000) : nw < 0.f ? __int_as_float(0xff800000) : __int_as_float(0x7fc00000));
+    const int64_t id = row_newid(a, j);
+    __stcs(a.contrib_out + id, cv);
+    __stcs(contrib_other + id, cv);
+  }
   err = warp_sum(err);
   if (lane == 0) a.err_partial[a.err_slot0 + warp] = err;
 }
@@ -521,8 +624,16 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
   // L2 residency tiers of the gathered vector (see pull_one); tunables for the profiling scripts
   const char *e_pol = getenv("GDN_PR_POLICY"), *e_warm = getenv("GDN_PR_WARM_MB");
   const int policy = e_pol ? atoi(e_pol) : 1;
-  const int64_t warm_ids = (int64_t)(e_warm ? atoi(e_warm) : 64) * (1 << 20) / 4;
-  void (*kern)(SellArgs) = policy == 0 ? pr_sell_kernel<0> : policy == 1 ? pr_sell_kernel<1> : pr_sell_kernel<2>;
+  const int64_t warm_ids = (int64_t)(e_warm ? atoi(e_warm) : 48) * (1 << 20) / 4;   // 48 MB measured best at Kron-26 (32: +4 %, 64: +5 %, 96: +17 %)
+  void (*kern)(SellArgs) = policy == 0 ? pr_sell_kernel<0> : policy == 2 ? pr_sell_kernel<2> : pr_sell_kernel<1>;
+  const char *e_persist = getenv("GDN_PR_PERSIST");
+  const int persist_mb = e_persist ? atoi(e_persist) : 0;
+  const bool persist = persist_mb > 0;
+  if (persist) {
+    cudaDeviceProp prop;
+    GDN_CUDA(cudaGetDeviceProperties(&prop, lib().device));
+    GDN_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize));
+  }
   GDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
   SellArgs a = {};
@@ -551,23 +662,35 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
     a.contrib_in = g->contrib[cur];
     a.contrib_out = g->contrib[cur ^ 1];
     a.err_slot0 = 0;
+    if (persist) {
+      // L2 set-aside for the warm prefix of the vector being gathered (experiment, GDN_PR_PERSIST=1)
+      cudaStreamAttrValue av = {};
+      av.accessPolicyWindow.base_ptr = (void *)(g->contrib[cur] + L.H);
+      av.accessPolicyWindow.num_bytes = (size_t)std::min<int64_t>((int64_t)persist_mb << 20, (L.Mp - L.H) * 4);
+      av.accessPolicyWindow.hitRatio = 1.0f;
+      av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      GDN_CUDA(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av));
+    }
     kev_begin();
     kern<<<sm, kSellThreads, smem, s>>>(a);
     kev_end();
     launches++;
+    if (persist) {
+      cudaStreamAttrValue av = {};
+      av.accessPolicyWindow.num_bytes = 0;
+      GDN_CUDA(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av));
+    }
     if (L.n_heavy_slices > 0) {
       a.err_slot0 = sm * wpc;
       pr_sell_finalize<<<fgrid, 256, 0, s>>>(a);
       launches++;
     }
-    if (L.rows > L.n_nz_rows && iter < 2) {
-      // rows without in-edges reach their fixed point base (+0 error) in the first iteration; the second
-      // pass only writes their (constant) contrib into the other buffer.  Later iterations skip them:
-      // their L1 delta is exactly 0 and both contrib buffers already hold base/out_degree.
+    if (L.rows > L.n_nz_rows && iter == 0) {
       a.err_slot0 = sm * wpc + fgrid * 8;
-      pr_sell_isolated<<<igrid, 256, 0, s>>>(a);
+      pr_sell_isolated<<<igrid, 256, 0, s>>>(a, g->contrib[cur]);
       launches++;
-    } else if (L.rows > L.n_nz_rows && iter == 2) {
+    } else if (L.rows > L.n_nz_rows && iter == 1) {
       GDN_CUDA(cudaMemsetAsync(g->err_partial + sm * wpc + fgrid * 8, 0, sizeof(double) * igrid * 8, s));
     }
     pr_reduce_err2<<<1, 256, 0, s>>>(g->err_partial, n_partial, g->err_trace, iter, multi ? -1.0 : eps, g->pr_done);

@@ -82,7 +82,12 @@ class Graph:
     def in_colidx(self): return self._in_colidx
     def has_reverse_graph(self): return self._has_reverse
     def get_degree(self, v): return int(self._out_rowptr[v + 1] - self._out_rowptr[v])
-    def out_degrees(self): return np.diff(self._out_rowptr).astype(np.int32)
+    def out_degrees(self):
+        """int32 out-degree of every vertex (the `degree` array of the gen-1 readers, include/graph_io.h:357-377);
+        computed once per Graph, like the reference's reader does at load time."""
+        if getattr(self, "_deg", None) is None:
+            self._deg = np.diff(self._out_rowptr).astype(np.int32)
+        return self._deg
 
     def write_bin(self, prefix):
         check(lib.gdn_host_graph_write_bin(self._h, str(prefix).encode()))

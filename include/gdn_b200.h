@@ -195,6 +195,9 @@ const uint64_t *gdn_host_graph_in_rowptr(const gdn_host_graph *hg);   /* NULL wi
 const int32_t *gdn_host_graph_in_colidx(const gdn_host_graph *hg);
 const int32_t *gdn_host_graph_weights(const gdn_host_graph *hg);      /* gen-1 loader only, else NULL */
 int gdn_host_graph_write_bin(const gdn_host_graph *hg, const char *prefix);
+/* OpenMP threads used by the host side (generator, readers, layout preprocessing).  Launchers such as
+ * torchrun export OMP_NUM_THREADS=1, which would make the Kronecker generator 15x slower. */
+int gdn_set_host_threads(int n);
 /* Deterministic fp32 U[0,1) fill: std::mt19937(seed), (draw >> 8) * 2^-24. */
 int gdn_fill_uniform(uint32_t seed, int64_t n, float *out);
 /* BFS sources as SURVEY §8(d): mt19937(27491095) + uniform_int over [0,m-1],

@@ -271,3 +271,24 @@ def test_resident_matches_oneshot_and_is_deterministic():
     dg.spmv(Ax, 2 * x, y3)
     assert torch.equal(y3, 2 * y1)
     dg.close()
+
+
+def test_spmv_tma_variant(monkeypatch):
+    """The TMA-staged SpMV (cp.async.bulk + mbarrier) computes the same rows as the register-staged kernel."""
+    import torch
+    for kind, scale in (("u", 16), ("g", 16)):
+        g = gb.Graph.generate(kind, scale, 16)
+        m = g.m
+        dg = gb.DeviceGraph(g)
+        Ax = torch.from_numpy(gb.fill_uniform(13, g.nnz)).cuda()
+        x = torch.from_numpy(gb.fill_uniform(14, m)).cuda()
+        y0 = torch.from_numpy(gb.fill_uniform(15, m)).cuda()
+        ya, yb = y0.clone(), y0.clone()
+        dg.spmv(Ax, x, ya)
+        monkeypatch.setenv("GDN_SPMV_TMA", "1")
+        dg.spmv(Ax, x, yb)
+        monkeypatch.delenv("GDN_SPMV_TMA")
+        oy = po.spmv(m, g.out_rowptr(), g.out_colidx(), Ax.cpu().numpy(), x.cpu().numpy(), y0.cpu().numpy())
+        assert _rel(yb.cpu().numpy(), oy) <= SPMV_REL_TOL
+        assert _rel(ya.cpu().numpy(), oy) <= SPMV_REL_TOL
+        dg.close()
