@@ -58,6 +58,8 @@ struct GatherArgs {
   double *err_partial;
   const int32_t *done;    // device flag set once converged: later launches are no-ops
   int err_slot0;          // first err_partial slot of this kernel
+  // column window of this pass (SpMV column passes, see spmv_t): entries outside [col_lo, col_hi) add +0.0f
+  int32_t col_lo, col_hi;
 };
 
 template <int MODE>
@@ -96,10 +98,10 @@ __device__ __forceinline__ float stream_gather(const GatherArgs &a, const int32_
     }
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-      const bool ok = (i + j >= b) && (i + j < e);
+      const bool ok = (i + j >= b) && (i + j < e) && (MODE != kModeSpmv || (q[j] >= a.col_lo && q[j] < a.col_hi));
       float g = 0.f;
       if (ok) g = ld_gather_f32(a.vec + q[j], pol);
-      v[j] = (MODE == kModeSpmv) ? __fmul_rn(g, ax[j]) : g;
+      v[j] = (MODE == kModeSpmv) ? (ok ? __fmul_rn(g, ax[j]) : 0.f) : g;
     }
     if (STAGE) {
       float4 *dst = reinterpret_cast<float4 *>(sv + (i - a0));
@@ -504,9 +506,25 @@ static int spmv_t(gdn_graph *g, const float *d_Ax, const float *d_x, float *d_y,
   // describe -> copy -> gather -> row-sum chain.  Kept selectable for the next round's rework.
   const bool legacy = getenv("GDN_SPMV_TMA") == nullptr;
   const size_t tma_smem = sizeof(TmaStage) * 2 * kTmaWarps + sizeof(uint64_t) * 2 * kTmaWarps;
+  // Column passes.  A gathered vector larger than the part of L2 one die keeps (~50 MB measured) misses on
+  // every LRU turn-over (urand-24, x = 64 MB: 19 % of the gathers went to HBM at 48 G/s instead of 280 G/s).  With P
+  // passes, pass p gathers only the columns of window p (a prefix / middle / suffix of every sorted row): the window
+  // stays L2-resident, the other entries add +0.0f, and y carries the running sum from pass to pass -- the fp32
+  // addition order of a light row is still exactly the reference's (src/spmv/omp_base.cc:26-31).  The price is
+  // streaming col/Ax once per pass.
+  const char *e_pass = getenv("GDN_SPMV_PASSES"), *e_win = getenv("GDN_SPMV_WINDOW_MB");
+  const int64_t win_ids = (int64_t)(e_win ? atoi(e_win) : 40) * (1 << 20) / 4;
+  int passes = e_pass ? atoi(e_pass) : (int)std::min<int64_t>(4, (g->m + win_ids - 1) / win_ids);
+  if (passes < 1 || !legacy) passes = 1;
+  a.col_lo = 0; a.col_hi = 0x7fffffff;
   kev_begin();
   if (legacy) {
-    gather_kernel<OffT, kModeSpmv><<<gather_grid(c), kThreads, 0, s>>>(rp, c.col, a);
+    for (int p = 0; p < passes; p++) {
+      a.col_lo = (int32_t)(g->m * p / passes);
+      a.col_hi = p + 1 == passes ? 0x7fffffff : (int32_t)(g->m * (p + 1) / passes);
+      gather_kernel<OffT, kModeSpmv><<<gather_grid(c), kThreads, 0, s>>>(rp, c.col, a);
+      if (c.n_heavy_rows > 0 && p + 1 < passes) finalize_heavy<OffT, kModeSpmv><<<heavy_grid(c), kThreads, 0, s>>>(rp, a);
+    }
   } else {
     GDN_CUDA(cudaFuncSetAttribute(spmv_tma_kernel<OffT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem));
     const int64_t items = (int64_t)c.n_chunks + c.n_heavy_segs;
@@ -514,10 +532,10 @@ static int spmv_t(gdn_graph *g, const float *d_Ax, const float *d_x, float *d_y,
     spmv_tma_kernel<OffT><<<grid, kTmaWarps * 32, tma_smem, s>>>(rp, c.col, a);
   }
   kev_end();
-  int launches = 1;
+  int launches = passes;
   if (c.n_heavy_rows > 0) {
     finalize_heavy<OffT, kModeSpmv><<<heavy_grid(c), kThreads, 0, s>>>(rp, a);
-    launches++;
+    launches += passes;
   }
   GDN_CUDA(cudaEventRecord(lib().ev1, s));
   GDN_CUDA(cudaStreamSynchronize(s));

@@ -373,6 +373,7 @@ struct SellArgs {
   const int32_t *done;
   int32_t err_slot0;
   int32_t warm;                // new ids below this are kept L2-resident; colder ids are gathered evict-first
+  int32_t skip_from;           // TIMING EXPERIMENT ONLY (GDN_PR_SKIP_FROM_MB): ids at or above this are not gathered (wrong results)
 };
 
 __device__ __forceinline__ int64_t row_newid(const SellArgs &a, int64_t j) {
@@ -413,16 +414,18 @@ __device__ __forceinline__ float pull_one(const SellArgs &a, uint32_t s_hot_addr
   uint64_t pol_norm = 0;
   if (POLICY == 2) asm volatile("createpolicy.fractional.L2::evict_unchanged.b64 %0, 1.0;" : "=l"(pol_norm));
   asm volatile(
-      "{\n\t.reg .pred ph, pw, pc;\n\t"
+      "{\n\t.reg .pred ph, pw, pc, ph2;\n\t"
       "setp.lt.u32 ph, %1, %2;\n\t"               // hot: 0 <= c < H   (c = -1 is 0xffffffff: never hot)
       "setp.ge.s32 pw, %1, %2;\n\t"               // not hot and not padding
       "setp.ge.s32 pc, %1, %3;\n\t"               // cold
       "and.pred pw, pw, !pc;\n\t"
+      "setp.lt.s32 ph2, %1, %8;\n\t"
+      "and.pred pc, pc, ph2;\n\t"
       "@ph ld.shared.f32 %0, [%4];\n\t"
       "@pw ld.global.nc.L2::cache_hint.f32 %0, [%5], %6;\n\t"
       "@pc ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%5], %7;\n\t}"
       : "+f"(v)
-      : "r"(c), "r"(a.H), "r"(a.warm), "r"(s_hot_addr + 4u * (uint32_t)c), "l"(p), "l"(POLICY == 2 ? pol_norm : pol_last), "l"(pol_first));
+      : "r"(c), "r"(a.H), "r"(a.warm), "r"(s_hot_addr + 4u * (uint32_t)c), "l"(p), "l"(POLICY == 2 ? pol_norm : pol_last), "l"(pol_first), "r"(a.skip_from));
   return v;
 }
 
@@ -645,6 +648,9 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
   a.base = (1.0f - damp) / (float)(int32_t)g->m;            // src/pr/omp_base.cc:16
   a.damp = damp; a.err_partial = g->err_partial; a.done = g->pr_done;
   a.warm = (int32_t)std::min<int64_t>(warm_ids, 0x7fffffff);
+  const char *e_skip = getenv("GDN_PR_SKIP_FROM_MB");
+  a.skip_from = e_skip ? (int32_t)std::min<int64_t>((int64_t)atoi(e_skip) * (1 << 20) / 4, 0x7fffffff) : 0x7fffffff;
+  a.warm = std::min(a.warm, a.skip_from);
   double *h_err = (double *)lib().pinned;
   int64_t launches = 0;
   const bool multi = L.P > 1;
