@@ -506,15 +506,15 @@ static int spmv_t(gdn_graph *g, const float *d_Ax, const float *d_x, float *d_y,
   // describe -> copy -> gather -> row-sum chain.  Kept selectable for the next round's rework.
   const bool legacy = getenv("GDN_SPMV_TMA") == nullptr;
   const size_t tma_smem = sizeof(TmaStage) * 2 * kTmaWarps + sizeof(uint64_t) * 2 * kTmaWarps;
-  // Column passes.  A gathered vector larger than the part of L2 one die keeps (~50 MB measured) misses on
-  // every LRU turn-over (urand-24, x = 64 MB: 19 % of the gathers went to HBM at 48 G/s instead of 280 G/s).  With P
-  // passes, pass p gathers only the columns of window p (a prefix / middle / suffix of every sorted row): the window
-  // stays L2-resident, the other entries add +0.0f, and y carries the running sum from pass to pass -- the fp32
-  // addition order of a light row is still exactly the reference's (src/spmv/omp_base.cc:26-31).  The price is
-  // streaming col/Ax once per pass.
+  // Column passes (experiment, GDN_SPMV_PASSES=P): pass p gathers only the columns of window p (a prefix / middle /
+  // suffix of every sorted row) so that the window stays L2-resident; the other entries add +0.0f and y carries the
+  // running sum from pass to pass -- the fp32 addition order of a light row is still exactly the reference's
+  // (src/spmv/omp_base.cc:26-31).  Measured (profiles/r1_spmv_column_passes.txt): urand-24 3.16 -> 3.03 ms at P=2,
+  // slower everywhere else (col/Ax are streamed once per pass): the kernel is not bound by the gather's L2 misses.
+  // Default: one pass.
   const char *e_pass = getenv("GDN_SPMV_PASSES"), *e_win = getenv("GDN_SPMV_WINDOW_MB");
   const int64_t win_ids = (int64_t)(e_win ? atoi(e_win) : 40) * (1 << 20) / 4;
-  int passes = e_pass ? atoi(e_pass) : (int)std::min<int64_t>(4, (g->m + win_ids - 1) / win_ids);
+  int passes = e_pass ? atoi(e_pass) : (e_win ? (int)std::min<int64_t>(4, (g->m + win_ids - 1) / win_ids) : 1);
   if (passes < 1 || !legacy) passes = 1;
   a.col_lo = 0; a.col_hi = 0x7fffffff;
   kev_begin();

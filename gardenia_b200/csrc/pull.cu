@@ -504,6 +504,179 @@ pr_sell_kernel(SellArgs a) {
   if (lane == 0) a.err_partial[a.err_slot0 + warp] = err;
 }
 
+// ------------------------------------------------------------------ the pipelined iteration kernel
+// pr_sell_kernel above keeps ONE trip (16 gathers per lane) in flight and then waits for it.  Measured
+// (profiles/r1_pr_tier_probe.txt): its time is the SUM of a 3.3 ms "stream + shared-table" floor and the L2-tier
+// gathers at exactly the 1 sector/clk/SM miss-path rate -- the two never overlap, because all warps of an SM queue
+// their gathers behind each other, drain together, and then wait together for the next index groups (a convoy; L1TEX
+// 53 % busy).  Here a warp's work is flattened into one sequence of trips that crosses slice and item boundaries, and
+// the loop is software-pipelined two trips deep:
+//      request index groups of trip t+2  |  issue the gathers of trip t+1  |  add the values of trip t
+// so the L1TEX miss path always holds gathers of this warp while it waits, adds and runs epilogues.  The row epilogue's
+// inputs (old score, degree) are requested with the last trip of their slice.  The per-row addition order is unchanged
+// (column order, sequential fp32): results are bit-identical to pr_sell_kernel.
+struct TripDesc {
+  uint32_t g;      // first int4 unit of the trip (lane 0's)
+  int32_t n;       // index groups per lane (0: this warp has no work left)
+  int32_t fin;     // 1: last trip of a light slice (ref = slice), 2: last trip of a wide-slice segment (ref = item), 0: neither
+  int32_t ref;
+};
+
+template <int G>
+struct TripIter {
+  const SellArgs &a;
+  int32_t item, nwarps;           // work items of one GPU fit 31 bits (checked by pr_run_sell)
+  int32_t s, s_end, sa;
+  uint32_t g, g_end, lo, hi;      // lo/hi: slice_ptr[sa + lane], slice_ptr[sa + lane + 1] of the current chunk
+  int32_t kind, ref;
+  int lane;
+  __device__ __forceinline__ TripIter(const SellArgs &a_, int32_t warp, int32_t nwarps_, int lane_)
+      : a(a_), item(warp - nwarps_), nwarps(nwarps_), s(0), s_end(0), sa(0),
+        g(0), g_end(0), lo(0), hi(0), kind(0), ref(0), lane(lane_) {}
+  __device__ __forceinline__ void load_bounds() {
+    lo = a.slice_ptr[min(sa + lane, s_end)];
+    hi = a.slice_ptr[min(sa + lane + 1, s_end)];
+  }
+  __device__ __forceinline__ TripDesc next() {
+    for (;;) {
+      if (g < g_end) {
+        TripDesc d;
+        const uint32_t left = (g_end - g) >> 5;
+        d.g = g;
+        d.n = left < (uint32_t)G ? (int32_t)left : G;
+        g += (uint32_t)d.n << 5;
+        d.fin = g >= g_end ? kind : 0;
+        d.ref = ref;
+        return d;
+      }
+      if (s < s_end) {
+        if (s - sa >= 32) { sa = s; load_bounds(); }
+        const uint32_t g0 = __shfl_sync(kFull, lo, s - sa), g1 = __shfl_sync(kFull, hi, s - sa);
+        ref = s;
+        s++;
+        if (g1 - g0 > (uint32_t)kGroupCh) continue;          // wide slice: handled as segments
+        g = g0; g_end = g1; kind = 1;
+        continue;
+      }
+      item += nwarps;
+      if (item >= a.n_chunks + a.n_heavy_segs || item < 0) { item = 0x7fffffff - nwarps; TripDesc d; d.g = 0; d.n = 0; d.fin = 0; d.ref = 0; return d; }
+      if (item < a.n_heavy_segs) {
+        const int2 hs = a.heavy_seg[item];
+        const uint32_t s0 = a.slice_ptr[hs.x], s1 = a.slice_ptr[hs.x + 1];
+        g = s0 + (uint32_t)hs.y * kGroupCh;
+        g_end = (s1 - g > (uint32_t)kGroupCh) ? g + kGroupCh : s1;
+        kind = 2; ref = item; s = s_end = 0;
+      } else {
+        const int32_t k = item - a.n_heavy_segs;
+        sa = a.chunk_slice[k]; s = sa; s_end = a.chunk_slice[k + 1];
+        load_bounds();
+        g = g_end = 0;
+      }
+    }
+  }
+};
+
+__device__ __forceinline__ void pr_epilogue_pre(const SellArgs &a, int64_t j, float acc, double &err, float old_score, int32_t deg) {
+  const float nw = __fadd_rn(a.base, __fmul_rn(a.damp, acc));
+  __stcs(a.scores + j, nw);
+  err += (double)fabsf(__fsub_rn(nw, old_score));
+  const int64_t id = row_newid(a, j);
+  const float cv = __fdiv_rn(nw, (float)deg);
+  if (id < a.warm) a.contrib_out[id] = cv; else __stcs(a.contrib_out + id, cv);
+}
+
+// G index groups (4 G gathers) per lane and trip, D trips of gathers in flight per warp, THREADS / 32 warps per SM.
+template <int POLICY, int G, int D, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+pr_sell_pipe(SellArgs a) {
+  extern __shared__ float s_hot[];
+  if (*a.done) return;
+  for (int i = threadIdx.x; i < a.H; i += THREADS) s_hot[i] = a.contrib_in[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int32_t warp = (int32_t)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
+  const int32_t nwarps = (int32_t)gridDim.x * (THREADS / 32);
+  const uint64_t pol = l2_policy_evict_first(), pol_last = l2_policy_evict_last();
+  const uint32_t s_hot_addr = (uint32_t)__cvta_generic_to_shared(s_hot);
+  const int32_t *degs = a.sout ? a.sout : a.sdeg;
+  double err = 0.0;
+  float acc = 0.f;
+  TripIter<G> it(a, warp, nwarps, lane);
+  int4 I[2][G];              // index groups: requested one step before their gathers are issued
+  float V[D][4 * G];         // gathered values of the D trips in flight
+  float S[D];                // old score / degree of the row a trip finishes (requested with its gathers)
+  int32_t Dg[D];
+  // a trip in flight is remembered as {fin | 4 * (n != 0), ref}
+  int32_t dflag[D], dref[D];
+  TripDesc dnext;
+#pragma unroll
+  for (int i = 0; i < D; i++) { S[i] = 0.f; Dg[i] = 1; dflag[i] = 0; dref[i] = 0; }
+
+  auto load_idx = [&](int4 (&X)[G], const TripDesc &d) {
+    const int4 *p = a.sell + d.g + lane;
+#pragma unroll
+    for (int u = 0; u < G; u++) X[u] = u < d.n ? ld_stream_v4(p + 32 * u, pol) : make_int4(-1, -1, -1, -1);
+  };
+  auto gather = [&](float (&W)[4 * G], const int4 (&X)[G], const TripDesc &d, float &Sc, int32_t &Dc) {
+#pragma unroll
+    for (int u = 0; u < G; u++) {
+      W[4 * u + 0] = pull_one<POLICY>(a, s_hot_addr, s_hot, X[u].x, pol, pol_last);
+      W[4 * u + 1] = pull_one<POLICY>(a, s_hot_addr, s_hot, X[u].y, pol, pol_last);
+      W[4 * u + 2] = pull_one<POLICY>(a, s_hot_addr, s_hot, X[u].z, pol, pol_last);
+      W[4 * u + 3] = pull_one<POLICY>(a, s_hot_addr, s_hot, X[u].w, pol, pol_last);
+    }
+    if (d.fin == 1) {
+      const int64_t j = (int64_t)d.ref * 32 + lane;
+      if (j < a.n_nz_rows) { Sc = __ldcs(a.scores + j); Dc = __ldcs(degs + j); }
+    }
+  };
+  auto consume = [&](const float (&W)[4 * G], int32_t flag, int32_t ref, float Sc, int32_t Dc) {
+#pragma unroll
+    for (int q = 0; q < 4 * G; q++) acc = __fadd_rn(acc, W[q]);
+    if ((flag & 3) == 1) {
+      const int64_t j = (int64_t)ref * 32 + lane;
+      if (j < a.n_nz_rows) pr_epilogue_pre(a, j, acc, err, Sc, Dc);
+      acc = 0.f;
+    } else if ((flag & 3) == 2) {
+      a.partial[(size_t)ref * 32 + lane] = acc;
+      acc = 0.f;
+    }
+  };
+
+  dnext = it.next();
+  if (dnext.n) {
+    load_idx(I[0], dnext);
+    // fill: trips 0 .. D-2
+#pragma unroll
+    for (int i = 0; i < D - 1; i++) {
+      const TripDesc d = dnext;
+      dnext = it.next();
+      load_idx(I[(i + 1) & 1], dnext);
+      gather(V[i], I[i & 1], d, S[i], Dg[i]);
+      dflag[i] = d.fin | (d.n ? 4 : 0); dref[i] = d.ref;
+    }
+    // steady state, unrolled so that every register array index is a constant: step k issues the gathers of trip
+    // base + D-1 + k and adds the values of trip base + k
+    constexpr int U = (D % 2 == 0) ? D : 2 * D;
+    for (;;) {
+      bool stop = false;
+#pragma unroll
+      for (int k = 0; k < U; k++) {
+        const TripDesc d = dnext;
+        dnext = it.next();
+        load_idx(I[(D + k) & 1], dnext);
+        gather(V[(D - 1 + k) % D], I[(D - 1 + k) & 1], d, S[(D - 1 + k) % D], Dg[(D - 1 + k) % D]);
+        dflag[(D - 1 + k) % D] = d.fin | (d.n ? 4 : 0); dref[(D - 1 + k) % D] = d.ref;
+        consume(V[k % D], dflag[k % D], dref[k % D], S[k % D], Dg[k % D]);
+        if (!dflag[(k + 1) % D]) { stop = true; break; }
+      }
+      if (stop) break;
+    }
+  }
+  err = warp_sum(err);
+  if (lane == 0) a.err_partial[a.err_slot0 + warp] = err;
+}
+
 // wide slices: one warp per slice adds the per-row partials of its segments in column order
 __global__ void __launch_bounds__(256, 4)
 pr_sell_finalize(SellArgs a) {
@@ -599,7 +772,7 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
   GDN_CHECK(pull_build_sell(g));
   cudaStream_t s = lib().stream;
   const int sm = lib().sm_count;
-  const int wpc = kSellThreads / 32;
+  const int wpc = kSellThreads / 32;             // err_partial slots per CTA (the pipelined variants use fewer warps)
   const int fgrid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)L.n_heavy_slices + 7) / 8, (int64_t)sm * 4));
   const int igrid = (int)std::max<int64_t>(1, std::min<int64_t>((L.rows - L.n_nz_rows + 255) / 256, (int64_t)sm * 8));
   const int n_partial = sm * wpc + fgrid * 8 + igrid * 8;
@@ -629,6 +802,28 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
   const int policy = e_pol ? atoi(e_pol) : 1;
   const int64_t warm_ids = (int64_t)(e_warm ? atoi(e_warm) : 48) * (1 << 20) / 4;   // 48 MB measured best at Kron-26 (32: +4 %, 64: +5 %, 96: +17 %)
   void (*kern)(SellArgs) = policy == 0 ? pr_sell_kernel<0> : policy == 2 ? pr_sell_kernel<2> : pr_sell_kernel<1>;
+  int threads = kSellThreads;
+  // GDN_PR_PIPE: 0 = one-trip kernel above; GDT = pipelined kernel, G index groups per trip, D trips in flight, T threads per SM
+  const char *e_pipe = getenv("GDN_PR_PIPE");
+  const int pipe = e_pipe ? atoi(e_pipe) : 121024;
+  if (policy == 1 && pipe != 0) {
+    switch (pipe) {     // GDT
+      case 22512: kern = pr_sell_pipe<1, 2, 2, 512>; threads = 512; break;
+      case 22640: kern = pr_sell_pipe<1, 2, 2, 640>; threads = 640; break;
+      case 22896: kern = pr_sell_pipe<1, 2, 2, 896>; threads = 896; break;
+      case 221024: kern = pr_sell_pipe<1, 2, 2, 1024>; threads = 1024; break;
+      case 42512: kern = pr_sell_pipe<1, 4, 2, 512>; threads = 512; break;
+      case 23768: kern = pr_sell_pipe<1, 2, 3, 768>; threads = 768; break;
+      case 23640: kern = pr_sell_pipe<1, 2, 3, 640>; threads = 640; break;
+      case 24512: kern = pr_sell_pipe<1, 2, 4, 512>; threads = 512; break;
+      case 131024: kern = pr_sell_pipe<1, 1, 3, 1024>; threads = 1024; break;
+      case 141024: kern = pr_sell_pipe<1, 1, 4, 1024>; threads = 1024; break;
+      case 13896: kern = pr_sell_pipe<1, 1, 3, 896>; threads = 896; break;
+      case 14768: kern = pr_sell_pipe<1, 1, 4, 768>; threads = 768; break;
+      case 22768: kern = pr_sell_pipe<1, 2, 2, 768>; threads = 768; break;
+      default: kern = pr_sell_pipe<1, 1, 2, 1024>; threads = 1024; break;   // measured best of the sweep (profiles/r1_pr_pipe_sweep.txt)
+    }
+  }
   const char *e_persist = getenv("GDN_PR_PERSIST");
   const int persist_mb = e_persist ? atoi(e_persist) : 0;
   const bool persist = persist_mb > 0;
@@ -679,7 +874,7 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
       GDN_CUDA(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av));
     }
     kev_begin();
-    kern<<<sm, kSellThreads, smem, s>>>(a);
+    kern<<<sm, threads, smem, s>>>(a);
     kev_end();
     launches++;
     if (persist) {
