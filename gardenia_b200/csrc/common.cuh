@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <vector>
 #include "../../include/gdn_b200.h"
 
 namespace gdn {
@@ -16,9 +17,15 @@ struct Lib {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // chunked host->device copies that kernels on `stream` consume chunk by chunk
+  bool stream_fill = false;             // hint set by the one-shot PageRank entry point: build the pull layout WHILE the CSR uploads
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   void *pinned = nullptr;          // small pinned mailbox for per-step counters
   size_t pinned_bytes = 0;
+  // grow-only page-locked scratch of the layout preprocessing (degree array, row order): no page faults on reuse, and
+  // the order goes to the device at full PCIe rate without a bounce buffer
+  void *arena[2] = {nullptr, nullptr};
+  size_t arena_bytes[2] = {0, 0};
   // event pairs bracketing each launch of the dominant kernel of a solve
   static constexpr int kMaxKev = 512;
   cudaEvent_t kev[2 * kMaxKev] = {};
@@ -38,6 +45,7 @@ inline void kev_collect(gdn_stats *st) {
   st->kernel_calls = l.n_kev;
 }
 Lib &lib();
+void *host_arena(int slot, size_t bytes);      // graph.cu; nullptr when page-locking fails (callers fall back to malloc)
 int ensure_init();
 // GDN_TRACE=1: wall-clock stage timings of the upload / preprocessing path on stderr
 void trace(const char *label);
@@ -135,7 +143,16 @@ struct gdn_graph {
   void *counters = nullptr;          // BfsCounters on device
   int64_t n_words = 0;               // bitmap words (32-bit), padded to a multiple of 32
   int64_t bm_alloc_words = 0;        // allocated words per bitmap (>= n_words; room for the allgather slices)
+  // chunked upload of the pull CSR's column array (graph.cu upload_csr_begin): col_ev[k] fires when entries
+  // [0, col_end[k]) are resident.  Transient: consumed by pull_prepare / upload_csr_end.
+  std::vector<cudaEvent_t> col_ev;
+  std::vector<uint64_t> col_end;
+  int *col_flag = nullptr;           // device verdict word shared with validate_csr (3 = column index out of range)
+  const int32_t *col_host = nullptr; // pieces not queued yet: host source, device destination, next entry, end
+  int32_t *col_dev = nullptr;
+  uint64_t col_next = 0, col_total = 0;
 };
+namespace gdn { int col_upload_rest(gdn_graph *g); }   // graph.cu: queue the remaining pieces of the column array
 
 namespace gdn {
 

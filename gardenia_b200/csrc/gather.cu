@@ -360,6 +360,185 @@ spmv_tma_kernel(const OffT *__restrict__ rowptr, const int32_t *__restrict__ col
   }
 }
 
+
+// ---------------------------------------------------------------- SpMV, software-pipelined (default: 384 threads x 2 CTAs per SM)
+// Same schedule and the same arithmetic as gather_kernel<., kModeSpmv> (products staged per warp, one lane per light
+// row adds them in the reference's order; heavy segments -> partials), different issue order.  gather_kernel lets a
+// warp wait for its column/value loads, then for its gathers, then sum rows: with every warp of an SM in the same
+// phase the L1TEX miss path idles between bursts (the convoy measured on PageRank, profiles/r1_pr_tier_probe.txt).
+// Here a warp's work is one flat sequence of 128-entry trips that crosses item boundaries, three trips deep:
+//      stream loads of trip n+1  |  x gathers of trip n  |  products of trip n-1 -> shared memory (+ row sums at item end)
+// and the descriptors of the next two items (chunk_row -> rowptr chains) are prefetched as raw values, so an item
+// boundary costs no dependent-load stall.
+template <typename OffT>
+struct SpTrip {
+  OffT tb;              // first entry of the trip (multiple of 4)
+  OffT b, e;            // entry range of the item it belongs to
+  int32_t r0, r1;       // light block rows [r0, r1), or {heavy segment index, -1}
+  int32_t flags;        // 1 valid, 2 last trip of its item
+};
+
+template <typename OffT>
+struct SpGen {
+  const OffT *__restrict__ rowptr;
+  const GatherArgs &a;
+  int64_t n_items, nwarps;
+  // item being cut into trips
+  OffT b, e, tb;
+  int32_t r0, r1;
+  bool have;
+  // level B: item k+1, offsets requested;  level A: item k+2, ids requested
+  int64_t itB, itA;
+  int32_t xB0, xB1, xA0, xA1;
+  OffT vB0, vB1, vB2;
+
+  __device__ __forceinline__ SpGen(const OffT *rp, const GatherArgs &a_, int64_t warp, int64_t nwarps_)
+      : rowptr(rp), a(a_), n_items((int64_t)a_.n_chunks + a_.n_heavy_segs), nwarps(nwarps_), b(0), e(0), tb(0), r0(0), r1(0),
+        have(false), itB(warp - nwarps_), itA(warp - nwarps_), xB0(0), xB1(0), xA0(0), xA1(0), vB0(0), vB1(0), vB2(0) {
+    loadA(warp);             // A <- first item
+    shift(warp + nwarps_);   // B <- first item (offsets requested), A <- second
+    take();                  // current <- first non-empty item
+  }
+  __device__ __forceinline__ void loadA(int64_t it) {
+    itA = it;
+    if (it < a.n_chunks) { xA0 = __ldcs(a.chunk_row + it); xA1 = __ldcs(a.chunk_row + it + 1); }
+    else if (it < n_items) { const int2 hs = a.heavy_seg[it - a.n_chunks]; xA0 = hs.x; xA1 = hs.y; }
+  }
+  // B <- A (request its offsets), A <- item `it_next`
+  __device__ __forceinline__ void shift(int64_t it_next) {
+    itB = itA; xB0 = xA0; xB1 = xA1;
+    if (itB < a.n_chunks) {
+      if (xB1 > xB0) { vB0 = rowptr[xB0]; vB1 = rowptr[xB1 - 1]; vB2 = rowptr[xB1]; }
+    } else if (itB < n_items) {
+      vB0 = rowptr[xB0]; vB1 = rowptr[xB0 + 1];
+    }
+    loadA(it_next);
+  }
+  // current <- B, skipping empty light blocks
+  __device__ __forceinline__ void take() {
+    for (;;) {
+      if (itB >= n_items) { have = false; return; }
+      bool ok;
+      if (itB < a.n_chunks) {
+        r0 = xB0; r1 = xB1;
+        ok = r1 > r0;
+        if (ok) {
+          const bool dec = (vB2 - vB1) > (OffT)kChunk;          // heavy last row: handled as segments
+          if (dec) r1--;
+          ok = r1 > r0;
+          b = vB0; e = dec ? vB1 : vB2;
+        }
+      } else {
+        r0 = (int32_t)(itB - a.n_chunks); r1 = -1;
+        b = vB0 + (OffT)xB1 * (OffT)kSeg;
+        e = (vB1 - b > (OffT)kSeg) ? b + (OffT)kSeg : vB1;
+        ok = true;
+      }
+      shift(itA + nwarps);
+      if (ok && e > b) { tb = b & ~(OffT)3; have = true; return; }
+    }
+  }
+  __device__ __forceinline__ SpTrip<OffT> next() {
+    SpTrip<OffT> t;
+    t.tb = tb; t.b = b; t.e = e; t.r0 = r0; t.r1 = r1; t.flags = have ? 1 : 0;
+    if (have) {
+      tb += 128;
+      if (tb >= e) { t.flags |= 2; take(); }
+    }
+    return t;
+  }
+};
+
+template <typename OffT, int THREADS, int CTAS>
+__global__ void __launch_bounds__(THREADS, CTAS)
+spmv_pipe(const OffT *__restrict__ rowptr, const int32_t *__restrict__ col, GatherArgs a) {
+  extern __shared__ __align__(16) float s_stage[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t warp = (int64_t)blockIdx.x * (THREADS / 32) + wib, nwarps = (int64_t)gridDim.x * (THREADS / 32);
+  float *sv = s_stage + (size_t)wib * kCap;
+  const uint64_t pol_x = l2_policy_evict_last(), pol_s = l2_policy_evict_first();
+  SpGen<OffT> gen(rowptr, a, warp, nwarps);
+
+  int4 q1; float4 x1;                 // trip n+1: column ids, matrix values
+  float4 x0; float g0[4];             // trip n  : matrix values, gathered x
+  float4 xm; float gm[4];             // trip n-1
+  SpTrip<OffT> t1, t0, tm;
+  float hacc = 0.f;
+  t0.flags = 0; tm.flags = 0;
+  x0 = make_float4(0.f, 0.f, 0.f, 0.f); xm = x0; x1 = x0; q1 = make_int4(0, 0, 0, 0);
+#pragma unroll
+  for (int u = 0; u < 4; u++) { g0[u] = 0.f; gm[u] = 0.f; }
+
+  auto stream = [&](const SpTrip<OffT> &t) {
+    if (!(t.flags & 1)) return;
+    const uint64_t i = (uint64_t)t.tb + 4ull * lane;
+    if (i < (uint64_t)t.e) {
+      q1 = ld_stream_v4(reinterpret_cast<const int4 *>(col + i), pol_s);       // col has 256 B of slack past nnz
+      if (i + 4 <= a.nnz) {
+        const int4 r = ld_stream_v4(reinterpret_cast<const int4 *>(a.Ax + i), pol_s);
+        x1 = make_float4(__int_as_float(r.x), __int_as_float(r.y), __int_as_float(r.z), __int_as_float(r.w));
+      } else {
+        x1.x = i < a.nnz ? a.Ax[i] : 0.f; x1.y = i + 1 < a.nnz ? a.Ax[i + 1] : 0.f;
+        x1.z = i + 2 < a.nnz ? a.Ax[i + 2] : 0.f; x1.w = 0.f;
+      }
+    }
+  };
+  auto gather = [&](const SpTrip<OffT> &t, const int4 &q) {
+    const OffT i = t.tb + (OffT)(4 * lane);
+    const int c[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      g0[u] = 0.f;
+      if ((t.flags & 1) && i + u >= t.b && i + u < t.e) g0[u] = ld_gather_f32(a.vec + c[u], pol_x);
+    }
+  };
+  auto consume = [&](const SpTrip<OffT> &t) {
+    if (!(t.flags & 1)) return;
+    const OffT a0 = t.b & ~(OffT)3;
+    const OffT i = t.tb + (OffT)(4 * lane);
+    const float p0 = __fmul_rn(gm[0], xm.x), p1 = __fmul_rn(gm[1], xm.y), p2 = __fmul_rn(gm[2], xm.z), p3 = __fmul_rn(gm[3], xm.w);
+    if (t.r1 >= 0) {
+      if (i < t.e) *reinterpret_cast<float4 *>(sv + (i - a0)) = make_float4(p0, p1, p2, p3);
+      if (t.flags & 2) {
+        __syncwarp();
+        for (int32_t r = t.r0 + lane; r < t.r1; r += 32) {
+          const int32_t s = (int32_t)(rowptr[r] - a0), e = (int32_t)(rowptr[r + 1] - a0);
+          float acc = __ldcs(a.y + r);
+          for (int32_t j = s; j < e; j++) acc = __fadd_rn(acc, sv[j]);
+          __stcs(a.y + r, acc);
+        }
+        __syncwarp();
+      }
+    } else {
+      // entries outside [b, e) add +0.0f (their value slots hold a neighbouring row's entries)
+      const float m0 = (i >= t.b && i < t.e) ? p0 : 0.f, m1 = (i + 1 >= t.b && i + 1 < t.e) ? p1 : 0.f;
+      const float m2 = (i + 2 >= t.b && i + 2 < t.e) ? p2 : 0.f, m3 = (i + 3 >= t.b && i + 3 < t.e) ? p3 : 0.f;
+      hacc += (m0 + m1) + (m2 + m3);
+      if (t.flags & 2) {
+        const float tot = warp_sum(hacc);
+        if (lane == 0) a.heavy_partial[t.r0] = tot;
+        hacc = 0.f;
+      }
+    }
+  };
+
+  t1 = gen.next();
+  stream(t1);
+  for (;;) {
+    // rotate: n+1 -> n -> n-1
+    tm = t0; xm = x0;
+#pragma unroll
+    for (int u = 0; u < 4; u++) gm[u] = g0[u];
+    t0 = t1; x0 = x1;
+    const int4 q0 = q1;
+    t1 = gen.next();
+    stream(t1);
+    gather(t0, q0);
+    consume(tm);
+    if (!(t0.flags & 1) && !(tm.flags & 1)) break;
+  }
+}
+
 // contrib[v] = scores[v] / out_degree(v)  (src/pr/omp_base.cc:24-25) for the local rows.
 template <typename OffT>
 __global__ void pr_init_contrib(const OffT *__restrict__ rowptr, const int32_t *__restrict__ out_degree,
@@ -517,8 +696,27 @@ static int spmv_t(gdn_graph *g, const float *d_Ax, const float *d_x, float *d_y,
   int passes = e_pass ? atoi(e_pass) : (e_win ? (int)std::min<int64_t>(4, (g->m + win_ids - 1) / win_ids) : 1);
   if (passes < 1 || !legacy) passes = 1;
   a.col_lo = 0; a.col_hi = 0x7fffffff;
+  // GDN_SPMV_PIPE: 0 = gather_kernel (one trip at a time); 10*T + C = spmv_pipe with T threads per CTA, C CTAs per SM
+  const char *e_pipe = getenv("GDN_SPMV_PIPE");
+  const int pipe = (legacy && passes == 1) ? (e_pipe ? atoi(e_pipe) : 3842) : 0;
   kev_begin();
-  if (legacy) {
+  if (pipe) {
+    // measured on urand-24 (profiles/r1_spmv_pipe_sweep.txt): 24 warps per SM at 76-80 registers win; 32 warps force 64
+    // registers and spill (4.2 ms), 16 warps are short of gathers in flight (2.8 ms)
+    void (*kern)(const OffT *, const int32_t *, GatherArgs) = spmv_pipe<OffT, 384, 2>;
+    int threads = 384, ctas = 2;
+    switch (pipe) {
+      case 10241: kern = spmv_pipe<OffT, 1024, 1>; threads = 1024; ctas = 1; break;
+      case 5122: kern = spmv_pipe<OffT, 512, 2>; threads = 512; ctas = 2; break;
+      case 2563: kern = spmv_pipe<OffT, 256, 3>; threads = 256; ctas = 3; break;
+      case 2562: kern = spmv_pipe<OffT, 256, 2>; threads = 256; ctas = 2; break;     // 128 registers
+      case 2564: kern = spmv_pipe<OffT, 256, 4>; threads = 256; ctas = 4; break;
+      default: break;
+    }
+    const size_t smem = sizeof(float) * (size_t)kCap * (threads / 32);
+    GDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<lib().sm_count * ctas, threads, smem, s>>>(rp, c.col, a);
+  } else if (legacy) {
     for (int p = 0; p < passes; p++) {
       a.col_lo = (int32_t)(g->m * p / passes);
       a.col_hi = p + 1 == passes ? 0x7fffffff : (int32_t)(g->m * (p + 1) / passes);

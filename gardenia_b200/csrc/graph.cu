@@ -38,6 +38,34 @@ int ensure_init() {
   return gdn_init(0);
 }
 
+void *host_arena(int slot, size_t bytes) {
+  Lib &l = lib();
+  if (l.arena_bytes[slot] >= bytes) return l.arena[slot];
+  if (l.arena[slot]) cudaFreeHost(l.arena[slot]);
+  l.arena[slot] = nullptr; l.arena_bytes[slot] = 0;
+  const size_t want = bytes + bytes / 8;
+  if (cudaHostAlloc(&l.arena[slot], want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); l.arena[slot] = nullptr; return nullptr; }
+  l.arena_bytes[slot] = want;
+  return l.arena[slot];
+}
+
+// Queue the pieces of a chunked column upload that upload_csr_begin held back (see there).
+int col_upload_rest(gdn_graph *g) {
+  cudaStream_t cs = lib().copy_stream;
+  const uint64_t piece = 64ull << 20;                    // entries (multiple of 1024)
+  while (g->col_next < g->col_total) {
+    const uint64_t e0 = g->col_next, e1 = std::min<uint64_t>(g->col_total, e0 + piece);
+    GDN_CUDA(cudaMemcpyAsync(g->col_dev + e0, g->col_host + e0, sizeof(int32_t) * (e1 - e0), cudaMemcpyHostToDevice, cs));
+    cudaEvent_t ev;
+    GDN_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    GDN_CUDA(cudaEventRecord(ev, cs));
+    g->col_ev.push_back(ev);
+    g->col_end.push_back(e1);
+    g->col_next = e1;
+  }
+  return GDN_OK;
+}
+
 int build_schedule(gdn_graph *g, DevCsr &c);
 template <typename HostOffT>
 int pull_prepare(gdn_graph *g, const HostOffT *row_off, const HostOffT *key_off);   // pull.cu
@@ -61,12 +89,13 @@ __global__ void row_lengths(const OffT *__restrict__ rp, int32_t *__restrict__ d
 // Checks monotone offsets and 0 <= col < m; flag[0] != 0 on violation.
 template <typename OffT>
 __global__ void validate_csr(const OffT *__restrict__ rp, const int32_t *__restrict__ col, int64_t rows,
-                             uint64_t nnz, int64_t m, int *flag) {
+                             uint64_t nnz, int64_t m, int *flag, bool check_cols) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nth = (int64_t)gridDim.x * blockDim.x;
   for (int64_t r = tid; r < rows; r += nth)
     if (rp[r] > rp[r + 1]) atomicExch(flag, 1);
   if (tid == 0 && (rp[0] != 0 || (uint64_t)rp[rows] != nnz)) atomicExch(flag, 2);
+  if (!check_cols) return;                 // the streaming layout build checks every column id as it consumes it
   for (uint64_t e = tid; e < nnz; e += nth) {
     const int32_t c = col[e];
     if (c < 0 || c >= m) atomicExch(flag, 3);
@@ -81,6 +110,7 @@ struct PendingUpload {
   int *flag = nullptr;
   int *h_flag = nullptr;      // slot in the pinned mailbox
   bool want_schedule = false;
+  bool chunked = false;       // column array copied piecewise on the copy stream (gdn_graph::col_ev)
 };
 
 template <typename HostOffT>
@@ -104,23 +134,64 @@ static int upload_csr_begin(gdn_graph *g, DevCsr &c, const HostOffT *h_rowptr, c
   const int grid = (int)std::min<int64_t>((c.rows + 256) / 256, (int64_t)lib().sm_count * 8);
   if (c.off64) convert_offsets<HostOffT, uint64_t><<<grid, 256, 0, st>>>(tmp, (uint64_t *)c.rowptr, c.rows + 1, base);
   else convert_offsets<HostOffT, uint32_t><<<grid, 256, 0, st>>>(tmp, (uint32_t *)c.rowptr, c.rows + 1, base);
-  GDN_CUDA(cudaMemcpyAsync(c.col, h_col + base, sizeof(int32_t) * c.nnz, cudaMemcpyHostToDevice, st));
-  GDN_CUDA(cudaMemsetAsync((char *)c.col + sizeof(int32_t) * c.nnz, 0, 256, st));
   GDN_CUDA(cudaMalloc((void **)&pu.flag, sizeof(int)));
   GDN_CUDA(cudaMemsetAsync(pu.flag, 0, sizeof(int), st));
+  GDN_CUDA(cudaMemsetAsync((char *)c.col + sizeof(int32_t) * c.nnz, 0, 256, st));
+  const bool chunked = lib().stream_fill && want_schedule && c.nnz > 0;
+  if (chunked) {
+    // One-shot PageRank: the column array crosses PCIe in 256 MB pieces on the copy stream, one event per piece, and
+    // pull_prepare launches the layout build piece by piece behind them (pull.cu sell_scatter).
+    cudaStream_t cs = lib().copy_stream;
+    cudaEvent_t ready;
+    GDN_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    GDN_CUDA(cudaEventRecord(ready, st));                 // allocations / memsets above are ordered before the copies
+    GDN_CUDA(cudaStreamWaitEvent(cs, ready, 0));
+    GDN_CUDA(cudaEventDestroy(ready));
+    // Copies execute in issue order on the one host->device engine, whatever their stream: the row order that the
+    // host computes meanwhile (pull_prepare, ~1 ns per vertex) would queue behind EVERY piece issued now and the build
+    // could not start before the whole array is in.  So only ~64 bytes per vertex of pieces go now -- about the time
+    // the host needs -- and pull_prepare issues the rest right after its own uploads (col_upload_rest).
+    const uint64_t piece = 64ull << 20;                    // entries (multiple of 1024)
+    const uint64_t first = std::min<uint64_t>(c.nnz, std::max<uint64_t>(piece, ((uint64_t)g->m * 16 + piece - 1) / piece * piece));
+    g->col_host = h_col + base; g->col_dev = c.col; g->col_next = 0; g->col_total = first;
+    GDN_CHECK(col_upload_rest(g));
+    g->col_total = c.nnz;
+    g->col_flag = pu.flag;
+  } else {
+    GDN_CUDA(cudaMemcpyAsync(c.col, h_col + base, sizeof(int32_t) * c.nnz, cudaMemcpyHostToDevice, st));
+  }
   const int vgrid = lib().sm_count * 8;
-  if (c.off64) validate_csr<uint64_t><<<vgrid, 256, 0, st>>>((const uint64_t *)c.rowptr, c.col, c.rows, c.nnz, g->m, pu.flag);
-  else validate_csr<uint32_t><<<vgrid, 256, 0, st>>>((const uint32_t *)c.rowptr, c.col, c.rows, c.nnz, g->m, pu.flag);
+  if (c.off64) validate_csr<uint64_t><<<vgrid, 256, 0, st>>>((const uint64_t *)c.rowptr, c.col, c.rows, c.nnz, g->m, pu.flag, !chunked);
+  else validate_csr<uint32_t><<<vgrid, 256, 0, st>>>((const uint32_t *)c.rowptr, c.col, c.rows, c.nnz, g->m, pu.flag, !chunked);
+  pu.chunked = chunked;
   pu.h_flag = (int *)((char *)lib().pinned + 1024) + slot;
   *pu.h_flag = 0;
-  GDN_CUDA(cudaMemcpyAsync(pu.h_flag, pu.flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (!chunked) GDN_CUDA(cudaMemcpyAsync(pu.h_flag, pu.flag, sizeof(int), cudaMemcpyDeviceToHost, st));   // chunked: read in _end, after the build
   pu.want_schedule = want_schedule;
   return GDN_OK;
 }
 
 static int upload_csr_end(gdn_graph *g, DevCsr &c, PendingUpload &pu) {
   if (!pu.flag) return GDN_OK;
+  if (pu.chunked) {
+    // every piece must have landed (and every layout kernel that consumed one has been queued on the stream)
+    GDN_CHECK(col_upload_rest(g));
+    for (cudaEvent_t ev : g->col_ev) { cudaStreamWaitEvent(lib().stream, ev, 0); }
+    GDN_CUDA(cudaMemcpyAsync(pu.h_flag, pu.flag, sizeof(int), cudaMemcpyDeviceToHost, lib().stream));
+  }
   GDN_CUDA(cudaStreamSynchronize(lib().stream));
+  if (pu.chunked) {
+    for (cudaEvent_t ev : g->col_ev) cudaEventDestroy(ev);
+    g->col_ev.clear(); g->col_end.clear(); g->col_flag = nullptr; g->col_host = nullptr; g->col_dev = nullptr;
+    if (!g->pull.sell && *pu.h_flag == 0) {
+      // the layout build did not run (no SELL layout for this graph): nobody has looked at the column ids yet
+      int *d_flag = pu.flag;
+      if (c.off64) validate_csr<uint64_t><<<lib().sm_count * 8, 256, 0, lib().stream>>>((const uint64_t *)c.rowptr, c.col, c.rows, c.nnz, g->m, d_flag, true);
+      else validate_csr<uint32_t><<<lib().sm_count * 8, 256, 0, lib().stream>>>((const uint32_t *)c.rowptr, c.col, c.rows, c.nnz, g->m, d_flag, true);
+      GDN_CUDA(cudaMemcpyAsync(pu.h_flag, pu.flag, sizeof(int), cudaMemcpyDeviceToHost, lib().stream));
+      GDN_CUDA(cudaStreamSynchronize(lib().stream));
+    }
+  }
   const int hflag = *pu.h_flag;
   cudaFree(pu.tmp);
   cudaFree(pu.flag);
@@ -130,7 +201,8 @@ static int upload_csr_end(gdn_graph *g, DevCsr &c, PendingUpload &pu) {
     set_error("malformed CSR (%s)", hflag == 1 ? "row offsets not monotone" : hflag == 2 ? "offset ends" : "column index out of range");
     return GDN_ERR_GRAPH;
   }
-  if (pu.want_schedule) GDN_CHECK(build_schedule(g, c));
+  // one-shot PageRank with its SELL layout already built: the row-block schedule of the plain CSR is never used
+  if (pu.want_schedule && !(lib().stream_fill && g->pull.sell)) GDN_CHECK(build_schedule(g, c));
   return GDN_OK;
 }
 
@@ -265,6 +337,7 @@ int gdn_init(int device) {
   l.device = device;
   l.sm_count = p.multiProcessorCount;
   GDN_CUDA(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+  GDN_CUDA(cudaStreamCreateWithFlags(&l.copy_stream, cudaStreamNonBlocking));
   GDN_CUDA(cudaEventCreate(&l.ev0));
   GDN_CUDA(cudaEventCreate(&l.ev1));
   for (int i = 0; i < 2 * Lib::kMaxKev; i++) GDN_CUDA(cudaEventCreate(&l.kev[i]));
@@ -279,10 +352,13 @@ int gdn_finalize(void) {
   if (!l.inited) return GDN_OK;
   cudaStreamSynchronize(l.stream);
   cudaStreamDestroy(l.stream);
+  cudaStreamSynchronize(l.copy_stream);
+  cudaStreamDestroy(l.copy_stream);
   cudaEventDestroy(l.ev0);
   cudaEventDestroy(l.ev1);
   for (int i = 0; i < 2 * Lib::kMaxKev; i++) cudaEventDestroy(l.kev[i]);
   cudaFreeHost(l.pinned);
+  for (int i = 0; i < 2; i++) if (l.arena[i]) cudaFreeHost(l.arena[i]);
   l = Lib();
   return GDN_OK;
 }
@@ -312,6 +388,7 @@ int gdn_graph_set_out_degree(gdn_graph *g, const int32_t *h_out_degree) {
 
 int gdn_graph_destroy(gdn_graph *g) {
   if (!g) return GDN_OK;
+  for (cudaEvent_t ev : g->col_ev) cudaEventDestroy(ev);
   if (g->symmetric) { free_csr(g->out); g->in = DevCsr(); }
   else { free_csr(g->out); free_csr(g->in); }
   cudaFree(g->contrib[0]); cudaFree(g->contrib[1]); cudaFree(g->out_degree); cudaFree(g->err_partial);

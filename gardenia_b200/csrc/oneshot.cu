@@ -79,12 +79,22 @@ int pr_oneshot(int64_t m, int64_t nnz, const OffT *irp, const int32_t *ici, cons
   if (!irp || !ici || !out_degree || !scores) { set_error("gdn_pagerank_pull: null argument"); return GDN_ERR_ARG; }
   GDN_CHECK(ensure_init());
   const double t0 = now_ms();
-  GraphGuard gg;
-  GDN_CHECK(create<OffT>(m, nnz, nullptr, nullptr, irp, ici, &gg.g));
-  GDN_CHECK(gdn_graph_set_out_degree(gg.g, out_degree));
-  DevBuf sc;
+  // the two small inputs go first (queued, not waited for); then the CSR, whose column array crosses PCIe in
+  // pieces with the PageRank layout built behind them (Lib::stream_fill, graph.cu / pull.cu)
+  DevBuf sc, od;
   GDN_CHECK(sc.alloc(sizeof(float) * m));
+  GDN_CHECK(od.alloc(sizeof(int32_t) * (m + 1)));
   GDN_CHECK(h2d(sc.p, scores, sizeof(float) * m));
+  GDN_CHECK(h2d(od.p, out_degree, sizeof(int32_t) * m));
+  GraphGuard gg;
+  lib().stream_fill = true;
+  const int rc = create<OffT>(m, nnz, nullptr, nullptr, irp, ici, &gg.g);
+  lib().stream_fill = false;
+  GDN_CHECK(rc);
+  gg.g->one_shot = true;
+  gg.g->out_degree = (int32_t *)od.p;      // the graph owns it from here (gdn_graph_destroy frees it)
+  od.p = nullptr;
+  gg.g->device_bytes += sizeof(int32_t) * (m + 1);
   GDN_CUDA(cudaStreamSynchronize(lib().stream));
   const double t1 = now_ms();
   gdn_stats local;

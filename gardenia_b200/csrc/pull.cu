@@ -126,6 +126,8 @@ __global__ void sdeg_from_perm(const OffT *__restrict__ rowptr, const int32_t *_
   }
 }
 
+static int pull_stream_fill(gdn_graph *g);     // below, next to the kernel it launches
+
 template <typename HostOffT>
 int pull_prepare(gdn_graph *g, const HostOffT *row_off, const HostOffT *key_off) {
   PullLayout &L = g->pull;
@@ -146,15 +148,18 @@ int pull_prepare(gdn_graph *g, const HostOffT *row_off, const HostOffT *key_off)
   L.symmetric_order = (key_off == row_off);
 
   trace("pull_prepare: begin");
-  RawBuf<int32_t> rdeg(m), kdeg;
-  if (!rdeg.p) { set_error("out of host memory"); return GDN_ERR_NOMEM; }
+  // degree array and row order live in the library's page-locked scratch (reused from call to call)
+  RawBuf<int32_t> rdeg_own, kdeg;
+  int32_t *rdeg = (int32_t *)host_arena(0, sizeof(int32_t) * (size_t)m);
+  if (!rdeg) { rdeg_own.alloc(m); rdeg = rdeg_own.data(); }
+  if (!rdeg) { set_error("out of host memory"); return GDN_ERR_NOMEM; }
   int64_t bad = 0;          // the device-side validation of these offsets is still in flight: do not index with garbage
 #pragma omp parallel for reduction(+ : bad)
   for (int64_t v = 0; v < m; v++) {
     rdeg[v] = (int32_t)(row_off[v + 1] - row_off[v]);
     bad += row_off[v + 1] < row_off[v];
   }
-  const int32_t *kd = rdeg.data();
+  const int32_t *kd = rdeg;
   if (!L.symmetric_order) {
     kdeg.alloc(m);
 #pragma omp parallel for reduction(+ : bad)
@@ -168,9 +173,12 @@ int pull_prepare(gdn_graph *g, const HostOffT *row_off, const HostOffT *key_off)
   // on one GPU of a symmetric graph the row order IS the column order: one sort, and newid / sdeg are
   // derived from it on the device (no 268 MB host scatter, no upload)
   const bool one_sort = L.symmetric_order && P == 1;
-  RawBuf<int32_t> perm(std::max<int64_t>(rows, 1)), newid, tmp, sdeg, rowid;
+  RawBuf<int32_t> perm_own, newid, tmp, sdeg, rowid;
+  int32_t *perm = (int32_t *)host_arena(1, sizeof(int32_t) * (size_t)std::max<int64_t>(rows, 1));
+  if (!perm) { perm_own.alloc(std::max<int64_t>(rows, 1)); perm = perm_own.data(); }
+  if (!perm) { set_error("out of host memory"); return GDN_ERR_NOMEM; }
   if (one_sort) {
-    sort_by_degree(kd, 0, m, perm.data());
+    sort_by_degree(kd, 0, m, perm);
   } else {
     newid.alloc(m); tmp.alloc(W); sdeg.alloc(std::max<int64_t>(rows, 1));
     for (int q = 0; q < P; q++) {
@@ -182,7 +190,7 @@ int pull_prepare(gdn_graph *g, const HostOffT *row_off, const HostOffT *key_off)
       for (int64_t j = 0; j < n; j++)
         newid[qlo + tmp[j]] = (int32_t)(j < L.Hp ? (int64_t)q * L.Hp + j : L.H + (int64_t)q * L.Wc + (j - L.Hp));
     }
-    if (rows > 0) sort_by_degree(rdeg.data(), lo, hi, perm.data(), sdeg.data());
+    if (rows > 0) sort_by_degree(rdeg, lo, hi, perm, sdeg.data());
     if (!L.symmetric_order) {
       rowid.alloc(std::max<int64_t>(rows, 1));
 #pragma omp parallel for
@@ -242,7 +250,7 @@ int pull_prepare(gdn_graph *g, const HostOffT *row_off, const HostOffT *key_off)
 
   trace("pull_prepare: slices");
   cudaStream_t st = lib().stream;
-  GDN_CHECK(upload(g, &L.perm, perm.data(), (size_t)rows));
+  GDN_CHECK(upload(g, &L.perm, perm, (size_t)rows));
   if (one_sort) {
     // the device offsets were queued on this stream by upload_csr_begin, so they are ready for sdeg_from_perm
     GDN_CUDA(cudaMalloc((void **)&L.newid, sizeof(int32_t) * std::max<int64_t>(m, 4)));
@@ -267,7 +275,19 @@ int pull_prepare(gdn_graph *g, const HostOffT *row_off, const HostOffT *key_off)
     GDN_CUDA(cudaMalloc((void **)&L.partial, sizeof(float) * 32 * (size_t)L.n_heavy_segs));
     g->device_bytes += sizeof(float) * 32 * (size_t)L.n_heavy_segs;
   }
-  GDN_CUDA(cudaStreamSynchronize(st));      // host buffers die here
+  // one-shot PageRank: build the SELL array behind the pieces of the column upload still in flight
+  const bool stream_build = one_sort && !g->col_ev.empty() && L.n_slices > 0;
+  cudaEvent_t staged = nullptr;
+  if (stream_build) {
+    GDN_CUDA(cudaEventCreateWithFlags(&staged, cudaEventDisableTiming));
+    GDN_CUDA(cudaEventRecord(staged, st));  // the uploads above have left the host buffers once this fires
+    GDN_CHECK(col_upload_rest(g));          // the pieces upload_csr_begin held back so that the uploads above were not queued behind them
+    GDN_CHECK(pull_stream_fill(g));
+    GDN_CUDA(cudaEventSynchronize(staged));
+    GDN_CUDA(cudaEventDestroy(staged));
+  } else {
+    GDN_CUDA(cudaStreamSynchronize(st));    // host buffers die here
+  }
   GDN_CUDA(cudaGetLastError());
   trace("pull_prepare: uploaded");
   L.prepared = true;
@@ -325,6 +345,114 @@ sell_fill(const OffT *__restrict__ rowptr, const int32_t *__restrict__ col, cons
     for (uint32_t k0 = 0; k0 < w; k0 += 32)
       fill_tile<OffT>(col, newid, tiles[wib], b_l, d_l, k0, ngk, sell + slice_ptr[s], lane);
   }
+}
+
+
+// ------------------------------------------------------------------ device: streaming build of the SELL array
+// The one-shot entry point (oneshot.cu) pays for the layout inside the call, and sell_fill above needs the whole
+// column array resident before its first slice (44 ms at Kron-26, all of it waiting on 2.1 G random newid[]
+// lookups).  sell_scatter builds the same array from the CSR side instead, for any range [e0, e1) of non-zeros, so it
+// runs piece by piece BEHIND the PCIe copy of the column array (graph.cu upload_csr_begin, 256 MB pieces) and is hidden
+// by it.  A CTA owns 1024 consecutive non-zeros: two binary searches bound the rows they belong to, the offsets of
+// those rows are staged in shared memory, every thread locates the row of its four entries there and writes
+//     sell[slice_ptr[j / 32] * 4 + (k / 4) * 128 + (j % 32) * 4 + k % 4] = newid[col[e]]      (j = newid[row], k = e - rowptr[row])
+// into the array pre-filled with -1 (the padding).  Column ids are range-checked here (validate_csr skips them in
+// this mode): a bad id raises the verdict word and is not followed.
+constexpr int kScatRows = 2048;        // offsets staged per CTA; longer row runs (mostly empty rows) search in global memory
+
+template <typename OffT>
+__global__ void __launch_bounds__(256, 4)
+sell_scatter(const OffT *__restrict__ rowptr, const int32_t *__restrict__ col, const int32_t *__restrict__ newid,
+             const uint32_t *__restrict__ slice_ptr, int32_t *__restrict__ sell, int64_t rows, uint64_t e0, uint64_t e1,
+             int64_t m, int *flag) {
+  __shared__ int32_t s_off[kScatRows + 1];
+  __shared__ int64_t s_row[2];
+  const uint64_t n_tiles = (e1 - e0 + 1023) / 1024;
+  for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint64_t tb = e0 + tile * 1024, te = tb + 1024 < e1 ? tb + 1024 : e1;
+    if (threadIdx.x == 0 || threadIdx.x == 32) {
+      // last row whose first non-zero is at or before `key` (upper_bound - 1); rowptr[0] = 0 <= key
+      const uint64_t key = threadIdx.x == 0 ? tb : te - 1;
+      int64_t lo = 0, hi = rows;
+      while (lo < hi) {
+        const int64_t mid = (lo + hi + 1) >> 1;
+        if ((uint64_t)rowptr[mid] <= key) lo = mid; else hi = mid - 1;
+      }
+      s_row[threadIdx.x >> 5] = lo;
+    }
+    __syncthreads();
+    const int64_t r_lo = s_row[0], r_hi = s_row[1];
+    const int64_t nr = r_hi - r_lo + 1;
+    const bool staged = nr <= kScatRows;
+    if (staged)
+      for (int64_t i = threadIdx.x; i <= nr; i += 256) s_off[i] = (int32_t)((int64_t)rowptr[r_lo + i] - (int64_t)tb);
+    __syncthreads();
+    const uint64_t e = tb + 4ull * threadIdx.x;
+    if (e < te) {
+      int c4[4];
+      if (e + 4 <= te) { const int4 q = *reinterpret_cast<const int4 *>(col + e); c4[0] = q.x; c4[1] = q.y; c4[2] = q.z; c4[3] = q.w; }
+      else { for (int u = 0; u < 4; u++) c4[u] = e + u < te ? col[e + u] : 0; }
+      // row of the first entry
+      int64_t i;
+      if (staged) {
+        const int32_t key = (int32_t)(e - tb);
+        int32_t lo = 0, hi = (int32_t)nr - 1;
+        while (lo < hi) { const int32_t mid = (lo + hi + 1) >> 1; if (s_off[mid] <= key) lo = mid; else hi = mid - 1; }
+        i = lo;
+      } else {
+        int64_t lo = r_lo, hi = r_hi;
+        while (lo < hi) { const int64_t mid = (lo + hi + 1) >> 1; if ((uint64_t)rowptr[mid] <= e) lo = mid; else hi = mid - 1; }
+        i = lo - r_lo;
+      }
+      int64_t row_end = staged ? (int64_t)s_off[i + 1] + (int64_t)tb : (int64_t)rowptr[r_lo + i + 1];
+      int64_t row_beg = staged ? (int64_t)s_off[i] + (int64_t)tb : (int64_t)rowptr[r_lo + i];
+      int32_t j = newid[r_lo + i];
+      size_t base = (size_t)slice_ptr[j >> 5] * 4 + (size_t)(j & 31) * 4;
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int64_t ee = (int64_t)e + u;
+        if ((uint64_t)ee >= te) break;
+        while (ee >= row_end) {                    // next non-empty row
+          i++;
+          row_beg = row_end;
+          row_end = staged ? (int64_t)s_off[i + 1] + (int64_t)tb : (int64_t)rowptr[r_lo + i + 1];
+          if (ee < row_end) { j = newid[r_lo + i]; base = (size_t)slice_ptr[j >> 5] * 4 + (size_t)(j & 31) * 4; }
+        }
+        const uint32_t k = (uint32_t)(ee - row_beg);
+        const int c = c4[u];
+        int v = -1;
+        if ((unsigned)c < (unsigned)m) v = newid[c]; else atomicExch(flag, 3);
+        sell[base + (size_t)(k >> 2) * 128 + (k & 3)] = v;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// Queue the streaming build behind the chunked column upload (gdn_graph::col_ev).  Everything it reads besides the
+// columns (offsets, newid, slice_ptr) was queued on the library stream before.
+static int pull_stream_fill(gdn_graph *g) {
+  PullLayout &L = g->pull;
+  const DevCsr &c = g->has_in && g->in.col ? g->in : g->out;
+  cudaStream_t st = lib().stream;
+  GDN_CUDA(cudaMalloc((void **)&L.sell, sizeof(int4) * std::max<uint64_t>(L.n_groups, 1) + 256));
+  g->device_bytes += sizeof(int4) * L.n_groups;
+  GDN_CUDA(cudaMemsetAsync(L.sell, 0xff, sizeof(int4) * std::max<uint64_t>(L.n_groups, 1) + 256, st));
+  uint64_t e0 = 0;
+  for (size_t k = 0; k < g->col_ev.size(); k++) {
+    const uint64_t e1 = g->col_end[k];
+    GDN_CUDA(cudaStreamWaitEvent(st, g->col_ev[k], 0));
+    const int grid = (int)std::min<uint64_t>((e1 - e0 + 1023) / 1024, (uint64_t)lib().sm_count * 8);
+    if (c.off64)
+      sell_scatter<uint64_t><<<grid, 256, 0, st>>>((const uint64_t *)c.rowptr, c.col, L.newid, L.slice_ptr, (int32_t *)L.sell,
+                                                   c.rows, e0, e1, g->m, g->col_flag);
+    else
+      sell_scatter<uint32_t><<<grid, 256, 0, st>>>((const uint32_t *)c.rowptr, c.col, L.newid, L.slice_ptr, (int32_t *)L.sell,
+                                                   c.rows, e0, e1, g->m, g->col_flag);
+    e0 = e1;
+  }
+  GDN_CUDA(cudaGetLastError());
+  return GDN_OK;
 }
 
 int pull_build_sell(gdn_graph *g) {
@@ -677,31 +805,46 @@ pr_sell_pipe(SellArgs a) {
   if (lane == 0) a.err_partial[a.err_slot0 + warp] = err;
 }
 
-// wide slices: one warp per slice adds the per-row partials of its segments in column order
+// wide slices: the per-row partials of a slice's segments are added in a FIXED order -- the eight warps of a CTA each
+// add a contiguous run of segments in column order, warp 0 then adds the eight run sums in run order.  (One warp per
+// slice walked up to 500 dependent adds for the hub slices of Kron-26: 0.62 ms per iteration, a tenth of the gather.)
+// Slices are taken widest first by CTA index, so the long ones start together.
 __global__ void __launch_bounds__(256, 4)
 pr_sell_finalize(SellArgs a) {
+  __shared__ float s_run[8][32];
   if (*a.done) return;
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * 8;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   double err = 0.0;
-  for (int64_t h = warp; h < a.n_heavy_slices; h += nwarps) {
+  for (int64_t h = blockIdx.x; h < a.n_heavy_slices; h += gridDim.x) {
     const int32_t s = a.heavy_slice[h];
     const int32_t f0 = a.heavy_first[h], f1 = a.heavy_first[h + 1];
+    const int32_t n = f1 - f0;
+    const int32_t q0 = f0 + (int32_t)((int64_t)n * w / 8), q1 = f0 + (int32_t)((int64_t)n * (w + 1) / 8);
     float acc = 0.f;
-    int32_t q = f0;
-    for (; q + 8 <= f1; q += 8) {                   // 8 independent loads, then the adds in segment order
+    int32_t q = q0;
+    for (; q + 8 <= q1; q += 8) {                   // 8 independent loads, then the adds in segment order
       float t[8];
 #pragma unroll
       for (int u = 0; u < 8; u++) t[u] = __ldcs(a.partial + (size_t)(q + u) * 32 + lane);
 #pragma unroll
       for (int u = 0; u < 8; u++) acc = __fadd_rn(acc, t[u]);
     }
-    for (; q < f1; q++) acc = __fadd_rn(acc, __ldcs(a.partial + (size_t)q * 32 + lane));
-    const int64_t j = (int64_t)s * 32 + lane;
-    if (j < a.n_nz_rows) pr_epilogue(a, j, acc, err);
+    for (; q < q1; q++) acc = __fadd_rn(acc, __ldcs(a.partial + (size_t)q * 32 + lane));
+    s_run[w][lane] = acc;
+    __syncthreads();
+    if (w == 0) {
+      float tot = s_run[0][lane];
+#pragma unroll
+      for (int u = 1; u < 8; u++) tot = __fadd_rn(tot, s_run[u][lane]);
+      const int64_t j = (int64_t)s * 32 + lane;
+      if (j < a.n_nz_rows) pr_epilogue(a, j, tot, err);
+    }
+    __syncthreads();
   }
-  err = warp_sum(err);
-  if (lane == 0) a.err_partial[a.err_slot0 + warp] = err;
+  if (w == 0) {
+    err = warp_sum(err);
+    if (lane == 0) a.err_partial[a.err_slot0 + blockIdx.x] = err;
+  }
 }
 
 // rows without in-edges: score = base (src/pr/omp_base.cc:28-32 with an empty sum).  They reach that
@@ -773,7 +916,7 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
   cudaStream_t s = lib().stream;
   const int sm = lib().sm_count;
   const int wpc = kSellThreads / 32;             // err_partial slots per CTA (the pipelined variants use fewer warps)
-  const int fgrid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)L.n_heavy_slices + 7) / 8, (int64_t)sm * 4));
+  const int fgrid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)L.n_heavy_slices, (int64_t)sm * 8));   // one CTA per wide slice
   const int igrid = (int)std::max<int64_t>(1, std::min<int64_t>((L.rows - L.n_nz_rows + 255) / 256, (int64_t)sm * 8));
   const int n_partial = sm * wpc + fgrid * 8 + igrid * 8;
   if (!g->contrib[0]) {

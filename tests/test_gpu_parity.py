@@ -241,6 +241,20 @@ def test_error_behaviour():
     assert "column index" in _lib.last_error()
 
 
+def test_oneshot_pr_refuses_bad_column():
+    """Column ids are range-checked by the streaming layout build of the one-shot PageRank (no UB, GDN_ERR_GRAPH)."""
+    csr, _ = load_case("chesapeake_sym")
+    g = RawGraph(csr)
+    bad_ci = csr["in_colidx"].copy()
+    bad_ci[len(bad_ci) // 2] = g.m + 5
+    scores = np.full(g.m, np.float32(1.0) / np.float32(g.m), dtype=np.float32)
+    od = g.out_degrees()
+    rc = _lib.lib.gdn_pagerank_pull(g.m, g.nnz, csr["in_rowptr"].ctypes.data, bad_ci.ctypes.data,
+                                    od.ctypes.data, scores.ctypes.data, 0.85, 1e-4, 100, None)
+    assert rc == _lib.GDN_ERR_GRAPH
+    assert "column index" in _lib.last_error()
+
+
 def test_resident_matches_oneshot_and_is_deterministic():
     import torch
     g = gb.Graph.generate("g", 15, 16)
@@ -259,6 +273,11 @@ def test_resident_matches_oneshot_and_is_deterministic():
     st1 = dg.pagerank(s1)
     st2 = dg.pagerank(s2)
     assert st1.iterations == st2.iterations and torch.equal(s1, s2), "PR must be bit-reproducible run to run"
+    # the one-shot entry point builds the SELL layout piece by piece behind the chunked column upload (sell_scatter);
+    # the resident graph builds it slice by slice (sell_fill): same array, hence bit-identical scores
+    hs = np.full(m, np.float32(1.0) / np.float32(m), dtype=np.float32)
+    st3 = gb.PRSolver(g, hs, verbose=False)
+    assert st3.iterations == st1.iterations and np.array_equal(hs, s1.cpu().numpy())
     Ax = torch.from_numpy(gb.fill_uniform(13, g.nnz)).cuda()
     x = torch.from_numpy(gb.fill_uniform(14, m)).cuda()
     y1 = torch.zeros(m, device="cuda")

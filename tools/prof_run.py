@@ -56,10 +56,15 @@ def main():
     else:
         Ax = torch.from_numpy(gb.fill_uniform(13, g.nnz)).to(dev)
         x = torch.from_numpy(gb.fill_uniform(14, g.m)).to(dev)
-        y = torch.zeros(g.m, dtype=torch.float32, device=dev)
-        for _ in range(args.reps):
-            st = dg.spmv(Ax, x, y)
-            out["runs"].append({"solve_ms": st.solve_ms, "kernel_ms": st.kernel_ms})
+        for sw in sweeps:
+            for kv in [x for x in sw.split(",") if x]:
+                k, v = kv.split("=")
+                os.environ[k] = v
+            for _ in range(args.reps):
+                y = torch.zeros(g.m, dtype=torch.float32, device=dev)
+                st = dg.spmv(Ax, x, y)
+                out["runs"].append({"env": sw, "solve_ms": st.solve_ms, "kernel_ms": st.kernel_ms,
+                                    "checksum": float(y.double().sum().item())})
     dg.close()
     print(json.dumps(out))
 
