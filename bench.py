@@ -253,6 +253,14 @@ def main():
 
     for _ in range(args.warmup):
         st = pr_step()
+    pinfo = dg.pull_info()
+    if pinfo["banded"]:
+        # one iteration of the banded layout (csrc/band.cu) is four launches timed as one unit
+        kernel_name = ("pr_band_kernel + pr_sell_pipe + pr_sell_finalize + pr_band_finalize (the launches of ONE PageRank iteration "
+                       f"over all rows; {pinfo['band_entries'] / max(nnz, 1):.1%} of the column ids are gathered from {pinfo['bands']} "
+                       "shared-memory bands)")
+    else:
+        kernel_name = "pr_sell_pipe (one launch = one PageRank iteration over all rows)"
     sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
@@ -357,7 +365,7 @@ def main():
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "pr_sell_pipe (one launch = one PageRank iteration over all rows)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_kernel_ms,
                          "launches_timed": int(kern_calls),

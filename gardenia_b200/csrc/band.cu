@@ -1,0 +1,523 @@
+// band.cu -- banded shared-memory gather for the heavy rows of the PageRank pull layout.
+//
+// Why (profiles/r1_pr_tier_probe.txt, r1_ncu_pr_pipe_kron26.txt): pr_sell_pipe sits on the L1TEX miss path -- one
+// 32-byte sector per clock and SM for every contrib[src] (src/pr/omp_base.cc:29-30) that is not in the 48 K-entry
+// shared-memory table, 1.5 G sectors per iteration at Kronecker scale 26 -- while a gather out of shared memory costs
+// a fifth of that.  Only 28 % of the column ids fall into the ONE table every SM holds; 73 % fall into the hottest
+// 3 M ids.  So the id space is cut into bands of 48 K ids and each band's table is held by the CTAs that own it:
+//
+//   * for every sorted row of length >= dmin and every band b in which the row has >= cmin column ids, those ids
+//     leave the row's main SELL slice and are stored as 16-bit band-local ids in band b's own SELL-32 array, whose
+//     rows are sorted by their count IN THAT BAND (13 % padding instead of 85 %);
+//   * pr_band_kernel: a CTA loads contrib[band b] into shared memory once and streams a contiguous run of band b's
+//     index groups (8 ids per 128-bit load, lane = row, sequential fp32 sum per row in column order); one partial
+//     sum per (band slice segment, row);
+//   * what is left (cold ids, sparse (row, band) pairs) is a compacted main SELL array that the unchanged
+//     pr_sell_pipe walks; its epilogue for these rows only deposits the main sum;
+//   * pr_band_finalize adds main sum + band partials of a row in a FIXED (band, segment) order and runs the row
+//     epilogue (score, L1 delta, next contrib).  No atomics: bit-reproducible from run to run.
+//
+// The layout is built once per resident graph (untimed, like include/segmenting.h preprocessing of the reference):
+// two device passes over the existing SELL array (count, fill) around a host pass that sorts each band's rows.
+// One GPU only (the multi-GPU id space interleaves the ranks' hot slices); one-shot calls keep the plain layout.
+#include "pull.cuh"
+#include <omp.h>
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+namespace gdn {
+
+constexpr int kBandSeg = 64;            // index groups (8 ids each) per lane and item: 512 ids of a row
+constexpr int kBandTab = kHotMax + 256; // table entries in shared memory: [band, kBandTab) is zero
+constexpr uint32_t kBandPadId = 0xC0C0; // padding id = a zero table entry; byte-uniform so cudaMemset can write it
+constexpr uint32_t kNone = 0xffffffffu;
+static_assert(kBandPadId >= (uint32_t)kHotMax && kBandPadId < (uint32_t)kBandTab, "padding id must hit the zero tail");
+
+// ------------------------------------------------------------------ build pass 1: count[b][j]
+// One warp per slice of the existing SELL array (lane = row): how many ids of row j fall into band b.
+__global__ void __launch_bounds__(128)
+band_count(const int4 *__restrict__ sell, const uint32_t *__restrict__ slice_ptr, int32_t nb_slices, int B, uint32_t band,
+           uint32_t *__restrict__ cnt, int64_t n_rows) {
+  extern __shared__ uint32_t s_u32[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  uint32_t *c = s_u32 + (size_t)wib * B * 32;
+  for (int32_t s = blockIdx.x * 4 + wib; s < nb_slices; s += gridDim.x * 4) {
+    for (int b = 0; b < B; b++) c[b * 32 + lane] = 0;
+    const uint32_t g0 = slice_ptr[s], g1 = slice_ptr[s + 1];
+    const int4 *p = sell + g0 + lane;
+    const uint32_t n = (g1 - g0) >> 5;
+    for (uint32_t k = 0; k < n; k += 4) {
+      int4 q[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) q[u] = k + u < n ? p[(size_t)(k + u) * 32] : make_int4(-1, -1, -1, -1);
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int v[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+          if (v[t] >= 0) { const uint32_t b = (uint32_t)v[t] / band; if (b < (uint32_t)B) c[b * 32 + lane]++; }
+      }
+    }
+    for (int b = 0; b < B; b++) cnt[(size_t)b * n_rows + (size_t)s * 32 + lane] = c[b * 32 + lane];
+  }
+}
+
+// (row, band) pairs with fewer than cmin ids stay in the main array; rem_w[s] = widest remainder of slice s.
+__global__ void __launch_bounds__(256)
+band_select(uint32_t *__restrict__ cnt, int B, int64_t n_rows, uint32_t cmin, const int32_t *__restrict__ sdeg,
+            uint32_t *__restrict__ rem_w) {
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_rows; j += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t tot = 0;
+    for (int b = 0; b < B; b++) {
+      const uint32_t v = cnt[(size_t)b * n_rows + j];
+      if (v < cmin) { if (v) cnt[(size_t)b * n_rows + j] = 0; } else tot += v;
+    }
+    uint32_t rem = (uint32_t)sdeg[j] - tot;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rem = max(rem, __shfl_xor_sync(kFull, rem, o));
+    if ((threadIdx.x & 31) == 0) rem_w[j >> 5] = rem;       // n_rows is a multiple of 32 and j is warp-aligned
+  }
+}
+
+// ------------------------------------------------------------------ build pass 2: fill both arrays
+// One warp per slice again.  rank[b][j] = position of row j among band b's rows (kNone: the pair stays in the main
+// array).  A lane walks ITS row in column order, so the order of a row's ids inside a band section and inside the
+// compacted main slice is the order they had before.
+__global__ void __launch_bounds__(128)
+band_fill(const int4 *__restrict__ sell, const uint32_t *__restrict__ slice_ptr, int32_t nb_slices, int B, uint32_t band,
+          const uint32_t *__restrict__ rank, int64_t n_rows, const uint32_t *__restrict__ bslice_ptr,
+          const int32_t *__restrict__ bslice_first, uint16_t *__restrict__ bsell16, int4 *__restrict__ sell2,
+          const uint32_t *__restrict__ slice_ptr2) {
+  extern __shared__ uint32_t s_u32[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  uint32_t *base = s_u32 + (size_t)wib * 2 * B * 32;     // unit of group 0 of this row in band b (kNone: not there)
+  uint32_t *kcnt = base + (size_t)B * 32;
+  for (int32_t s = blockIdx.x * 4 + wib; s < nb_slices; s += gridDim.x * 4) {
+    const int64_t j = (int64_t)s * 32 + lane;
+    for (int b = 0; b < B; b++) {
+      const uint32_t r = rank[(size_t)b * n_rows + j];
+      base[b * 32 + lane] = r == kNone ? kNone : bslice_ptr[bslice_first[b] + (r >> 5)] + (r & 31);
+      kcnt[b * 32 + lane] = 0;
+    }
+    const uint32_t g0 = slice_ptr[s], g1 = slice_ptr[s + 1];
+    const int4 *p = sell + g0 + lane;
+    const uint32_t n = (g1 - g0) >> 5;
+    int4 *dst = sell2 + slice_ptr2[s] + lane;
+    int4 pend = make_int4(-1, -1, -1, -1);
+    int np = 0;
+    for (uint32_t k = 0; k < n; k += 4) {
+      int4 q[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) q[u] = k + u < n ? p[(size_t)(k + u) * 32] : make_int4(-1, -1, -1, -1);
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int v[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+          const int c = v[t];
+          if (c < 0) continue;
+          const uint32_t b = (uint32_t)c / band;
+          uint32_t bs = kNone;
+          if (b < (uint32_t)B) bs = base[b * 32 + lane];
+          if (bs != kNone) {
+            const uint32_t kk = kcnt[b * 32 + lane]++;
+            bsell16[((size_t)bs + (size_t)(kk >> 3) * 32) * 8 + (kk & 7)] = (uint16_t)((uint32_t)c - b * band);
+          } else {
+            if (np == 0) pend.x = c; else if (np == 1) pend.y = c; else if (np == 2) pend.z = c; else pend.w = c;
+            if (++np == 4) { *dst = pend; dst += 32; pend = make_int4(-1, -1, -1, -1); np = 0; }
+          }
+        }
+      }
+    }
+    if (np) *dst = pend;
+  }
+}
+
+// ------------------------------------------------------------------ the iteration: band partial sums
+struct BandArgs {
+  const uint4 *bsell;
+  const uint32_t *item_ptr;
+  const int4 *job;
+  const int32_t *job_first;
+  const int32_t *wrun;
+  int32_t band;
+  int64_t Mp;
+  const float *contrib_in;
+  float *bpartial;
+  const int32_t *done;
+};
+
+__device__ __forceinline__ uint4 ld_stream_u4(const uint4 *p, uint64_t pol) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p), "l"(pol));
+  return r;
+}
+
+// PD index groups (8 ids each) requested ahead per lane.  A warp owns a contiguous run of items = one contiguous
+// piece of the band's array: it streams through it without a bubble at item boundaries; the item lengths come 32 at a
+// time (lane i holds the length of item ibase + i) with the next batch requested one batch ahead.
+template <int PD>
+__global__ void __launch_bounds__(kSellThreads, 1)
+pr_band_kernel(BandArgs a) {
+  extern __shared__ float tab[];
+  if (*a.done) return;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint64_t pol = l2_policy_evict_first();
+  const uint4 padq = make_uint4(kBandPadId * 0x10001u, kBandPadId * 0x10001u, kBandPadId * 0x10001u, kBandPadId * 0x10001u);
+  for (int32_t jb = a.job_first[blockIdx.x]; jb < a.job_first[blockIdx.x + 1]; jb++) {
+    const int4 J = a.job[jb];
+    __syncthreads();                                       // the previous band's readers are done
+    const int64_t id0 = (int64_t)J.x * a.band;
+    for (int i = threadIdx.x; i < kBandTab; i += kSellThreads)
+      tab[i] = (i < a.band && id0 + i < a.Mp) ? a.contrib_in[id0 + i] : 0.f;
+    __syncthreads();
+    const int32_t i0 = a.wrun[J.y + w], i1 = a.wrun[J.y + w + 1];
+    if (i0 >= i1) continue;
+    const uint32_t u0 = a.item_ptr[i0], u1 = a.item_ptr[i1];
+    const uint4 *p = a.bsell + u0 + lane;
+    const uint32_t nrows = (u1 - u0) >> 5;
+    auto len_batch = [&](int32_t ib) -> uint32_t {
+      const int32_t i = ib + lane;
+      return i < i1 ? (a.item_ptr[i + 1] - a.item_ptr[i]) >> 5 : 0u;
+    };
+    int32_t ibase = i0, item = i0;
+    uint32_t lens = len_batch(ibase), lens_next = len_batch(ibase + 32);
+    uint32_t left = __shfl_sync(kFull, lens, 0);
+    uint4 q[PD];
+#pragma unroll
+    for (int d = 0; d < PD; d++) q[d] = (uint32_t)d < nrows ? ld_stream_u4(p + 32 * d, pol) : padq;
+    float acc = 0.f;
+    for (uint32_t r = 0; r < nrows; r += PD) {
+#pragma unroll
+      for (int d = 0; d < PD; d++) {
+        if (r + d < nrows) {                               // warp-uniform
+          const uint4 c = q[d];
+          q[d] = r + d + PD < nrows ? ld_stream_u4(p + (size_t)(r + d + PD) * 32, pol) : padq;
+          const float v0 = tab[c.x & 0xffffu], v1 = tab[c.x >> 16], v2 = tab[c.y & 0xffffu], v3 = tab[c.y >> 16];
+          const float v4 = tab[c.z & 0xffffu], v5 = tab[c.z >> 16], v6 = tab[c.w & 0xffffu], v7 = tab[c.w >> 16];
+          acc = __fadd_rn(acc, v0); acc = __fadd_rn(acc, v1); acc = __fadd_rn(acc, v2); acc = __fadd_rn(acc, v3);
+          acc = __fadd_rn(acc, v4); acc = __fadd_rn(acc, v5); acc = __fadd_rn(acc, v6); acc = __fadd_rn(acc, v7);
+          if (--left == 0) {
+            __stcs(a.bpartial + (size_t)item * 32 + lane, acc);
+            acc = 0.f;
+            item++;
+            if (item - ibase == 32) { ibase += 32; lens = lens_next; lens_next = len_batch(ibase + 32); }
+            left = __shfl_sync(kFull, lens, item - ibase);
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ the iteration: main sum + band partials -> epilogue
+__global__ void __launch_bounds__(256, 4)
+pr_band_finalize(SellArgs a, const uint32_t *__restrict__ rslot_ptr, const uint32_t *__restrict__ rslot,
+                 const float *__restrict__ bpartial) {
+  if (*a.done) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  double err = 0.0;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < a.n_band_rows; j += (int64_t)gridDim.x * blockDim.x) {
+    float acc = __ldcs(a.acc_main + j);
+    uint32_t k = rslot_ptr[j];
+    const uint32_t k1 = rslot_ptr[j + 1];
+    for (; k + 4 <= k1; k += 4) {                          // four gathers in flight, added in slot order
+      float t[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) t[u] = __ldcs(bpartial + rslot[k + u]);
+#pragma unroll
+      for (int u = 0; u < 4; u++) acc = __fadd_rn(acc, t[u]);
+    }
+    for (; k < k1; k++) acc = __fadd_rn(acc, __ldcs(bpartial + rslot[k]));
+    if (j < a.n_nz_rows) pr_epilogue_core(a, j, acc, err);
+  }
+  err = warp_sum(err);
+  if (lane == 0) a.err_partial[a.err_slot0 + warp] = err;
+}
+
+// ------------------------------------------------------------------ host: tables
+// Work tables of a SELL array from its slice pointers (same meaning as in pull_prepare; widths need not be monotone).
+static void make_work_tables(const std::vector<uint32_t> &sptr, int32_t n_slices, std::vector<int32_t> &chunk,
+                             std::vector<int32_t> &hslice, std::vector<int32_t> &hfirst, std::vector<int2> &hseg) {
+  const uint64_t tot = sptr[n_slices];
+  const int32_t n_chunks = (int32_t)(tot / kGroupCh + 1);
+  chunk.assign((size_t)n_chunks + 1, 0);
+  int32_t s = 0;
+  for (int32_t k = 0; k < n_chunks; k++) {
+    while (s < n_slices && sptr[s] < (uint64_t)k * kGroupCh) s++;
+    chunk[k] = s;
+  }
+  chunk[n_chunks] = n_slices;
+  hslice.clear(); hfirst.clear(); hseg.clear();
+  for (int32_t t = 0; t < n_slices; t++) {
+    const uint32_t sz = sptr[t + 1] - sptr[t];
+    if (sz <= (uint32_t)kGroupCh) continue;
+    hslice.push_back(t);
+    hfirst.push_back((int32_t)hseg.size());
+    for (uint32_t q = 0; q < (sz + kGroupCh - 1) / kGroupCh; q++) hseg.push_back(make_int2(t, (int)q));
+  }
+  hfirst.push_back((int32_t)hseg.size());
+}
+
+template <typename T>
+static int up(gdn_graph *g, T **dptr, const T *h, size_t n) {
+  GDN_CUDA(cudaMalloc((void **)dptr, std::max<size_t>(n, 4) * sizeof(T)));
+  g->device_bytes += n * sizeof(T);
+  if (n) GDN_CUDA(cudaMemcpyAsync(*dptr, h, n * sizeof(T), cudaMemcpyHostToDevice, lib().stream));
+  return GDN_OK;
+}
+
+void band_free(BandLayout &b) {
+  cudaFree(b.bsell); cudaFree(b.item_ptr); cudaFree(b.job); cudaFree(b.job_first); cudaFree(b.wrun); cudaFree(b.bpartial);
+  cudaFree(b.rslot_ptr); cudaFree(b.rslot); cudaFree(b.acc_main); cudaFree(b.sell); cudaFree(b.slice_ptr);
+  cudaFree(b.chunk_slice); cudaFree(b.heavy_slice); cudaFree(b.heavy_first); cudaFree(b.heavy_seg); cudaFree(b.partial);
+  b = BandLayout();
+}
+
+static int env_int(const char *name, int dflt) {
+  const char *e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+// Build the banded layout from the (already built) SELL array.  Leaves b.built = false -- and the plain layout in
+// use -- when the graph is too small or too flat for any (row, band) pair to qualify.
+int band_build(gdn_graph *g) {
+  PullLayout &L = g->pull;
+  BandLayout &bd = L.band;
+  if (bd.tried) return GDN_OK;
+  bd.tried = true;
+  const int B_want = env_int("GDN_PR_BANDS", 64);
+  if (B_want <= 0 || L.P != 1 || !L.prepared || !L.sell || L.n_slices < 2 || L.h_slice_ptr.empty()) return GDN_OK;
+  const int band = std::min(std::max(env_int("GDN_PR_BAND_SIZE", kHotMax), 32), kHotMax);
+  const int cmin = std::max(env_int("GDN_PR_BAND_CMIN", 4), 1);
+  const int dmin = std::max(env_int("GDN_PR_BAND_DMIN", 64), 1);
+  const int B = (int)std::min<int64_t>(std::min(B_want, 96), (L.Mp + band - 1) / band);
+  const std::vector<uint32_t> &sp = L.h_slice_ptr;
+  // slices whose rows are all at least dmin long: the first row of the NEXT slice is (rows sorted by length, descending)
+  int32_t nb = 0;
+  while (nb + 1 < L.n_slices && (int64_t)(sp[nb + 2] - sp[nb + 1]) / 32 * 4 >= dmin) nb++;
+  if (nb == 0) return GDN_OK;
+  const int64_t n_rows = (int64_t)nb * 32;
+  cudaStream_t st = lib().stream;
+  const int sm = lib().sm_count;
+  trace("band_build: begin");
+
+  // pass 1 on the device
+  uint32_t *d_cnt = nullptr, *d_remw = nullptr;
+  GDN_CUDA(cudaMalloc((void **)&d_cnt, sizeof(uint32_t) * (size_t)B * n_rows));
+  GDN_CUDA(cudaMalloc((void **)&d_remw, sizeof(uint32_t) * (size_t)nb));
+  const size_t smem1 = sizeof(uint32_t) * 4 * (size_t)B * 32, smem2 = 2 * smem1;
+  GDN_CUDA(cudaFuncSetAttribute(band_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+  GDN_CUDA(cudaFuncSetAttribute(band_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+  const int grid = (int)std::min<int64_t>((nb + 3) / 4, (int64_t)sm * 16);
+  band_count<<<grid, 128, smem1, st>>>(L.sell, L.slice_ptr, nb, B, (uint32_t)band, d_cnt, n_rows);
+  band_select<<<(int)std::min<int64_t>((n_rows + 255) / 256, (int64_t)sm * 8), 256, 0, st>>>(d_cnt, B, n_rows, (uint32_t)cmin, L.sdeg, d_remw);
+  std::vector<uint32_t> cnt((size_t)B * n_rows), remw((size_t)nb);
+  GDN_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, sizeof(uint32_t) * cnt.size(), cudaMemcpyDeviceToHost, st));
+  GDN_CUDA(cudaMemcpyAsync(remw.data(), d_remw, sizeof(uint32_t) * remw.size(), cudaMemcpyDeviceToHost, st));
+  GDN_CUDA(cudaStreamSynchronize(st));
+  GDN_CUDA(cudaGetLastError());
+  trace("band_build: counted");
+
+  // host: every band's rows sorted by their count in it; slices, items, ranks
+  struct PerBand {
+    std::vector<uint32_t> order;           // rows by (count desc, row asc)
+    std::vector<uint32_t> slice_units;     // unit offset of each band slice inside the band
+    std::vector<uint32_t> slice_item;      // first item of each band slice inside the band
+    std::vector<uint32_t> item_ng;         // index groups per lane of each item
+    uint64_t units = 0, moved = 0;
+  };
+  std::vector<PerBand> pb((size_t)B);
+  std::vector<uint32_t> rank(cnt.size());
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int b = 0; b < B; b++) {
+    PerBand &q = pb[b];
+    const uint32_t *c = cnt.data() + (size_t)b * n_rows;
+    uint32_t *rk = rank.data() + (size_t)b * n_rows;
+    for (int64_t j = 0; j < n_rows; j++) { rk[j] = kNone; if (c[j]) { q.order.push_back((uint32_t)j); q.moved += c[j]; } }
+    std::stable_sort(q.order.begin(), q.order.end(), [&](uint32_t x, uint32_t y) { return c[x] > c[y]; });
+    const size_t n = q.order.size();
+    for (size_t pos = 0; pos < n; pos++) rk[q.order[pos]] = (uint32_t)pos;
+    for (size_t s0 = 0; s0 < n; s0 += 32) {
+      const uint32_t ng = (c[q.order[s0]] + 7) / 8;
+      q.slice_units.push_back((uint32_t)q.units);
+      q.slice_item.push_back((uint32_t)q.item_ng.size());
+      for (uint32_t t = 0; t < ng; t += kBandSeg) q.item_ng.push_back(std::min<uint32_t>(kBandSeg, ng - t));
+      q.units += 32ull * ng;
+    }
+  }
+  uint64_t units = 0, n_items64 = 0, n_bslices = 0, moved = 0, pairs = 0;
+  std::vector<uint64_t> band_unit0((size_t)B + 1), band_item0((size_t)B + 1);
+  std::vector<int32_t> bslice_first((size_t)B + 1);
+  for (int b = 0; b < B; b++) {
+    band_unit0[b] = units; band_item0[b] = n_items64; bslice_first[b] = (int32_t)n_bslices;
+    units += pb[b].units; n_items64 += pb[b].item_ng.size(); n_bslices += pb[b].slice_units.size();
+    moved += pb[b].moved; pairs += pb[b].order.size();
+  }
+  band_unit0[B] = units; band_item0[B] = n_items64; bslice_first[B] = (int32_t)n_bslices;
+  if (n_items64 == 0 || units >= 0xfffffff0ull / 8 * 8 || n_items64 * 32 >= 0xfffffff0ull) {
+    cudaFree(d_cnt); cudaFree(d_remw);
+    return GDN_OK;                                   // nothing qualifies (or 32-bit unit offsets would overflow): plain layout
+  }
+  const int32_t n_items = (int32_t)n_items64;
+  std::vector<uint32_t> item_ptr((size_t)n_items + 1), bslice_ptr(n_bslices), bslice_item(n_bslices);
+  std::vector<int32_t> item_band((size_t)n_items);
+  for (int b = 0; b < B; b++) {
+    const PerBand &q = pb[b];
+    uint64_t u = band_unit0[b];
+    for (size_t i = 0; i < q.item_ng.size(); i++) {
+      item_ptr[band_item0[b] + i] = (uint32_t)u;
+      item_band[band_item0[b] + i] = b;
+      u += 32ull * q.item_ng[i];
+    }
+    for (size_t s0 = 0; s0 < q.slice_units.size(); s0++) {
+      bslice_ptr[bslice_first[b] + s0] = (uint32_t)(band_unit0[b] + q.slice_units[s0]);
+      bslice_item[bslice_first[b] + s0] = (uint32_t)(band_item0[b] + q.slice_item[s0]);
+    }
+  }
+  item_ptr[n_items] = (uint32_t)units;
+
+  // partial slots of every row, in (band, segment) order
+  std::vector<uint32_t> rslot_ptr((size_t)n_rows + 1, 0);
+#pragma omp parallel for
+  for (int64_t j = 0; j < n_rows; j++) {
+    uint32_t n = 0;
+    for (int b = 0; b < B; b++) { const uint32_t c = cnt[(size_t)b * n_rows + j]; if (c) n += (c + 8 * kBandSeg - 1) / (8 * kBandSeg); }
+    rslot_ptr[j + 1] = n;
+  }
+  uint64_t n_rslot = 0;
+  for (int64_t j = 0; j < n_rows; j++) { const uint32_t n = rslot_ptr[j + 1]; rslot_ptr[j] = (uint32_t)n_rslot; n_rslot += n; }
+  rslot_ptr[n_rows] = (uint32_t)n_rslot;
+  if (n_rslot >= 0xfffffff0ull) { cudaFree(d_cnt); cudaFree(d_remw); return GDN_OK; }
+  std::vector<uint32_t> rslot(std::max<uint64_t>(n_rslot, 1));
+#pragma omp parallel for
+  for (int64_t j = 0; j < n_rows; j++) {
+    uint32_t k = rslot_ptr[j];
+    for (int b = 0; b < B; b++) {
+      const uint32_t c = cnt[(size_t)b * n_rows + j];
+      if (!c) continue;
+      const uint32_t r = rank[(size_t)b * n_rows + j];
+      const uint32_t it0 = bslice_item[bslice_first[b] + (r >> 5)];
+      for (uint32_t t = 0; t < (c + 8 * kBandSeg - 1) / (8 * kBandSeg); t++) rslot[k++] = (it0 + t) * 32 + (r & 31);
+    }
+  }
+
+  // jobs: equal-cost contiguous runs of items per CTA, cut at band boundaries, each cut into 32 warp runs
+  const int n_cta = sm;
+  std::vector<uint64_t> pc((size_t)n_items + 1, 0);
+  for (int32_t i = 0; i < n_items; i++) pc[i + 1] = pc[i] + ((item_ptr[i + 1] - item_ptr[i]) >> 5) + 2;
+  auto first_at = [&](uint64_t cost) -> int32_t { return (int32_t)(std::lower_bound(pc.begin(), pc.end(), cost) - pc.begin()); };
+  std::vector<int4> job;
+  std::vector<int32_t> job_first((size_t)n_cta + 1, 0), wrun;
+  for (int c = 0; c < n_cta; c++) {
+    job_first[c] = (int32_t)job.size();
+    int32_t lo = std::min(first_at(pc[n_items] * c / n_cta), n_items), hi = std::min(first_at(pc[n_items] * (c + 1) / n_cta), n_items);
+    if (c == n_cta - 1) hi = n_items;
+    while (lo < hi) {
+      const int b = item_band[lo];
+      const int32_t e = (int32_t)std::min<uint64_t>((uint64_t)hi, band_item0[b + 1]);
+      const int32_t w0 = (int32_t)wrun.size();
+      for (int w = 0; w <= 32; w++) {
+        int32_t x = w == 32 ? e : first_at(pc[lo] + (pc[e] - pc[lo]) * w / 32);
+        x = std::max(lo, std::min(x, e));
+        wrun.push_back(x);
+      }
+      job.push_back(make_int4(b, w0, lo, e));
+      lo = e;
+    }
+  }
+  job_first[n_cta] = (int32_t)job.size();
+  trace("band_build: host tables");
+
+  // compacted main array: band slices get their remaining width, the others keep theirs
+  std::vector<uint32_t> sp2((size_t)L.n_slices + 1);
+  uint64_t tot2 = 0;
+  for (int32_t s = 0; s < L.n_slices; s++) {
+    sp2[s] = (uint32_t)tot2;
+    tot2 += s < nb ? 32ull * ((remw[s] + 3) / 4) : (uint64_t)(sp[s + 1] - sp[s]);
+  }
+  sp2[L.n_slices] = (uint32_t)tot2;
+  std::vector<int32_t> chunk, hslice, hfirst;
+  std::vector<int2> hseg;
+  make_work_tables(sp2, L.n_slices, chunk, hslice, hfirst, hseg);
+
+  bd.B = B; bd.band = band; bd.cmin = cmin; bd.dmin = dmin; bd.n_rows = n_rows;
+  bd.n_units = units; bd.n_items = n_items; bd.n_jobs = (int32_t)job.size(); bd.n_cta = n_cta; bd.n_rslot = n_rslot;
+  bd.n_groups = tot2; bd.n_chunks = (int32_t)chunk.size() - 1;
+  bd.n_heavy_slices = (int32_t)hslice.size(); bd.n_heavy_segs = (int32_t)hseg.size();
+  bd.moved = moved; bd.pairs = pairs;
+  uint32_t *d_rank = d_cnt;                         // the counts are not needed on the device any more
+  uint32_t *d_bslice_ptr = nullptr;
+  int32_t *d_bslice_first = nullptr;
+  GDN_CUDA(cudaMemcpyAsync(d_rank, rank.data(), sizeof(uint32_t) * rank.size(), cudaMemcpyHostToDevice, st));
+  GDN_CHECK(up(g, &d_bslice_ptr, bslice_ptr.data(), bslice_ptr.size()));
+  GDN_CHECK(up(g, &d_bslice_first, bslice_first.data(), bslice_first.size()));
+  GDN_CHECK(up(g, &bd.item_ptr, item_ptr.data(), item_ptr.size()));
+  GDN_CHECK(up(g, &bd.job, job.data(), job.size()));
+  GDN_CHECK(up(g, &bd.job_first, job_first.data(), job_first.size()));
+  GDN_CHECK(up(g, &bd.wrun, wrun.data(), wrun.size()));
+  GDN_CHECK(up(g, &bd.rslot_ptr, rslot_ptr.data(), rslot_ptr.size()));
+  GDN_CHECK(up(g, &bd.rslot, rslot.data(), (size_t)n_rslot));
+  GDN_CHECK(up(g, &bd.slice_ptr, sp2.data(), sp2.size()));
+  GDN_CHECK(up(g, &bd.chunk_slice, chunk.data(), chunk.size()));
+  if (bd.n_heavy_slices) {
+    GDN_CHECK(up(g, &bd.heavy_slice, hslice.data(), hslice.size()));
+    GDN_CHECK(up(g, &bd.heavy_first, hfirst.data(), hfirst.size()));
+    GDN_CHECK(up(g, &bd.heavy_seg, hseg.data(), hseg.size()));
+    GDN_CUDA(cudaMalloc((void **)&bd.partial, sizeof(float) * 32 * (size_t)bd.n_heavy_segs));
+  }
+  GDN_CUDA(cudaMalloc((void **)&bd.bsell, sizeof(uint4) * units + 256));
+  GDN_CUDA(cudaMalloc((void **)&bd.sell, sizeof(int4) * std::max<uint64_t>(tot2, 1) + 256));
+  GDN_CUDA(cudaMalloc((void **)&bd.bpartial, sizeof(float) * 32 * (size_t)n_items));
+  GDN_CUDA(cudaMalloc((void **)&bd.acc_main, sizeof(float) * (size_t)n_rows));
+  g->device_bytes += sizeof(uint4) * units + sizeof(int4) * tot2 + sizeof(float) * (32 * (size_t)n_items + n_rows);
+  GDN_CUDA(cudaMemsetAsync(bd.bsell, (int)(kBandPadId & 0xff), sizeof(uint4) * units + 256, st));
+  GDN_CUDA(cudaMemsetAsync(bd.sell, 0xff, sizeof(int4) * (size_t)sp2[nb] + (tot2 == sp2[nb] ? 256 : 0), st));
+  GDN_CUDA(cudaMemsetAsync(bd.acc_main, 0, sizeof(float) * (size_t)n_rows, st));
+  if (tot2 > sp2[nb])
+    GDN_CUDA(cudaMemcpyAsync(bd.sell + sp2[nb], L.sell + sp[nb], sizeof(int4) * (size_t)(tot2 - sp2[nb]) + 256, cudaMemcpyDeviceToDevice, st));
+  band_fill<<<grid, 128, smem2, st>>>(L.sell, L.slice_ptr, nb, B, (uint32_t)band, d_rank, n_rows, d_bslice_ptr, d_bslice_first,
+                                      (uint16_t *)bd.bsell, bd.sell, bd.slice_ptr);
+  GDN_CUDA(cudaStreamSynchronize(st));
+  GDN_CUDA(cudaGetLastError());
+  cudaFree(d_cnt); cudaFree(d_remw); cudaFree(d_bslice_ptr); cudaFree(d_bslice_first);
+  GDN_CUDA(cudaFuncSetAttribute(pr_band_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * kBandTab)));
+  GDN_CUDA(cudaFuncSetAttribute(pr_band_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * kBandTab)));
+  bd.built = true;
+  if (getenv("GDN_TRACE"))
+    fprintf(stderr, "[gdn] band layout: B=%d band=%d cmin=%d rows=%lld  moved=%llu ids (%.1f %% of nnz) in %llu pairs, %d items, "
+                    "%llu padded ids (x%.2f), %d jobs; main array %llu -> %llu groups\n",
+            B, band, cmin, (long long)n_rows, (unsigned long long)moved, 100.0 * (double)moved / (double)std::max<uint64_t>(g->in.nnz, 1),
+            (unsigned long long)pairs, n_items, (unsigned long long)(units * 8), (double)(units * 8) / (double)std::max<uint64_t>(moved, 1),
+            bd.n_jobs, (unsigned long long)L.n_groups, (unsigned long long)tot2);
+  trace("band_build: done");
+  return GDN_OK;
+}
+
+int band_launch(gdn_graph *g, const SellArgs &sa, cudaStream_t s) {
+  const BandLayout &bd = g->pull.band;
+  BandArgs a;
+  a.bsell = bd.bsell; a.item_ptr = bd.item_ptr; a.job = bd.job; a.job_first = bd.job_first; a.wrun = bd.wrun;
+  a.band = bd.band; a.Mp = g->pull.Mp; a.contrib_in = sa.contrib_in; a.bpartial = bd.bpartial; a.done = sa.done;
+  const size_t smem = sizeof(float) * kBandTab;
+  if (env_int("GDN_PR_BAND_PD", 4) == 8) pr_band_kernel<8><<<bd.n_cta, kSellThreads, smem, s>>>(a);
+  else pr_band_kernel<4><<<bd.n_cta, kSellThreads, smem, s>>>(a);
+  return GDN_OK;
+}
+
+int band_finalize_grid(const gdn_graph *g) {
+  return (int)std::max<int64_t>(1, std::min<int64_t>((g->pull.band.n_rows + 255) / 256, (int64_t)lib().sm_count * 8));
+}
+
+int band_finalize_launch(gdn_graph *g, const SellArgs &a, int grid, cudaStream_t s) {
+  const BandLayout &bd = g->pull.band;
+  pr_band_finalize<<<grid, 256, 0, s>>>(a, bd.rslot_ptr, bd.rslot, bd.bpartial);
+  return GDN_OK;
+}
+
+}  // namespace gdn

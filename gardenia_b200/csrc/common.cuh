@@ -87,6 +87,41 @@ struct DevCsr {
   float *heavy_partial = nullptr;  // float[n_heavy_segs]
 };
 
+// Banded shared-memory layout of the heavy rows of the pull layout (band.cu): the column ids of a row that fall into
+// band b = [b * band, (b + 1) * band) of the degree-sorted id space are stored as 16-bit band-local ids in band b's own
+// SELL-32 array (rows of a band sorted by their count in it), and a CTA that holds contrib[band b] in shared memory
+// sums them; what stays behind (cold ids, rows with too few entries in a band) forms a compacted main SELL array.
+struct BandLayout {
+  bool tried = false, built = false;
+  int32_t B = 0, band = 0, cmin = 0, dmin = 0;   // bands, ids per band, min entries of a (row, band) pair, min row length
+  int64_t n_rows = 0;              // sorted rows [0, n_rows) take part (whole slices)
+  uint4 *bsell = nullptr;          // 8 band-local ids (uint16) per unit; item i = units [item_ptr[i], item_ptr[i+1]), lane-interleaved
+  uint64_t n_units = 0;
+  int32_t n_items = 0;             // one item = up to kBandSeg index groups of one band slice (32 rows)
+  uint32_t *item_ptr = nullptr;    // [n_items + 1]
+  int32_t n_jobs = 0;              // a job = a run of items of ONE band given to one CTA, cut into 32 warp runs
+  int4 *job = nullptr;             // [n_jobs] {band, first warp-run boundary index, 0, 0}
+  int32_t *job_first = nullptr;    // [n_cta + 1] jobs of CTA c
+  int32_t *wrun = nullptr;         // [n_jobs * 33] item boundaries of the warp runs
+  int32_t n_cta = 0;
+  float *bpartial = nullptr;       // [n_items * 32] per-row partial sums of the items
+  uint32_t *rslot_ptr = nullptr;   // [n_rows + 1] partial slots of sorted row j ...
+  uint32_t *rslot = nullptr;       // ... in (band, segment) order
+  uint64_t n_rslot = 0;
+  float *acc_main = nullptr;       // [n_rows] sum over the columns left in the main array
+  // the compacted main SELL array and its work tables (same meaning as the PullLayout fields)
+  int4 *sell = nullptr;
+  uint64_t n_groups = 0;
+  uint32_t *slice_ptr = nullptr;
+  int32_t n_chunks = 0;
+  int32_t *chunk_slice = nullptr;
+  int32_t n_heavy_slices = 0, n_heavy_segs = 0;
+  int32_t *heavy_slice = nullptr, *heavy_first = nullptr;
+  int2 *heavy_seg = nullptr;
+  float *partial = nullptr;
+  uint64_t moved = 0, pairs = 0;   // statistics: entries served from shared-memory bands, (row, band) pairs
+};
+
 // Degree-sorted SELL-32 layout of the pull (in-) CSR used by PageRank (pull.cu).
 struct PullLayout {
   bool prepared = false;       // host part done (orders, ids, slice pointers, work items)
@@ -109,6 +144,8 @@ struct PullLayout {
   int32_t *heavy_slice = nullptr, *heavy_first = nullptr;
   int2 *heavy_seg = nullptr;
   float *partial = nullptr;        // [n_heavy_segs * 32]
+  std::vector<uint32_t> h_slice_ptr;   // host copy of slice_ptr (band.cu re-derives work tables from it)
+  BandLayout band;
 };
 
 }  // namespace gdn
@@ -152,7 +189,7 @@ struct gdn_graph {
   int32_t *col_dev = nullptr;
   uint64_t col_next = 0, col_total = 0;
 };
-namespace gdn { int col_upload_rest(gdn_graph *g); }   // graph.cu: queue the remaining pieces of the column array
+namespace gdn { int col_upload_rest(gdn_graph *g); void band_free(BandLayout &b); }   // graph.cu: queue the remaining pieces of the column array
 
 namespace gdn {
 

@@ -401,6 +401,7 @@ int gdn_graph_destroy(gdn_graph *g) {
     cudaFree(L.perm); cudaFree(L.newid); cudaFree(L.sdeg); cudaFree(L.sout); cudaFree(L.rowid); cudaFree(L.slice_ptr);
     cudaFree(L.sell); cudaFree(L.chunk_slice); cudaFree(L.heavy_slice); cudaFree(L.heavy_first); cudaFree(L.heavy_seg);
     cudaFree(L.partial); cudaFree(g->scores_sorted);
+    gdn::band_free(L.band);
   }
   cudaGetLastError();
   delete g;
@@ -412,6 +413,15 @@ int gdn_graph_info(const gdn_graph *g, int64_t info[8]) {
   info[0] = g->m; info[1] = (int64_t)g->in.nnz; info[2] = g->row_lo; info[3] = g->row_hi;
   info[4] = g->in.n_chunks; info[5] = g->in.n_heavy_segs; info[6] = (int64_t)g->device_bytes;
   info[7] = g->in.off64 ? 64 : 32;
+  return GDN_OK;
+}
+
+int gdn_graph_pull_info(const gdn_graph *g, int64_t info[8]) {
+  if (!g || !info) return GDN_ERR_ARG;
+  const gdn::BandLayout &b = g->pull.band;
+  info[0] = b.built ? 1 : 0; info[1] = b.B; info[2] = b.band; info[3] = b.n_rows;
+  info[4] = (int64_t)b.moved; info[5] = (int64_t)b.pairs; info[6] = b.n_items;
+  info[7] = (int64_t)(b.built ? b.n_groups : g->pull.n_groups);
   return GDN_OK;
 }
 

@@ -29,17 +29,13 @@
 //   [ hot slice of rank 0 | ... | hot slice of rank P-1 | cold slice of rank 0 | ... ]
 // so the hot table is one contiguous prefix and each rank still owns two
 // contiguous slices of contrib (two in-place NCCL allgathers per iteration).
-#include "common.cuh"
+#include "pull.cuh"
 #include <omp.h>
 #include <cstdlib>
 #include <algorithm>
 #include <vector>
 
 namespace gdn {
-
-constexpr int kHotMax = 49152;          // fp32 entries in the shared-memory table (192 KB)
-constexpr int kGroupCh = 1024;          // int4 groups per work item (= 4096 column ids)
-constexpr int kSellThreads = 1024;      // one CTA per SM
 
 int comm_size();
 int comm_rank();
@@ -221,6 +217,7 @@ int pull_prepare(gdn_graph *g, const HostOffT *row_off, const HostOffT *key_off)
   }
   sptr[L.n_slices] = (uint32_t)tot;
   L.n_groups = tot;
+  L.h_slice_ptr = sptr;
   // work items: chunk k owns the light slices that START in [k*CH,(k+1)*CH); wide slices are cut into segments
   L.n_chunks = (int32_t)(tot / kGroupCh + 1);
   std::vector<int32_t> chunk((size_t)L.n_chunks + 1);
@@ -477,53 +474,6 @@ int pull_build_sell(gdn_graph *g) {
 }
 
 // ------------------------------------------------------------------ device: the PageRank iteration
-struct SellArgs {
-  const int4 *sell;
-  const uint32_t *slice_ptr;
-  const int32_t *chunk_slice;
-  int32_t n_chunks;
-  const int2 *heavy_seg;
-  const int32_t *heavy_slice, *heavy_first;
-  int32_t n_heavy_segs, n_heavy_slices;
-  float *partial;
-  const float *contrib_in;     // indexed by NEW global id, length Mp
-  float *contrib_out;
-  float *scores;               // sorted local order
-  const int32_t *sdeg;         // row length of sorted row j
-  const int32_t *sout;         // out-degree of sorted row j (nullptr: = sdeg)
-  const int32_t *rowid;        // new global id of sorted row j (nullptr: formula below)
-  int64_t n_nz_rows, rows;
-  int32_t H;
-  int64_t Hp, Wc;
-  int32_t rank;
-  float base, damp;
-  double *err_partial;
-  const int32_t *done;
-  int32_t err_slot0;
-  int32_t warm;                // new ids below this are kept L2-resident; colder ids are gathered evict-first
-  int32_t skip_from;           // TIMING EXPERIMENT ONLY (GDN_PR_SKIP_FROM_MB): ids at or above this are not gathered (wrong results)
-};
-
-__device__ __forceinline__ int64_t row_newid(const SellArgs &a, int64_t j) {
-  if (a.rowid) return a.rowid[j];
-  return j < a.Hp ? (int64_t)a.rank * a.Hp + j : (int64_t)a.H + (int64_t)a.rank * a.Wc + (j - a.Hp);
-}
-
-// scores[dst] = base + damp * sum; error += |new - old|; next contrib   (src/pr/omp_base.cc:24-25,31-33)
-__device__ __forceinline__ void pr_epilogue(const SellArgs &a, int64_t j, float acc, double &err) {
-  // scores / sdeg are touched once per iteration: streaming (evict-first) accesses keep them from
-  // displacing the warm part of contrib in L2; the new contrib of a warm id is stored normally (it is
-  // gathered in the next iteration), a cold one streaming.
-  const float old_score = __ldcs(a.scores + j);
-  const float nw = __fadd_rn(a.base, __fmul_rn(a.damp, acc));
-  __stcs(a.scores + j, nw);
-  err += (double)fabsf(__fsub_rn(nw, old_score));
-  const int32_t deg = a.sout ? __ldcs(a.sout + j) : __ldcs(a.sdeg + j);
-  const int64_t id = row_newid(a, j);
-  const float cv = __fdiv_rn(nw, (float)deg);
-  if (id < a.warm) a.contrib_out[id] = cv; else __stcs(a.contrib_out + id, cv);
-}
-
 // One gathered contrib value.  Three tiers (profiles/r1_gather_microbench_b200.txt): ids < H come from the
 // shared-memory table; ids < warm are the part of contrib that fits the 126 MB L2 and are loaded with an
 // L2 evict-last hint; colder ids (a few % of the edges of a Kronecker graph) are loaded evict-first so that
@@ -704,15 +654,6 @@ struct TripIter {
   }
 };
 
-__device__ __forceinline__ void pr_epilogue_pre(const SellArgs &a, int64_t j, float acc, double &err, float old_score, int32_t deg) {
-  const float nw = __fadd_rn(a.base, __fmul_rn(a.damp, acc));
-  __stcs(a.scores + j, nw);
-  err += (double)fabsf(__fsub_rn(nw, old_score));
-  const int64_t id = row_newid(a, j);
-  const float cv = __fdiv_rn(nw, (float)deg);
-  if (id < a.warm) a.contrib_out[id] = cv; else __stcs(a.contrib_out + id, cv);
-}
-
 // G index groups (4 G gathers) per lane and trip, D trips of gathers in flight per warp, THREADS / 32 warps per SM.
 template <int POLICY, int G, int D, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -755,7 +696,7 @@ pr_sell_pipe(SellArgs a) {
     }
     if (d.fin == 1) {
       const int64_t j = (int64_t)d.ref * 32 + lane;
-      if (j < a.n_nz_rows) { Sc = __ldcs(a.scores + j); Dc = __ldcs(degs + j); }
+      if (j < a.n_nz_rows && j >= a.n_band_rows) { Sc = __ldcs(a.scores + j); Dc = __ldcs(degs + j); }
     }
   };
   auto consume = [&](const float (&W)[4 * G], int32_t flag, int32_t ref, float Sc, int32_t Dc) {
@@ -763,7 +704,8 @@ pr_sell_pipe(SellArgs a) {
     for (int q = 0; q < 4 * G; q++) acc = __fadd_rn(acc, W[q]);
     if ((flag & 3) == 1) {
       const int64_t j = (int64_t)ref * 32 + lane;
-      if (j < a.n_nz_rows) pr_epilogue_pre(a, j, acc, err, Sc, Dc);
+      if (j < a.n_band_rows) a.acc_main[j] = acc;          // whole slices: warp-uniform
+      else if (j < a.n_nz_rows) pr_epilogue_pre(a, j, acc, err, Sc, Dc);
       acc = 0.f;
     } else if ((flag & 3) == 2) {
       a.partial[(size_t)ref * 32 + lane] = acc;
@@ -913,12 +855,20 @@ int pull_exchange(gdn_graph *g, float *contrib, double *err_slot);   // comm.cu
 int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_iter, gdn_stats *st) {
   PullLayout &L = g->pull;
   GDN_CHECK(pull_build_sell(g));
+  // banded shared-memory layout of the heavy rows (band.cu): resident graphs on one GPU; GDN_PR_BANDS=0 turns it off
+  const char *e_bands = getenv("GDN_PR_BANDS");
+  const bool bands_off = e_bands && atoi(e_bands) <= 0;
+  if (!g->one_shot && L.P == 1 && !bands_off) GDN_CHECK(band_build(g));
+  const bool banded = L.band.built && !bands_off;
+  const BandLayout &bd = L.band;
   cudaStream_t s = lib().stream;
   const int sm = lib().sm_count;
   const int wpc = kSellThreads / 32;             // err_partial slots per CTA (the pipelined variants use fewer warps)
-  const int fgrid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)L.n_heavy_slices, (int64_t)sm * 8));   // one CTA per wide slice
+  const int32_t n_heavy_slices = banded ? bd.n_heavy_slices : L.n_heavy_slices;
+  const int fgrid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)n_heavy_slices, (int64_t)sm * 8));   // one CTA per wide slice
   const int igrid = (int)std::max<int64_t>(1, std::min<int64_t>((L.rows - L.n_nz_rows + 255) / 256, (int64_t)sm * 8));
-  const int n_partial = sm * wpc + fgrid * 8 + igrid * 8;
+  const int bgrid = banded ? band_finalize_grid(g) : 0;
+  const int n_partial = sm * wpc + fgrid * 8 + igrid * 8 + bgrid * 8;
   if (!g->contrib[0]) {
     GDN_CUDA(cudaMalloc((void **)&g->contrib[0], sizeof(float) * (L.Mp + 64)));
     GDN_CUDA(cudaMalloc((void **)&g->contrib[1], sizeof(float) * (L.Mp + 64)));
@@ -985,6 +935,12 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
   a.n_nz_rows = L.n_nz_rows; a.rows = L.rows; a.H = (int32_t)L.H; a.Hp = L.Hp; a.Wc = L.Wc; a.rank = L.R;
   a.base = (1.0f - damp) / (float)(int32_t)g->m;            // src/pr/omp_base.cc:16
   a.damp = damp; a.err_partial = g->err_partial; a.done = g->pr_done;
+  if (banded) {
+    a.sell = bd.sell; a.slice_ptr = bd.slice_ptr; a.chunk_slice = bd.chunk_slice; a.n_chunks = bd.n_chunks;
+    a.heavy_seg = bd.heavy_seg; a.heavy_slice = bd.heavy_slice; a.heavy_first = bd.heavy_first;
+    a.n_heavy_segs = bd.n_heavy_segs; a.n_heavy_slices = bd.n_heavy_slices; a.partial = bd.partial;
+    a.n_band_rows = bd.n_rows; a.acc_main = bd.acc_main;
+  }
   a.warm = (int32_t)std::min<int64_t>(warm_ids, 0x7fffffff);
   const char *e_skip = getenv("GDN_PR_SKIP_FROM_MB");
   a.skip_from = e_skip ? (int32_t)std::min<int64_t>((int64_t)atoi(e_skip) * (1 << 20) / 4, 0x7fffffff) : 0x7fffffff;
@@ -1017,17 +973,25 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
       GDN_CUDA(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av));
     }
     kev_begin();
+    if (banded) { GDN_CHECK(band_launch(g, a, s)); launches++; }
     kern<<<sm, threads, smem, s>>>(a);
-    kev_end();
+    if (!banded) kev_end();
     launches++;
     if (persist) {
       cudaStreamAttrValue av = {};
       av.accessPolicyWindow.num_bytes = 0;
       GDN_CUDA(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av));
     }
-    if (L.n_heavy_slices > 0) {
+    if (n_heavy_slices > 0) {
       a.err_slot0 = sm * wpc;
       pr_sell_finalize<<<fgrid, 256, 0, s>>>(a);
+      launches++;
+    }
+    if (banded) {
+      // the iteration of the banded layout is band sums + main sums + the two finalize launches: timed as one
+      a.err_slot0 = sm * wpc + fgrid * 8 + igrid * 8;
+      GDN_CHECK(band_finalize_launch(g, a, bgrid, s));
+      kev_end();
       launches++;
     }
     if (L.rows > L.n_nz_rows && iter == 0) {

@@ -1,0 +1,76 @@
+// pull.cuh -- what pull.cu (SELL PageRank iteration) and band.cu (banded shared-memory part of it) share.
+#pragma once
+#include "common.cuh"
+
+namespace gdn {
+
+constexpr int kHotMax = 49152;          // fp32 entries in the shared-memory table (192 KB)
+constexpr int kGroupCh = 1024;          // int4 groups per work item (= 4096 column ids)
+constexpr int kSellThreads = 1024;      // one CTA per SM
+
+struct SellArgs {
+  const int4 *sell;
+  const uint32_t *slice_ptr;
+  const int32_t *chunk_slice;
+  int32_t n_chunks;
+  const int2 *heavy_seg;
+  const int32_t *heavy_slice, *heavy_first;
+  int32_t n_heavy_segs, n_heavy_slices;
+  float *partial;
+  const float *contrib_in;     // indexed by NEW global id, length Mp
+  float *contrib_out;
+  float *scores;               // sorted local order
+  const int32_t *sdeg;         // row length of sorted row j
+  const int32_t *sout;         // out-degree of sorted row j (nullptr: = sdeg)
+  const int32_t *rowid;        // new global id of sorted row j (nullptr: formula below)
+  int64_t n_nz_rows, rows;
+  int32_t H;
+  int64_t Hp, Wc;
+  int32_t rank;
+  float base, damp;
+  double *err_partial;
+  const int32_t *done;
+  int32_t err_slot0;
+  int32_t warm;                // new ids below this are kept L2-resident; colder ids are gathered evict-first
+  int32_t skip_from;           // TIMING EXPERIMENT ONLY (GDN_PR_SKIP_FROM_MB): ids at or above this are not gathered (wrong results)
+  // banded layout (band.cu): sorted rows below n_band_rows (a multiple of 32) only deposit the sum over the columns left
+  // in the main array; pr_band_finalize adds their band partials and runs the row epilogue
+  int64_t n_band_rows;
+  float *acc_main;
+};
+
+__device__ __forceinline__ int64_t row_newid(const SellArgs &a, int64_t j) {
+  if (a.rowid) return a.rowid[j];
+  return j < a.Hp ? (int64_t)a.rank * a.Hp + j : (int64_t)a.H + (int64_t)a.rank * a.Wc + (j - a.Hp);
+}
+
+// scores[dst] = base + damp * sum; error += |new - old|; next contrib   (src/pr/omp_base.cc:24-25,31-33)
+__device__ __forceinline__ void pr_epilogue_pre(const SellArgs &a, int64_t j, float acc, double &err, float old_score, int32_t deg) {
+  // scores / sdeg are touched once per iteration: streaming (evict-first) accesses keep them from
+  // displacing the warm part of contrib in L2; the new contrib of a warm id is stored normally (it is
+  // gathered in the next iteration), a cold one streaming.
+  const float nw = __fadd_rn(a.base, __fmul_rn(a.damp, acc));
+  __stcs(a.scores + j, nw);
+  err += (double)fabsf(__fsub_rn(nw, old_score));
+  const int64_t id = row_newid(a, j);
+  const float cv = __fdiv_rn(nw, (float)deg);
+  if (id < a.warm) a.contrib_out[id] = cv; else __stcs(a.contrib_out + id, cv);
+}
+__device__ __forceinline__ void pr_epilogue_core(const SellArgs &a, int64_t j, float acc, double &err) {
+  const float old_score = __ldcs(a.scores + j);
+  const int32_t deg = a.sout ? __ldcs(a.sout + j) : __ldcs(a.sdeg + j);
+  pr_epilogue_pre(a, j, acc, err, old_score, deg);
+}
+__device__ __forceinline__ void pr_epilogue(const SellArgs &a, int64_t j, float acc, double &err) {
+  if (j < a.n_band_rows) { a.acc_main[j] = acc; return; }
+  pr_epilogue_core(a, j, acc, err);
+}
+
+// band.cu
+int band_build(gdn_graph *g);
+void band_free(BandLayout &b);
+int band_launch(gdn_graph *g, const SellArgs &a, cudaStream_t s);                       // the band partial sums of one iteration
+int band_finalize_launch(gdn_graph *g, const SellArgs &a, int grid, cudaStream_t s);    // + main sums -> row epilogue
+int band_finalize_grid(const gdn_graph *g);
+
+}  // namespace gdn

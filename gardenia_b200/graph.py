@@ -142,6 +142,13 @@ class DeviceGraph:
         keys = ["m", "nnz_local", "row_lo", "row_hi", "n_row_blocks", "n_heavy_segments", "device_bytes", "offset_bits"]
         return dict(zip(keys, list(a)))
 
+    def pull_info(self):
+        """PageRank pull layout in use (banded shared-memory layout of the heavy rows, csrc/band.cu)."""
+        a = (C.c_int64 * 8)()
+        check(lib.gdn_graph_pull_info(self._h, C.byref(a)))
+        keys = ["banded", "bands", "band_ids", "band_rows", "band_entries", "band_pairs", "band_items", "main_groups"]
+        return dict(zip(keys, list(a)))
+
     def close(self):
         if getattr(self, "_h", None):
             lib.gdn_graph_destroy(self._h)

@@ -140,6 +140,11 @@ int gdn_graph_destroy(gdn_graph *g);
 /* info[0]=m info[1]=nnz_local(in) info[2]=row_lo info[3]=row_hi info[4]=n_row_blocks
  * info[5]=n_heavy_segments info[6]=device_bytes info[7]=offset_bits */
 int gdn_graph_info(const gdn_graph *g, int64_t info[8]);
+/* PageRank pull layout of a resident graph (valid after the first gdn_pagerank_resident call):
+ * info[0]=banded layout in use (0/1) info[1]=bands info[2]=ids per band info[3]=rows taking part
+ * info[4]=column ids served from shared-memory bands info[5]=(row, band) pairs info[6]=band work items
+ * info[7]=int4 groups of the main SELL array in use */
+int gdn_graph_pull_info(const gdn_graph *g, int64_t info[8]);
 
 /* d_* are DEVICE pointers (cudaMalloc / torch tensors) of m elements; results
  * stay on the device.  Timed with CUDA events on the library stream. */

@@ -273,11 +273,13 @@ def test_resident_matches_oneshot_and_is_deterministic():
     st1 = dg.pagerank(s1)
     st2 = dg.pagerank(s2)
     assert st1.iterations == st2.iterations and torch.equal(s1, s2), "PR must be bit-reproducible run to run"
-    # the one-shot entry point builds the SELL layout piece by piece behind the chunked column upload (sell_scatter);
-    # the resident graph builds it slice by slice (sell_fill): same array, hence bit-identical scores
+    # the one-shot entry point keeps the plain SELL layout (built piece by piece behind the chunked column upload,
+    # sell_scatter); the resident graph adds the banded shared-memory layout of its heavy rows (band.cu), which sums a
+    # heavy row band by band: same iteration count, scores within the parity tolerance
     hs = np.full(m, np.float32(1.0) / np.float32(m), dtype=np.float32)
     st3 = gb.PRSolver(g, hs, verbose=False)
-    assert st3.iterations == st1.iterations and np.array_equal(hs, s1.cpu().numpy())
+    assert st3.iterations == st1.iterations
+    assert float(np.abs(hs.astype(np.float64) - s1.cpu().numpy().astype(np.float64)).sum()) <= PR_L1_TOL
     Ax = torch.from_numpy(gb.fill_uniform(13, g.nnz)).cuda()
     x = torch.from_numpy(gb.fill_uniform(14, m)).cuda()
     y1 = torch.zeros(m, device="cuda")
@@ -289,6 +291,99 @@ def test_resident_matches_oneshot_and_is_deterministic():
     y3 = torch.zeros(m, device="cuda")
     dg.spmv(Ax, 2 * x, y3)
     assert torch.equal(y3, 2 * y1)
+    dg.close()
+
+
+def test_resident_plain_layout_is_bit_identical_to_oneshot(monkeypatch):
+    """GDN_PR_BANDS=0: the resident graph walks the same SELL array (sell_fill) as the one-shot call (sell_scatter)."""
+    import torch
+    monkeypatch.setenv("GDN_PR_BANDS", "0")
+    g = gb.Graph.generate("g", 15, 16)
+    dg = gb.DeviceGraph(g)
+    s1 = torch.full((g.m,), 1.0 / g.m, dtype=torch.float32, device="cuda")
+    st1 = dg.pagerank(s1)
+    assert dg.pull_info()["banded"] == 0
+    hs = np.full(g.m, np.float32(1.0) / np.float32(g.m), dtype=np.float32)
+    st3 = gb.PRSolver(g, hs, verbose=False)
+    assert st3.iterations == st1.iterations and np.array_equal(hs, s1.cpu().numpy())
+    dg.close()
+
+
+@pytest.mark.parametrize("kind,scale,bands,band_ids,cmin,dmin", [
+    ("g", 14, 64, 256, 2, 8),        # many small bands: every table reload / job cut / multi-band row is exercised
+    ("g", 16, 24, 1024, 4, 32),
+    ("g", 16, 1, 49152, 1, 1),       # one band holding every id: the main array of the band rows is empty
+    ("u", 14, 16, 1024, 1, 4),       # flat degrees: pairs of one or two ids
+    ("g", 18, 64, 49152, 4, 64),     # the production parameters
+    ("g", 17, 96, 300, 3, 16),       # band size that is not a multiple of anything
+])
+def test_pr_banded_layout(monkeypatch, kind, scale, bands, band_ids, cmin, dmin):
+    """Banded shared-memory layout (csrc/band.cu): same iteration count and scores within 1e-6 L1 of the oracle,
+    bit-reproducible run to run, and the layout must actually be in use (no silent fallback to the plain array)."""
+    import torch
+    monkeypatch.setenv("GDN_PR_BANDS", str(bands))
+    monkeypatch.setenv("GDN_PR_BAND_SIZE", str(band_ids))
+    monkeypatch.setenv("GDN_PR_BAND_CMIN", str(cmin))
+    monkeypatch.setenv("GDN_PR_BAND_DMIN", str(dmin))
+    g = gb.Graph.generate(kind, scale, 16)
+    m, rp, ci = g.m, g.out_rowptr(), g.out_colidx()
+    dg = gb.DeviceGraph(g)
+    s1 = torch.full((m,), float(np.float32(1.0) / np.float32(m)), dtype=torch.float32, device="cuda")
+    s2 = s1.clone()
+    st1 = dg.pagerank(s1)
+    info = dg.pull_info()
+    assert info["banded"] == 1 and info["band_entries"] > 0 and info["band_pairs"] > 0, info
+    assert info["band_entries"] <= g.nnz and info["band_rows"] % 32 == 0
+    st2 = dg.pagerank(s2)
+    assert st1.iterations == st2.iterations and torch.equal(s1, s2), "banded PR must be bit-reproducible run to run"
+    oscores, oit, otrace = po.pr_pull(m, rp, ci, g.out_degrees())
+    assert st1.iterations == oit
+    l1 = float(np.abs(s1.cpu().numpy().astype(np.float64) - oscores.astype(np.float64)).sum())
+    assert l1 <= PR_L1_TOL, l1
+    assert po.pr_residual(m, rp, ci, s1.cpu().numpy()) < 1e-4                       # PRVerifier
+    # the other pipe variants and the one-trip kernel walk the same banded layout
+    for pipe in ("0", "22768"):
+        monkeypatch.setenv("GDN_PR_PIPE", pipe)
+        s3 = torch.full((m,), float(np.float32(1.0) / np.float32(m)), dtype=torch.float32, device="cuda")
+        st3 = dg.pagerank(s3)
+        assert st3.iterations == oit and torch.equal(s3, s1), pipe
+    monkeypatch.delenv("GDN_PR_PIPE")
+    # switching the layout off on the same graph falls back to the plain array
+    monkeypatch.setenv("GDN_PR_BANDS", "0")
+    s4 = torch.full((m,), float(np.float32(1.0) / np.float32(m)), dtype=torch.float32, device="cuda")
+    st4 = dg.pagerank(s4)
+    assert st4.iterations == oit
+    assert float(np.abs(s4.cpu().numpy().astype(np.float64) - oscores.astype(np.float64)).sum()) <= PR_L1_TOL
+    dg.close()
+
+
+def test_pr_banded_layout_directed(monkeypatch):
+    """Directed graph: rows are sorted by in-degree, columns renumbered by out-degree (rowid indirection)."""
+    import torch
+    monkeypatch.setenv("GDN_PR_BANDS", "32")
+    monkeypatch.setenv("GDN_PR_BAND_SIZE", "512")
+    monkeypatch.setenv("GDN_PR_BAND_CMIN", "2")
+    monkeypatch.setenv("GDN_PR_BAND_DMIN", "8")
+    rng = np.random.default_rng(5)
+    m = 20000
+    # skewed directed edges: sources concentrated on low ids
+    src = (rng.random(400000) ** 3 * m).astype(np.int64)
+    dst = rng.integers(0, m, 400000)
+    keep = src != dst
+    e = np.unique(np.stack([src[keep], dst[keep]], 1), axis=0)
+    out_rp = np.zeros(m + 1, np.uint64); np.add.at(out_rp, e[:, 0] + 1, 1); out_rp = np.cumsum(out_rp).astype(np.uint64)
+    out_ci = e[:, 1].astype(np.int32)
+    o = np.lexsort((e[:, 0], e[:, 1]))
+    in_rp = np.zeros(m + 1, np.uint64); np.add.at(in_rp, e[:, 1] + 1, 1); in_rp = np.cumsum(in_rp).astype(np.uint64)
+    in_ci = e[o, 0].astype(np.int32)
+    g = RawGraph(dict(m=m, nnz=len(e), symmetric=False, out_rowptr=out_rp, out_colidx=out_ci, in_rowptr=in_rp, in_colidx=in_ci))
+    dg = gb.DeviceGraph(g)
+    s1 = torch.full((m,), float(np.float32(1.0) / np.float32(m)), dtype=torch.float32, device="cuda")
+    st1 = dg.pagerank(s1)
+    assert dg.pull_info()["banded"] == 1
+    oscores, oit, _ = po.pr_pull(m, in_rp, in_ci, g.out_degrees())
+    assert st1.iterations == oit
+    assert float(np.abs(s1.cpu().numpy().astype(np.float64) - oscores.astype(np.float64)).sum()) <= PR_L1_TOL
     dg.close()
 
 
