@@ -19,7 +19,7 @@
 //
 // The layout is built once per resident graph (untimed, like include/segmenting.h preprocessing of the reference):
 // two device passes over the existing SELL array (count, fill) around a host pass that sorts each band's rows.
-// One GPU only (the multi-GPU id space interleaves the ranks' hot slices); one-shot calls keep the plain layout.
+// Every rank of a row partition bands ITS rows over the shared id space (band_of); one-shot calls keep the plain layout.
 #include "pull.cuh"
 #include <omp.h>
 #include <algorithm>
@@ -29,17 +29,40 @@
 
 namespace gdn {
 
-constexpr int kBandSeg = 64;            // index groups (8 ids each) per lane and item: 512 ids of a row
+constexpr int kBandSeg = 128;           // index groups (8 ids each) per lane and item: 1024 ids of a row
 constexpr int kBandTab = kHotMax + 256; // table entries in shared memory: [band, kBandTab) is zero
 constexpr uint32_t kBandPadId = 0xC0C0; // padding id = a zero table entry; byte-uniform so cudaMemset can write it
 constexpr uint32_t kNone = 0xffffffffu;
 static_assert(kBandPadId >= (uint32_t)kHotMax && kBandPadId < (uint32_t)kBandTab, "padding id must hit the zero tail");
 
+// Which band holds new id c.  The id space is [hot prefix of H ids | cold slice of rank 0 | ... | cold slice of rank
+// P-1] (pull.cu), every slice sorted hottest first: the hot prefix is cut into n0 bands, then the cold slices are cut
+// into pieces of `band` ids that are taken round-robin over the ranks, so that a low band index always means hot ids.
+// On one GPU this is simply b = c / band when band divides H.
+struct BandMap {
+  int32_t band, n0, P, B;
+  int64_t H, Wc;
+};
+__host__ __device__ __forceinline__ uint32_t band_of(const BandMap &mp, int64_t c, uint32_t &local) {
+  if (c < mp.H || mp.Wc <= 0) { const uint32_t b = (uint32_t)(c / mp.band); local = (uint32_t)(c - (int64_t)b * mp.band); return b; }
+  const int64_t off = c - mp.H, q = off / mp.Wc, r = off - q * mp.Wc, t = r / mp.band;
+  local = (uint32_t)(r - t * mp.band);
+  const int64_t b = mp.n0 + t * mp.P + q;
+  return b < mp.B ? (uint32_t)b : 0xffffffffu;
+}
+static void band_range(const BandMap &mp, int b, int64_t &start, int32_t &len) {
+  if (b < mp.n0) { start = (int64_t)b * mp.band; len = (int32_t)std::min<int64_t>(mp.band, mp.H - start); return; }
+  const int64_t k = b - mp.n0, t = k / mp.P, q = k % mp.P;
+  start = mp.H + q * mp.Wc + t * mp.band;
+  len = (int32_t)std::max<int64_t>(0, std::min<int64_t>(mp.band, mp.Wc - t * mp.band));
+}
+
 // ------------------------------------------------------------------ build pass 1: count[b][j]
 // One warp per slice of the existing SELL array (lane = row): how many ids of row j fall into band b.
 __global__ void __launch_bounds__(128)
-band_count(const int4 *__restrict__ sell, const uint32_t *__restrict__ slice_ptr, int32_t nb_slices, int B, uint32_t band,
+band_count(const int4 *__restrict__ sell, const uint32_t *__restrict__ slice_ptr, int32_t nb_slices, BandMap mp,
            uint32_t *__restrict__ cnt, int64_t n_rows) {
+  const int B = mp.B;
   extern __shared__ uint32_t s_u32[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   uint32_t *c = s_u32 + (size_t)wib * B * 32;
@@ -57,7 +80,7 @@ band_count(const int4 *__restrict__ sell, const uint32_t *__restrict__ slice_ptr
         const int v[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
 #pragma unroll
         for (int t = 0; t < 4; t++)
-          if (v[t] >= 0) { const uint32_t b = (uint32_t)v[t] / band; if (b < (uint32_t)B) c[b * 32 + lane]++; }
+          if (v[t] >= 0) { uint32_t loc; const uint32_t b = band_of(mp, v[t], loc); if (b < (uint32_t)B) c[b * 32 + lane]++; }
       }
     }
     for (int b = 0; b < B; b++) cnt[(size_t)b * n_rows + (size_t)s * 32 + lane] = c[b * 32 + lane];
@@ -86,11 +109,12 @@ band_select(uint32_t *__restrict__ cnt, int B, int64_t n_rows, uint32_t cmin, co
 // array).  A lane walks ITS row in column order, so the order of a row's ids inside a band section and inside the
 // compacted main slice is the order they had before.
 __global__ void __launch_bounds__(128)
-band_fill(const int4 *__restrict__ sell, const uint32_t *__restrict__ slice_ptr, int32_t nb_slices, int B, uint32_t band,
+band_fill(const int4 *__restrict__ sell, const uint32_t *__restrict__ slice_ptr, int32_t nb_slices, BandMap mp,
           const uint32_t *__restrict__ rank, int64_t n_rows, const uint32_t *__restrict__ bslice_ptr,
           const int32_t *__restrict__ bslice_first, uint16_t *__restrict__ bsell16, int4 *__restrict__ sell2,
           const uint32_t *__restrict__ slice_ptr2) {
   extern __shared__ uint32_t s_u32[];
+  const int B = mp.B;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   uint32_t *base = s_u32 + (size_t)wib * 2 * B * 32;     // unit of group 0 of this row in band b (kNone: not there)
   uint32_t *kcnt = base + (size_t)B * 32;
@@ -118,12 +142,13 @@ band_fill(const int4 *__restrict__ sell, const uint32_t *__restrict__ slice_ptr,
         for (int t = 0; t < 4; t++) {
           const int c = v[t];
           if (c < 0) continue;
-          const uint32_t b = (uint32_t)c / band;
+          uint32_t loc;
+          const uint32_t b = band_of(mp, c, loc);
           uint32_t bs = kNone;
           if (b < (uint32_t)B) bs = base[b * 32 + lane];
           if (bs != kNone) {
             const uint32_t kk = kcnt[b * 32 + lane]++;
-            bsell16[((size_t)bs + (size_t)(kk >> 3) * 32) * 8 + (kk & 7)] = (uint16_t)((uint32_t)c - b * band);
+            bsell16[((size_t)bs + (size_t)(kk >> 3) * 32) * 8 + (kk & 7)] = (uint16_t)loc;
           } else {
             if (np == 0) pend.x = c; else if (np == 1) pend.y = c; else if (np == 2) pend.z = c; else pend.w = c;
             if (++np == 4) { *dst = pend; dst += 32; pend = make_int4(-1, -1, -1, -1); np = 0; }
@@ -142,8 +167,8 @@ struct BandArgs {
   const int4 *job;
   const int32_t *job_first;
   const int32_t *wrun;
-  int32_t band;
-  int64_t Mp;
+  const int64_t *band_start;   // first new id of band b ...
+  const int32_t *band_len;     // ... and how many ids it holds (<= kHotMax)
   const float *contrib_in;
   float *bpartial;
   const int32_t *done;
@@ -160,9 +185,13 @@ __device__ __forceinline__ uint4 ld_stream_u4(const uint4 *p, uint64_t pol) {
 // PD index groups (8 ids each) requested ahead per lane.  A warp owns a contiguous run of items = one contiguous
 // piece of the band's array: it streams through it without a bubble at item boundaries; the item lengths come 32 at a
 // time (lane i holds the length of item ibase + i) with the next batch requested one batch ahead.
-template <int PD>
-__global__ void __launch_bounds__(kSellThreads, 1)
+// THREADS = 1024: the kernel has the SM to itself.  THREADS = 256 (<= 64 registers): it shares the SM with
+// pr_sell_pipe_co (pull.cu) -- eight warps already saturate the shared-memory pipe, and the main sums of the
+// iteration, which wait on the L1TEX miss path instead, run beside them.
+template <int PD, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 1)
 pr_band_kernel(BandArgs a) {
+  constexpr int kRuns = 32 / (THREADS / 32);             // warp runs of a job per warp
   extern __shared__ float tab[];
   if (*a.done) return;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -171,11 +200,11 @@ pr_band_kernel(BandArgs a) {
   for (int32_t jb = a.job_first[blockIdx.x]; jb < a.job_first[blockIdx.x + 1]; jb++) {
     const int4 J = a.job[jb];
     __syncthreads();                                       // the previous band's readers are done
-    const int64_t id0 = (int64_t)J.x * a.band;
-    for (int i = threadIdx.x; i < kBandTab; i += kSellThreads)
-      tab[i] = (i < a.band && id0 + i < a.Mp) ? a.contrib_in[id0 + i] : 0.f;
+    const int64_t id0 = a.band_start[J.x];
+    const int32_t len = a.band_len[J.x];
+    for (int i = threadIdx.x; i < kBandTab; i += THREADS) tab[i] = i < len ? a.contrib_in[id0 + i] : 0.f;
     __syncthreads();
-    const int32_t i0 = a.wrun[J.y + w], i1 = a.wrun[J.y + w + 1];
+    const int32_t i0 = a.wrun[J.y + w * kRuns], i1 = a.wrun[J.y + (w + 1) * kRuns];
     if (i0 >= i1) continue;
     const uint32_t u0 = a.item_ptr[i0], u1 = a.item_ptr[i1];
     const uint4 *p = a.bsell + u0 + lane;
@@ -215,26 +244,74 @@ pr_band_kernel(BandArgs a) {
 }
 
 // ------------------------------------------------------------------ the iteration: main sum + band partials -> epilogue
+// One warp per 32 sorted rows (lane = row).  The partial slots of the 32 rows are one contiguous run of rslot[]: the
+// warp gathers them kFinCh at a time with coalesced index loads and 8 independent gathers per lane, parks the values
+// in shared memory, and every lane then adds ITS row's slots in slot order -- the order is fixed, the loads are not
+// serialised behind each other (a thread per row walked a hub row's thousands of slots four at a time).
+constexpr int kFinCh = 1024;
+constexpr int kFinCoop = 4 * kFinCh;     // slices with more slots than this are summed by a whole CTA
+
+// gather one chunk of slot values into `val` (coalesced index loads, 8 gathers in flight per lane)
+__device__ __forceinline__ void fin_stage(float *val, const uint32_t *__restrict__ rslot, const float *__restrict__ bpartial,
+                                          uint32_t c0, uint32_t n, int lane) {
+  for (uint32_t i = lane; i < n; i += 256) {
+    float t[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) t[u] = i + 32 * u < n ? __ldcs(bpartial + __ldcs(rslot + c0 + i + 32 * u)) : 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; u++) if (i + 32 * u < n) val[i + 32 * u] = t[u];
+  }
+  __syncwarp();
+}
+
 __global__ void __launch_bounds__(256, 4)
 pr_band_finalize(SellArgs a, const uint32_t *__restrict__ rslot_ptr, const uint32_t *__restrict__ rslot,
-                 const float *__restrict__ bpartial) {
+                 const float *__restrict__ bpartial, int32_t n_coop) {
+  __shared__ float s_val[8][kFinCh];
+  __shared__ float s_acc[8][32];
   if (*a.done) return;
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t warp = (int64_t)blockIdx.x * 8 + w, nwarps = (int64_t)gridDim.x * 8;
+  const int64_t n_sl = a.n_band_rows >> 5;
+  float *val = s_val[w];
   double err = 0.0;
-  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < a.n_band_rows; j += (int64_t)gridDim.x * blockDim.x) {
-    float acc = __ldcs(a.acc_main + j);
-    uint32_t k = rslot_ptr[j];
-    const uint32_t k1 = rslot_ptr[j + 1];
-    for (; k + 4 <= k1; k += 4) {                          // four gathers in flight, added in slot order
-      float t[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) t[u] = __ldcs(bpartial + rslot[k + u]);
-#pragma unroll
-      for (int u = 0; u < 4; u++) acc = __fadd_rn(acc, t[u]);
+  // the hub slices (thousands of slots per row): one CTA per slice, warp w takes chunks w, w + 8, ... and keeps a
+  // per-row sum over ITS chunks in chunk order; warp 0 then adds main sum + the eight warp sums in warp order
+  for (int64_t s = blockIdx.x; s < n_coop; s += gridDim.x) {
+    const int64_t j = s * 32 + lane;
+    const uint32_t my0 = rslot_ptr[j], my1 = rslot_ptr[j + 1];
+    const uint32_t k0 = __shfl_sync(kFull, my0, 0), k1 = __shfl_sync(kFull, my1, 31);
+    float acc = 0.f;
+    for (uint32_t c0 = k0 + (uint32_t)w * kFinCh; c0 < k1; c0 += 8 * kFinCh) {
+      const uint32_t n = min((uint32_t)kFinCh, k1 - c0);
+      fin_stage(val, rslot, bpartial, c0, n, lane);
+      const uint32_t b = max(my0, c0), e = min(my1, c0 + n);
+      for (uint32_t k = b; k < e; k++) acc = __fadd_rn(acc, val[k - c0]);
+      __syncwarp();
     }
-    for (; k < k1; k++) acc = __fadd_rn(acc, __ldcs(bpartial + rslot[k]));
-    if (j < a.n_nz_rows) pr_epilogue_core(a, j, acc, err);
+    s_acc[w][lane] = acc;
+    __syncthreads();
+    if (w == 0) {
+      float tot = __ldcs(a.acc_main + j);
+#pragma unroll
+      for (int u = 0; u < 8; u++) tot = __fadd_rn(tot, s_acc[u][lane]);
+      pr_epilogue_core(a, j, tot, err);
+    }
+    __syncthreads();
+  }
+  for (int64_t s = n_coop + warp; s < n_sl; s += nwarps) {
+    const int64_t j = s * 32 + lane;
+    const uint32_t my0 = rslot_ptr[j], my1 = rslot_ptr[j + 1];
+    const uint32_t k0 = __shfl_sync(kFull, my0, 0), k1 = __shfl_sync(kFull, my1, 31);
+    float acc = __ldcs(a.acc_main + j);
+    for (uint32_t c0 = k0; c0 < k1; c0 += kFinCh) {
+      const uint32_t n = min((uint32_t)kFinCh, k1 - c0);
+      fin_stage(val, rslot, bpartial, c0, n, lane);
+      const uint32_t b = max(my0, c0), e = min(my1, c0 + n);
+      for (uint32_t k = b; k < e; k++) acc = __fadd_rn(acc, val[k - c0]);
+      __syncwarp();
+    }
+    pr_epilogue_core(a, j, acc, err);                     // band rows are non-empty rows (length >= dmin)
   }
   err = warp_sum(err);
   if (lane == 0) a.err_partial[a.err_slot0 + warp] = err;
@@ -273,7 +350,7 @@ static int up(gdn_graph *g, T **dptr, const T *h, size_t n) {
 }
 
 void band_free(BandLayout &b) {
-  cudaFree(b.bsell); cudaFree(b.item_ptr); cudaFree(b.job); cudaFree(b.job_first); cudaFree(b.wrun); cudaFree(b.bpartial);
+  cudaFree(b.bsell); cudaFree(b.band_start); cudaFree(b.band_len); cudaFree(b.item_ptr); cudaFree(b.job); cudaFree(b.job_first); cudaFree(b.wrun); cudaFree(b.bpartial);
   cudaFree(b.rslot_ptr); cudaFree(b.rslot); cudaFree(b.acc_main); cudaFree(b.sell); cudaFree(b.slice_ptr);
   cudaFree(b.chunk_slice); cudaFree(b.heavy_slice); cudaFree(b.heavy_first); cudaFree(b.heavy_seg); cudaFree(b.partial);
   b = BandLayout();
@@ -292,11 +369,16 @@ int band_build(gdn_graph *g) {
   if (bd.tried) return GDN_OK;
   bd.tried = true;
   const int B_want = env_int("GDN_PR_BANDS", 64);
-  if (B_want <= 0 || L.P != 1 || !L.prepared || !L.sell || L.n_slices < 2 || L.h_slice_ptr.empty()) return GDN_OK;
+  if (B_want <= 0 || !L.prepared || !L.sell || L.n_slices < 2 || L.h_slice_ptr.empty()) return GDN_OK;
   const int band = std::min(std::max(env_int("GDN_PR_BAND_SIZE", kHotMax), 32), kHotMax);
   const int cmin = std::max(env_int("GDN_PR_BAND_CMIN", 4), 1);
   const int dmin = std::max(env_int("GDN_PR_BAND_DMIN", 64), 1);
-  const int B = (int)std::min<int64_t>(std::min(B_want, 96), (L.Mp + band - 1) / band);
+  BandMap mp;
+  mp.band = band; mp.P = L.P; mp.H = L.H; mp.Wc = L.Wc;
+  mp.n0 = (int32_t)((L.H + band - 1) / band);
+  const int B = (int)std::min<int64_t>(std::min(B_want, 96), (int64_t)mp.n0 + (L.Wc + band - 1) / band * L.P);
+  mp.B = B;
+  if (B <= 0) return GDN_OK;
   const std::vector<uint32_t> &sp = L.h_slice_ptr;
   // slices whose rows are all at least dmin long: the first row of the NEXT slice is (rows sorted by length, descending)
   int32_t nb = 0;
@@ -315,7 +397,7 @@ int band_build(gdn_graph *g) {
   GDN_CUDA(cudaFuncSetAttribute(band_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
   GDN_CUDA(cudaFuncSetAttribute(band_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
   const int grid = (int)std::min<int64_t>((nb + 3) / 4, (int64_t)sm * 16);
-  band_count<<<grid, 128, smem1, st>>>(L.sell, L.slice_ptr, nb, B, (uint32_t)band, d_cnt, n_rows);
+  band_count<<<grid, 128, smem1, st>>>(L.sell, L.slice_ptr, nb, mp, d_cnt, n_rows);
   band_select<<<(int)std::min<int64_t>((n_rows + 255) / 256, (int64_t)sm * 8), 256, 0, st>>>(d_cnt, B, n_rows, (uint32_t)cmin, L.sdeg, d_remw);
   std::vector<uint32_t> cnt((size_t)B * n_rows), remw((size_t)nb);
   GDN_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, sizeof(uint32_t) * cnt.size(), cudaMemcpyDeviceToHost, st));
@@ -393,6 +475,9 @@ int band_build(gdn_graph *g) {
   uint64_t n_rslot = 0;
   for (int64_t j = 0; j < n_rows; j++) { const uint32_t n = rslot_ptr[j + 1]; rslot_ptr[j] = (uint32_t)n_rslot; n_rslot += n; }
   rslot_ptr[n_rows] = (uint32_t)n_rslot;
+  int32_t n_coop = 0;                              // leading slices whose rows own more than kFinCoop slots together
+  for (int32_t q = 0; q < nb; q++)
+    if (rslot_ptr[(size_t)q * 32 + 32] - rslot_ptr[(size_t)q * 32] > (uint32_t)kFinCoop) n_coop = q + 1;
   if (n_rslot >= 0xfffffff0ull) { cudaFree(d_cnt); cudaFree(d_remw); return GDN_OK; }
   std::vector<uint32_t> rslot(std::max<uint64_t>(n_rslot, 1));
 #pragma omp parallel for
@@ -450,13 +535,18 @@ int band_build(gdn_graph *g) {
   bd.n_units = units; bd.n_items = n_items; bd.n_jobs = (int32_t)job.size(); bd.n_cta = n_cta; bd.n_rslot = n_rslot;
   bd.n_groups = tot2; bd.n_chunks = (int32_t)chunk.size() - 1;
   bd.n_heavy_slices = (int32_t)hslice.size(); bd.n_heavy_segs = (int32_t)hseg.size();
-  bd.moved = moved; bd.pairs = pairs;
+  bd.moved = moved; bd.pairs = pairs; bd.n_fin_coop = n_coop;
   uint32_t *d_rank = d_cnt;                         // the counts are not needed on the device any more
   uint32_t *d_bslice_ptr = nullptr;
   int32_t *d_bslice_first = nullptr;
   GDN_CUDA(cudaMemcpyAsync(d_rank, rank.data(), sizeof(uint32_t) * rank.size(), cudaMemcpyHostToDevice, st));
   GDN_CHECK(up(g, &d_bslice_ptr, bslice_ptr.data(), bslice_ptr.size()));
   GDN_CHECK(up(g, &d_bslice_first, bslice_first.data(), bslice_first.size()));
+  std::vector<int64_t> band_start((size_t)B);
+  std::vector<int32_t> band_len((size_t)B);
+  for (int b = 0; b < B; b++) band_range(mp, b, band_start[b], band_len[b]);
+  GDN_CHECK(up(g, &bd.band_start, band_start.data(), band_start.size()));
+  GDN_CHECK(up(g, &bd.band_len, band_len.data(), band_len.size()));
   GDN_CHECK(up(g, &bd.item_ptr, item_ptr.data(), item_ptr.size()));
   GDN_CHECK(up(g, &bd.job, job.data(), job.size()));
   GDN_CHECK(up(g, &bd.job_first, job_first.data(), job_first.size()));
@@ -481,13 +571,18 @@ int band_build(gdn_graph *g) {
   GDN_CUDA(cudaMemsetAsync(bd.acc_main, 0, sizeof(float) * (size_t)n_rows, st));
   if (tot2 > sp2[nb])
     GDN_CUDA(cudaMemcpyAsync(bd.sell + sp2[nb], L.sell + sp[nb], sizeof(int4) * (size_t)(tot2 - sp2[nb]) + 256, cudaMemcpyDeviceToDevice, st));
-  band_fill<<<grid, 128, smem2, st>>>(L.sell, L.slice_ptr, nb, B, (uint32_t)band, d_rank, n_rows, d_bslice_ptr, d_bslice_first,
+  band_fill<<<grid, 128, smem2, st>>>(L.sell, L.slice_ptr, nb, mp, d_rank, n_rows, d_bslice_ptr, d_bslice_first,
                                       (uint16_t *)bd.bsell, bd.sell, bd.slice_ptr);
   GDN_CUDA(cudaStreamSynchronize(st));
   GDN_CUDA(cudaGetLastError());
   cudaFree(d_cnt); cudaFree(d_remw); cudaFree(d_bslice_ptr); cudaFree(d_bslice_first);
-  GDN_CUDA(cudaFuncSetAttribute(pr_band_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * kBandTab)));
-  GDN_CUDA(cudaFuncSetAttribute(pr_band_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * kBandTab)));
+  GDN_CUDA(cudaFuncSetAttribute(pr_band_kernel<4, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * kBandTab)));
+  GDN_CUDA(cudaFuncSetAttribute(pr_band_kernel<8, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * kBandTab)));
+  GDN_CUDA(cudaFuncSetAttribute(pr_band_kernel<4, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * kBandTab)));
+  GDN_CUDA(cudaFuncSetAttribute(pr_band_kernel<8, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * kBandTab)));
+  // co-resident pair: the SM must be configured for the full 228 KB of shared memory before either CTA arrives
+  GDN_CUDA(cudaFuncSetAttribute(pr_band_kernel<4, 256>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  GDN_CUDA(cudaFuncSetAttribute(pr_band_kernel<8, 256>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   bd.built = true;
   if (getenv("GDN_TRACE"))
     fprintf(stderr, "[gdn] band layout: B=%d band=%d cmin=%d rows=%lld  moved=%llu ids (%.1f %% of nnz) in %llu pairs, %d items, "
@@ -499,24 +594,30 @@ int band_build(gdn_graph *g) {
   return GDN_OK;
 }
 
-int band_launch(gdn_graph *g, const SellArgs &sa, cudaStream_t s) {
+int band_launch(gdn_graph *g, const SellArgs &sa, cudaStream_t s, bool co_resident) {
   const BandLayout &bd = g->pull.band;
   BandArgs a;
   a.bsell = bd.bsell; a.item_ptr = bd.item_ptr; a.job = bd.job; a.job_first = bd.job_first; a.wrun = bd.wrun;
-  a.band = bd.band; a.Mp = g->pull.Mp; a.contrib_in = sa.contrib_in; a.bpartial = bd.bpartial; a.done = sa.done;
+  a.band_start = bd.band_start; a.band_len = bd.band_len; a.contrib_in = sa.contrib_in; a.bpartial = bd.bpartial; a.done = sa.done;
   const size_t smem = sizeof(float) * kBandTab;
-  if (env_int("GDN_PR_BAND_PD", 4) == 8) pr_band_kernel<8><<<bd.n_cta, kSellThreads, smem, s>>>(a);
-  else pr_band_kernel<4><<<bd.n_cta, kSellThreads, smem, s>>>(a);
+  const bool pd8 = env_int("GDN_PR_BAND_PD", 4) == 8;
+  if (co_resident) {
+    if (pd8) pr_band_kernel<8, 256><<<bd.n_cta, 256, smem, s>>>(a);
+    else pr_band_kernel<4, 256><<<bd.n_cta, 256, smem, s>>>(a);
+  } else {
+    if (pd8) pr_band_kernel<8, 1024><<<bd.n_cta, kSellThreads, smem, s>>>(a);
+    else pr_band_kernel<4, 1024><<<bd.n_cta, kSellThreads, smem, s>>>(a);
+  }
   return GDN_OK;
 }
 
 int band_finalize_grid(const gdn_graph *g) {
-  return (int)std::max<int64_t>(1, std::min<int64_t>((g->pull.band.n_rows + 255) / 256, (int64_t)lib().sm_count * 8));
+  return (int)std::max<int64_t>(1, std::min<int64_t>((g->pull.band.n_rows / 32 + 7) / 8, (int64_t)lib().sm_count * 8));
 }
 
 int band_finalize_launch(gdn_graph *g, const SellArgs &a, int grid, cudaStream_t s) {
   const BandLayout &bd = g->pull.band;
-  pr_band_finalize<<<grid, 256, 0, s>>>(a, bd.rslot_ptr, bd.rslot, bd.bpartial);
+  pr_band_finalize<<<grid, 256, 0, s>>>(a, bd.rslot_ptr, bd.rslot, bd.bpartial, bd.n_fin_coop);
   return GDN_OK;
 }
 

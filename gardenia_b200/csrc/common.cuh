@@ -97,6 +97,8 @@ struct BandLayout {
   int64_t n_rows = 0;              // sorted rows [0, n_rows) take part (whole slices)
   uint4 *bsell = nullptr;          // 8 band-local ids (uint16) per unit; item i = units [item_ptr[i], item_ptr[i+1]), lane-interleaved
   uint64_t n_units = 0;
+  int64_t *band_start = nullptr;   // [B] first new id of band b (band.cu band_of: hot prefix, then the ranks' cold slices round-robin)
+  int32_t *band_len = nullptr;     // [B] ids in band b
   int32_t n_items = 0;             // one item = up to kBandSeg index groups of one band slice (32 rows)
   uint32_t *item_ptr = nullptr;    // [n_items + 1]
   int32_t n_jobs = 0;              // a job = a run of items of ONE band given to one CTA, cut into 32 warp runs
@@ -108,6 +110,7 @@ struct BandLayout {
   uint32_t *rslot_ptr = nullptr;   // [n_rows + 1] partial slots of sorted row j ...
   uint32_t *rslot = nullptr;       // ... in (band, segment) order
   uint64_t n_rslot = 0;
+  int32_t n_fin_coop = 0;          // leading slices that pr_band_finalize sums with a whole CTA (hub rows)
   float *acc_main = nullptr;       // [n_rows] sum over the columns left in the main array
   // the compacted main SELL array and its work tables (same meaning as the PullLayout fields)
   int4 *sell = nullptr;

@@ -484,7 +484,7 @@ template <int POLICY>
 __device__ __forceinline__ float pull_one(const SellArgs &a, uint32_t s_hot_addr, const float *s_hot, int c, uint64_t pol_first, uint64_t pol_last) {
   float v = 0.f;
   if (POLICY == 0) {
-    if ((unsigned)c < (unsigned)a.H) v = s_hot[c];
+    if ((unsigned)c < (unsigned)a.hot_n) v = s_hot[c];
     else if (c >= 0) v = __ldg(a.contrib_in + c);
     return v;
   }
@@ -503,7 +503,7 @@ __device__ __forceinline__ float pull_one(const SellArgs &a, uint32_t s_hot_addr
       "@pw ld.global.nc.L2::cache_hint.f32 %0, [%5], %6;\n\t"
       "@pc ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%5], %7;\n\t}"
       : "+f"(v)
-      : "r"(c), "r"(a.H), "r"(a.warm), "r"(s_hot_addr + 4u * (uint32_t)c), "l"(p), "l"(POLICY == 2 ? pol_norm : pol_last), "l"(pol_first), "r"(a.skip_from));
+      : "r"(c), "r"(a.hot_n), "r"(a.warm), "r"(s_hot_addr + 4u * (uint32_t)c), "l"(p), "l"(POLICY == 2 ? pol_norm : pol_last), "l"(pol_first), "r"(a.skip_from));
   return v;
 }
 
@@ -550,7 +550,7 @@ __global__ void __launch_bounds__(kSellThreads, 1)
 pr_sell_kernel(SellArgs a) {
   extern __shared__ float s_hot[];
   if (*a.done) return;
-  for (int i = threadIdx.x; i < a.H; i += kSellThreads) s_hot[i] = a.contrib_in[i];
+  for (int i = threadIdx.x; i < a.hot_n; i += kSellThreads) s_hot[i] = a.contrib_in[i];
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * (kSellThreads / 32) + (threadIdx.x >> 5);
@@ -656,11 +656,10 @@ struct TripIter {
 
 // G index groups (4 G gathers) per lane and trip, D trips of gathers in flight per warp, THREADS / 32 warps per SM.
 template <int POLICY, int G, int D, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1)
-pr_sell_pipe(SellArgs a) {
+__device__ __forceinline__ void pr_sell_pipe_body(const SellArgs &a) {
   extern __shared__ float s_hot[];
   if (*a.done) return;
-  for (int i = threadIdx.x; i < a.H; i += THREADS) s_hot[i] = a.contrib_in[i];
+  for (int i = threadIdx.x; i < a.hot_n; i += THREADS) s_hot[i] = a.contrib_in[i];
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int32_t warp = (int32_t)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
@@ -747,6 +746,16 @@ pr_sell_pipe(SellArgs a) {
   if (lane == 0) a.err_partial[a.err_slot0 + warp] = err;
 }
 
+template <int POLICY, int G, int D, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+pr_sell_pipe(SellArgs a) { pr_sell_pipe_body<POLICY, G, D, THREADS>(a); }
+
+// The same iteration kernel sized to share an SM with pr_band_kernel<256> (band.cu): 768 threads at <= 64 registers
+// (49152 of the SM's 65536; the band CTA takes the other 16384) and a small hot table, so that the shared-memory-bound
+// band sums and the L1TEX-miss-path-bound main sums of an iteration overlap instead of running back to back.
+__global__ void __maxnreg__(64)
+pr_sell_pipe_co(SellArgs a) { pr_sell_pipe_body<1, 1, 2, 768>(a); }
+
 // wide slices: the per-row partials of a slice's segments are added in a FIXED order -- the eight warps of a CTA each
 // add a contiguous run of segments in column order, warp 0 then adds the eight run sums in run order.  (One warp per
 // slice walked up to 500 dependent adds for the hub slices of Kron-26: 0.62 ms per iteration, a tenth of the gather.)
@@ -791,7 +800,9 @@ pr_sell_finalize(SellArgs a) {
 
 // rows without in-edges: score = base (src/pr/omp_base.cc:28-32 with an empty sum).  They reach that
 // fixed point in the first iteration and never move again (L1 delta exactly 0), so this runs ONCE per
-// solve and writes their constant contrib into both buffers.
+// solve and writes their constant contrib into both buffers.  DIRECTED graphs only: such a row may still have
+// out-edges, so its OLD contrib must survive the first iteration's gathers -- this runs after them.  On a symmetric
+// graph its contrib is x / 0, which nothing gathers, and pr_sell_load settles it on the way in.
 __global__ void __launch_bounds__(256, 4)
 pr_sell_isolated(SellArgs a, float *contrib_other) {
   if (*a.done) return;
@@ -815,18 +826,52 @@ pr_sell_isolated(SellArgs a, float *contrib_other) {
   if (lane == 0) a.err_partial[a.err_slot0 + warp] = err;
 }
 
-__global__ void pr_sell_load(const float *__restrict__ scores_user, const int32_t *__restrict__ perm, SellArgs a) {
+// Scores into sorted order + the first contrib (src/pr/omp_base.cc:24-25).  Rows without in-edges are settled here,
+// once per solve: score = base (:28-32 with an empty sum) is their fixed point from the first iteration on (L1 delta
+// exactly 0 afterwards), so their |base - old| goes into the FIRST iteration's error partials and their constant
+// contrib into both buffers; the iteration kernels never touch them.  (Not when max_iter = 0: no iteration runs.)
+__global__ void __launch_bounds__(256, 4)
+pr_sell_load(const float *__restrict__ scores_user, const int32_t *__restrict__ perm, SellArgs a, float *contrib_other,
+             int settle_isolated) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  double err = 0.0;
+  const float nw = __fadd_rn(a.base, __fmul_rn(a.damp, 0.f));
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < a.rows; j += (int64_t)gridDim.x * blockDim.x) {
     const float sc = scores_user[perm[j]];
-    a.scores[j] = sc;
-    const int32_t deg = a.sout ? a.sout[j] : a.sdeg[j];
-    a.contrib_out[row_newid(a, j)] = __fdiv_rn(sc, (float)deg);      // src/pr/omp_base.cc:24-25
+    const int32_t deg = a.sout ? __ldcs(a.sout + j) : __ldcs(a.sdeg + j);
+    const int64_t id = row_newid(a, j);
+    if (j < a.n_nz_rows || !settle_isolated) {
+      a.scores[j] = sc;
+      a.contrib_out[id] = __fdiv_rn(sc, (float)deg);
+    } else {
+      __stcs(a.scores + j, nw);
+      err += (double)fabsf(__fsub_rn(nw, sc));
+      // x / 0 without the division slow path (symmetric graphs: every such row has out-degree 0 too)
+      const float cv = deg != 0 ? __fdiv_rn(nw, (float)deg)
+                                : (nw > 0.f ? __int_as_float(0x7f800000) : nw < 0.f ? __int_as_float(0xff800000) : __int_as_float(0x7fc00000));
+      __stcs(a.contrib_out + id, cv);
+      __stcs(contrib_other + id, cv);
+    }
+  }
+  if (settle_isolated) {
+    err = warp_sum(err);
+    if (lane == 0) a.err_partial[a.err_slot0 + warp] = err;
   }
 }
 __global__ void pr_sell_store(float *__restrict__ scores_user, const int32_t *__restrict__ perm,
                               const float *__restrict__ scores_sorted, int64_t rows) {
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < rows; j += (int64_t)gridDim.x * blockDim.x)
     scores_user[perm[j]] = scores_sorted[j];
+}
+// One GPU, symmetric order (new id of a vertex == its sorted row): coalesced stores, and the settled rows (half the
+// vertices of a Kronecker graph) need no gather at all.
+__global__ void pr_sell_store_gather(float *__restrict__ scores_user, const int32_t *__restrict__ newid,
+                                     const float *__restrict__ scores_sorted, int64_t m, int64_t n_nz_rows, float iso, int use_iso) {
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < m; v += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t j = __ldcs(newid + v);
+    __stcs(scores_user + v, (use_iso && j >= n_nz_rows) ? iso : __ldcs(scores_sorted + j));
+  }
 }
 __global__ void gather_i32(const int32_t *__restrict__ src, const int32_t *__restrict__ perm, int32_t *__restrict__ dst, int64_t n) {
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) dst[j] = src[perm[j]];
@@ -855,10 +900,10 @@ int pull_exchange(gdn_graph *g, float *contrib, double *err_slot);   // comm.cu
 int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_iter, gdn_stats *st) {
   PullLayout &L = g->pull;
   GDN_CHECK(pull_build_sell(g));
-  // banded shared-memory layout of the heavy rows (band.cu): resident graphs on one GPU; GDN_PR_BANDS=0 turns it off
+  // banded shared-memory layout of the heavy rows (band.cu): resident graphs; GDN_PR_BANDS=0 turns it off
   const char *e_bands = getenv("GDN_PR_BANDS");
   const bool bands_off = e_bands && atoi(e_bands) <= 0;
-  if (!g->one_shot && L.P == 1 && !bands_off) GDN_CHECK(band_build(g));
+  if (!g->one_shot && !bands_off) GDN_CHECK(band_build(g));
   const bool banded = L.band.built && !bands_off;
   const BandLayout &bd = L.band;
   cudaStream_t s = lib().stream;
@@ -866,7 +911,7 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
   const int wpc = kSellThreads / 32;             // err_partial slots per CTA (the pipelined variants use fewer warps)
   const int32_t n_heavy_slices = banded ? bd.n_heavy_slices : L.n_heavy_slices;
   const int fgrid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)n_heavy_slices, (int64_t)sm * 8));   // one CTA per wide slice
-  const int igrid = (int)std::max<int64_t>(1, std::min<int64_t>((L.rows - L.n_nz_rows + 255) / 256, (int64_t)sm * 8));
+  const int igrid = sm * 8;                        // pr_sell_load's grid: its warps own the error partials of the settled rows
   const int bgrid = banded ? band_finalize_grid(g) : 0;
   const int n_partial = sm * wpc + fgrid * 8 + igrid * 8 + bgrid * 8;
   if (!g->contrib[0]) {
@@ -889,7 +934,7 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
     g->n_err_partial = n_partial;
   }
   if (max_iter > GDN_MAX_PR_ITER - 1) max_iter = GDN_MAX_PR_ITER - 1;
-  const size_t smem = sizeof(float) * (size_t)L.H;
+  size_t smem = sizeof(float) * (size_t)L.H;
   // L2 residency tiers of the gathered vector (see pull_one); tunables for the profiling scripts
   const char *e_pol = getenv("GDN_PR_POLICY"), *e_warm = getenv("GDN_PR_WARM_MB");
   const int policy = e_pol ? atoi(e_pol) : 1;
@@ -917,6 +962,24 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
       default: kern = pr_sell_pipe<1, 1, 2, 1024>; threads = 1024; break;   // measured best of the sweep (profiles/r1_pr_pipe_sweep.txt)
     }
   }
+  // GDN_PR_OVERLAP=1 (banded layout only): the band sums run on a second stream in 256-thread CTAs that share each SM
+  // with a 768-thread main CTA (pr_sell_pipe_co, 32 KB hot table)
+  const char *e_ovl = getenv("GDN_PR_OVERLAP");
+  const bool overlap = banded && policy == 1 && pipe != 0 && (e_ovl ? atoi(e_ovl) > 0 : false);
+  static cudaStream_t s2 = nullptr;
+  static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int32_t hot_n = (int32_t)L.H;
+  if (overlap) {
+    if (!s2) {
+      GDN_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+      GDN_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+      GDN_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    }
+    const char *e_hot = getenv("GDN_PR_CO_HOT");
+    hot_n = (int32_t)std::min<int64_t>(L.H, e_hot ? atoi(e_hot) : 8192);
+    kern = pr_sell_pipe_co; threads = 768;
+    GDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  }
   const char *e_persist = getenv("GDN_PR_PERSIST");
   const int persist_mb = e_persist ? atoi(e_persist) : 0;
   const bool persist = persist_mb > 0;
@@ -925,6 +988,7 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
     GDN_CUDA(cudaGetDeviceProperties(&prop, lib().device));
     GDN_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize));
   }
+  if (overlap) smem = sizeof(float) * (size_t)hot_n;
   GDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
   SellArgs a = {};
@@ -932,7 +996,7 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
   a.heavy_seg = L.heavy_seg; a.heavy_slice = L.heavy_slice; a.heavy_first = L.heavy_first;
   a.n_heavy_segs = L.n_heavy_segs; a.n_heavy_slices = L.n_heavy_slices; a.partial = L.partial;
   a.scores = g->scores_sorted; a.sdeg = L.sdeg; a.sout = L.sout; a.rowid = L.rowid;
-  a.n_nz_rows = L.n_nz_rows; a.rows = L.rows; a.H = (int32_t)L.H; a.Hp = L.Hp; a.Wc = L.Wc; a.rank = L.R;
+  a.n_nz_rows = L.n_nz_rows; a.rows = L.rows; a.H = (int32_t)L.H; a.hot_n = hot_n; a.Hp = L.Hp; a.Wc = L.Wc; a.rank = L.R;
   a.base = (1.0f - damp) / (float)(int32_t)g->m;            // src/pr/omp_base.cc:16
   a.damp = damp; a.err_partial = g->err_partial; a.done = g->pr_done;
   if (banded) {
@@ -954,7 +1018,11 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
   GDN_CUDA(cudaMemsetAsync(g->pr_done, 0, sizeof(int32_t), s));
   GDN_CUDA(cudaMemsetAsync(g->err_partial, 0, sizeof(double) * n_partial, s));
   a.contrib_out = g->contrib[0];
-  pr_sell_load<<<sm * 8, 256, 0, s>>>(d_scores, L.perm, a);
+  // rows without in-edges: settled by pr_sell_load (symmetric graph) or by pr_sell_isolated after the first iteration
+  const bool have_iso = max_iter > 0 && L.rows > L.n_nz_rows;
+  const int settle = (have_iso && !a.sout) ? 1 : 0;
+  a.err_slot0 = sm * wpc + fgrid * 8;
+  pr_sell_load<<<igrid, 256, 0, s>>>(d_scores, L.perm, a, g->contrib[1], settle);
   launches++;
   GDN_CHECK(pull_exchange(g, g->contrib[0], nullptr));
   int iter, cur = 0;
@@ -973,7 +1041,17 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
       GDN_CUDA(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av));
     }
     kev_begin();
-    if (banded) { GDN_CHECK(band_launch(g, a, s)); launches++; }
+    if (banded) {
+      if (overlap) {
+        GDN_CUDA(cudaEventRecord(ev_fork, s));
+        GDN_CUDA(cudaStreamWaitEvent(s2, ev_fork, 0));
+        GDN_CHECK(band_launch(g, a, s2, true));
+        GDN_CUDA(cudaEventRecord(ev_join, s2));
+      } else {
+        GDN_CHECK(band_launch(g, a, s, false));
+      }
+      launches++;
+    }
     kern<<<sm, threads, smem, s>>>(a);
     if (!banded) kev_end();
     launches++;
@@ -990,15 +1068,16 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
     if (banded) {
       // the iteration of the banded layout is band sums + main sums + the two finalize launches: timed as one
       a.err_slot0 = sm * wpc + fgrid * 8 + igrid * 8;
+      if (overlap) GDN_CUDA(cudaStreamWaitEvent(s, ev_join, 0));
       GDN_CHECK(band_finalize_launch(g, a, bgrid, s));
       kev_end();
       launches++;
     }
-    if (L.rows > L.n_nz_rows && iter == 0) {
+    if (have_iso && !settle && iter == 0) {
       a.err_slot0 = sm * wpc + fgrid * 8;
       pr_sell_isolated<<<igrid, 256, 0, s>>>(a, g->contrib[cur]);
       launches++;
-    } else if (L.rows > L.n_nz_rows && iter == 1) {
+    } else if (have_iso && iter == 1) {            // the settled rows' deltas belonged to the first iteration
       GDN_CUDA(cudaMemsetAsync(g->err_partial + sm * wpc + fgrid * 8, 0, sizeof(double) * igrid * 8, s));
     }
     pr_reduce_err2<<<1, 256, 0, s>>>(g->err_partial, n_partial, g->err_trace, iter, multi ? -1.0 : eps, g->pr_done);
@@ -1010,7 +1089,11 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
     cur ^= 1;
     if (*h_err < eps) break;                                 // src/pr/omp_base.cc:36
   }
-  pr_sell_store<<<sm * 8, 256, 0, s>>>(d_scores, L.perm, g->scores_sorted, L.rows);
+  if (L.P == 1 && L.symmetric_order && L.rows == g->m && !L.rowid)
+    pr_sell_store_gather<<<sm * 8, 256, 0, s>>>(d_scores, L.newid, g->scores_sorted, g->m, L.n_nz_rows,
+                                                 a.base /* = base + damp * 0 */, settle);
+  else
+    pr_sell_store<<<sm * 8, 256, 0, s>>>(d_scores, L.perm, g->scores_sorted, L.rows);
   launches++;
   GDN_CUDA(cudaEventRecord(lib().ev1, s));
   GDN_CUDA(cudaStreamSynchronize(s));

@@ -24,7 +24,8 @@ struct SellArgs {
   const int32_t *sout;         // out-degree of sorted row j (nullptr: = sdeg)
   const int32_t *rowid;        // new global id of sorted row j (nullptr: formula below)
   int64_t n_nz_rows, rows;
-  int32_t H;
+  int32_t H;                   // hot ids of the id space (row_newid)
+  int32_t hot_n;               // entries of the shared-memory table (<= H)
   int64_t Hp, Wc;
   int32_t rank;
   float base, damp;
@@ -69,7 +70,7 @@ __device__ __forceinline__ void pr_epilogue(const SellArgs &a, int64_t j, float 
 // band.cu
 int band_build(gdn_graph *g);
 void band_free(BandLayout &b);
-int band_launch(gdn_graph *g, const SellArgs &a, cudaStream_t s);                       // the band partial sums of one iteration
+int band_launch(gdn_graph *g, const SellArgs &a, cudaStream_t s, bool co_resident);                       // the band partial sums of one iteration
 int band_finalize_launch(gdn_graph *g, const SellArgs &a, int grid, cudaStream_t s);    // + main sums -> row epilogue
 int band_finalize_grid(const gdn_graph *g);
 

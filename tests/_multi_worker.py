@@ -27,7 +27,12 @@ def main():
     uid = t.cpu().numpy()
     _lib.check(_lib.lib.gdn_comm_init(rank, world, uid.ctypes.data))
     ok = True
-    for kind, scale in (("g", 16), ("u", 15)):
+    # third case: many small bands, so that the banded layout (csrc/band.cu) spreads over every rank's cold slice
+    small = dict(GDN_PR_BANDS="96", GDN_PR_BAND_SIZE="512", GDN_PR_BAND_CMIN="2", GDN_PR_BAND_DMIN="8")
+    for kind, scale, env in (("g", 16, {}), ("u", 15, {}), ("g", 17, small)):
+        for k in small:
+            os.environ.pop(k, None)
+        os.environ.update(env)
         g = gb.Graph.generate(kind, scale, 16)
         m = g.m
         b = gb.partition_rows(m, world)
@@ -37,6 +42,9 @@ def main():
         # ---- PageRank
         scores = torch.full((hi - lo,), float(np.float32(1.0) / np.float32(m)), dtype=torch.float32, device=dev)
         st = dg.pagerank(scores)
+        pinfo = dg.pull_info()
+        if kind == "g":
+            assert pinfo["banded"] == 1 and pinfo["band_entries"] > 0, pinfo       # no silent fallback to the plain layout
         full = torch.zeros(w * world, dtype=torch.float32, device=dev)
         full[lo:hi] = scores
         dist.all_gather_into_tensor(full, full[rank * w:(rank + 1) * w].clone())
@@ -53,7 +61,8 @@ def main():
             oscores, oit, _ = po.pr_pull(m, rp, ci, g.out_degrees())
             l1 = float(np.abs(full[:m].cpu().numpy().astype(np.float64) - oscores.astype(np.float64)).sum())
             good = (st.iterations == oit) and l1 <= 1e-6
-            print(f"[multi] {kind}{scale} world={world} PR iters {st.iterations} vs {oit} l1={l1:.3e} {'OK' if good else 'FAIL'}", flush=True)
+            print(f"[multi] {kind}{scale} world={world} PR iters {st.iterations} vs {oit} l1={l1:.3e} {'OK' if good else 'FAIL'} "
+                  f"bands={pinfo['bands']}x{pinfo['band_ids']} band_entries={pinfo['band_entries']}", flush=True)
             ok &= good
             for s, (d, it) in zip(srcs, depths):
                 od, oit, _ = po.bfs_do(m, rp, ci, rp, ci, s)

@@ -348,6 +348,13 @@ def test_pr_banded_layout(monkeypatch, kind, scale, bands, band_ids, cmin, dmin)
         st3 = dg.pagerank(s3)
         assert st3.iterations == oit and torch.equal(s3, s1), pipe
     monkeypatch.delenv("GDN_PR_PIPE")
+    # band sums and main sums on two streams, sharing each SM (pr_band_kernel<.,256> + pr_sell_pipe_co): same sums
+    for ovl in ("1", "0"):
+        monkeypatch.setenv("GDN_PR_OVERLAP", ovl)
+        s3 = torch.full((m,), float(np.float32(1.0) / np.float32(m)), dtype=torch.float32, device="cuda")
+        st3 = dg.pagerank(s3)
+        assert st3.iterations == oit and torch.equal(s3, s1), ("overlap", ovl)
+    monkeypatch.delenv("GDN_PR_OVERLAP")
     # switching the layout off on the same graph falls back to the plain array
     monkeypatch.setenv("GDN_PR_BANDS", "0")
     s4 = torch.full((m,), float(np.float32(1.0) / np.float32(m)), dtype=torch.float32, device="cuda")
