@@ -257,7 +257,7 @@ def main():
     if pinfo["banded"]:
         # one iteration of the banded layout (csrc/band.cu) is four launches timed as one unit
         kernel_name = ("pr_band_kernel + pr_sell_pipe + pr_sell_finalize + pr_band_finalize (the launches of ONE PageRank iteration "
-                       f"over all rows; {pinfo['band_entries'] / max(nnz, 1):.1%} of the column ids are gathered from {pinfo['bands']} "
+                       f"over this rank's rows; {pinfo['band_entries'] / max(info['nnz_local'], 1):.1%} of their column ids are gathered from {pinfo['bands']} "
                        "shared-memory bands)")
     else:
         kernel_name = "pr_sell_pipe (one launch = one PageRank iteration over all rows)"
@@ -306,6 +306,7 @@ def main():
     h2d = d2h = 0
     e2e_s = 0.0
     e2e_calls = []
+    e2e_parts = []           # per call: [upload + layout, solve, download] ms as the library timed them
     for k in range(e2e_steps + 1):
         if world == 1:
             hs = h_scores.numpy()
@@ -317,6 +318,9 @@ def main():
         else:
             h_scores.fill_(init)
             barrier()
+            # one solve per upload: the banded layout (1.3 s of preprocessing) would not amortise -- plain SELL layout,
+            # as the single-GPU one-shot entry point chooses by itself
+            os.environ["GDN_PR_BANDS"] = "0"
             t_call = time.perf_counter()
             dgi = gb.DeviceGraph(g, lo, hi, device=local_rank)
             sc = h_scores.to(dev, non_blocking=True)
@@ -332,9 +336,10 @@ def main():
         e_iters += st.iterations
         e2e_s += dt
         e2e_calls.append(round(dt * 1e3, 1))
+        e2e_parts.append([round(float(getattr(st, "h2d_ms", 0.0)), 1), round(float(st.solve_ms), 1), round(float(getattr(st, "d2h_ms", 0.0)), 1)])
     e2e_s = allmax(e2e_s)
     e2e = {"value": e_iters / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-           "steps": e2e_steps, "ms_per_step": e2e_s * 1e3 / e2e_steps, "ms_per_call": e2e_calls,
+           "steps": e2e_steps, "ms_per_step": e2e_s * 1e3 / e2e_steps, "ms_per_call": e2e_calls, "h2d_solve_d2h_ms_per_call": e2e_parts,
            "median_ms_per_call": sorted(e2e_calls)[len(e2e_calls) // 2],
            "timed": "wall clock around each PRSolver call on pinned host arrays (1 warm-up call)"}
 

@@ -29,7 +29,7 @@
 
 namespace gdn {
 
-constexpr int kBandSeg = 128;           // index groups (8 ids each) per lane and item: 1024 ids of a row
+constexpr int kBandSeg = 64;            // index groups (8 ids each) per lane and item: 512 ids of a row
 constexpr int kBandTab = kHotMax + 256; // table entries in shared memory: [band, kBandTab) is zero
 constexpr uint32_t kBandPadId = 0xC0C0; // padding id = a zero table entry; byte-uniform so cudaMemset can write it
 constexpr uint32_t kNone = 0xffffffffu;
@@ -244,6 +244,33 @@ pr_band_kernel(BandArgs a) {
 }
 
 // ------------------------------------------------------------------ the iteration: main sum + band partials -> epilogue
+__global__ void __launch_bounds__(256, 4)
+pr_band_finalize(SellArgs a, const uint32_t *__restrict__ rslot_ptr, const uint32_t *__restrict__ rslot,
+                 const float *__restrict__ bpartial) {
+  if (*a.done) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  double err = 0.0;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < a.n_band_rows; j += (int64_t)gridDim.x * blockDim.x) {
+    float acc = __ldcs(a.acc_main + j);
+    uint32_t k = rslot_ptr[j];
+    const uint32_t k1 = rslot_ptr[j + 1];
+    for (; k + 4 <= k1; k += 4) {                          // four gathers in flight, added in slot order
+      float t[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) t[u] = __ldcs(bpartial + rslot[k + u]);
+#pragma unroll
+      for (int u = 0; u < 4; u++) acc = __fadd_rn(acc, t[u]);
+    }
+    for (; k < k1; k++) acc = __fadd_rn(acc, __ldcs(bpartial + rslot[k]));
+    if (j < a.n_nz_rows) pr_epilogue_core(a, j, acc, err);
+  }
+  err = warp_sum(err);
+  if (lane == 0) a.err_partial[a.err_slot0 + warp] = err;
+}
+
+// Alternative (GDN_PR_BAND_FIN=1): cooperative gathers.  Measured SLOWER at Kron-26 (iteration 4.42 -> 4.70 ms): the
+// thread-per-row version above already keeps 600 K gathers in flight chip-wide, and the staging pass is pure overhead.
 // One warp per 32 sorted rows (lane = row).  The partial slots of the 32 rows are one contiguous run of rslot[]: the
 // warp gathers them kFinCh at a time with coalesced index loads and 8 independent gathers per lane, parks the values
 // in shared memory, and every lane then adds ITS row's slots in slot order -- the order is fixed, the loads are not
@@ -265,7 +292,7 @@ __device__ __forceinline__ void fin_stage(float *val, const uint32_t *__restrict
 }
 
 __global__ void __launch_bounds__(256, 4)
-pr_band_finalize(SellArgs a, const uint32_t *__restrict__ rslot_ptr, const uint32_t *__restrict__ rslot,
+pr_band_finalize_coop(SellArgs a, const uint32_t *__restrict__ rslot_ptr, const uint32_t *__restrict__ rslot,
                  const float *__restrict__ bpartial, int32_t n_coop) {
   __shared__ float s_val[8][kFinCh];
   __shared__ float s_acc[8][32];
@@ -594,6 +621,26 @@ int band_build(gdn_graph *g) {
   return GDN_OK;
 }
 
+}  // namespace gdn
+
+// Host-only probe of the id -> band map (tests/test_host.py): no device needed.
+extern "C" int gdn_band_map_probe(int64_t H, int64_t Wc, int32_t P, int32_t band, int32_t B, int64_t id, int32_t *band_out,
+                                  int32_t *local_out, int64_t *start_out, int32_t *len_out) {
+  if (H < 0 || Wc < 0 || P < 1 || band < 1 || B < 1 || id < 0 || !band_out || !local_out || !start_out || !len_out) return GDN_ERR_ARG;
+  gdn::BandMap mp;
+  mp.band = band; mp.P = P; mp.H = H; mp.Wc = Wc; mp.B = B;
+  mp.n0 = (int32_t)((H + band - 1) / band);
+  uint32_t loc = 0;
+  const uint32_t b = gdn::band_of(mp, id, loc);
+  *band_out = (b < (uint32_t)B) ? (int32_t)b : -1;
+  *local_out = (int32_t)loc;
+  *start_out = 0; *len_out = 0;
+  if (*band_out >= 0) gdn::band_range(mp, *band_out, *start_out, *len_out);
+  return GDN_OK;
+}
+
+namespace gdn {
+
 int band_launch(gdn_graph *g, const SellArgs &sa, cudaStream_t s, bool co_resident) {
   const BandLayout &bd = g->pull.band;
   BandArgs a;
@@ -612,12 +659,17 @@ int band_launch(gdn_graph *g, const SellArgs &sa, cudaStream_t s, bool co_reside
 }
 
 int band_finalize_grid(const gdn_graph *g) {
-  return (int)std::max<int64_t>(1, std::min<int64_t>((g->pull.band.n_rows / 32 + 7) / 8, (int64_t)lib().sm_count * 8));
+  return (int)std::max<int64_t>(1, std::min<int64_t>((g->pull.band.n_rows + 255) / 256, (int64_t)lib().sm_count * 8));
 }
 
 int band_finalize_launch(gdn_graph *g, const SellArgs &a, int grid, cudaStream_t s) {
   const BandLayout &bd = g->pull.band;
-  pr_band_finalize<<<grid, 256, 0, s>>>(a, bd.rslot_ptr, bd.rslot, bd.bpartial, bd.n_fin_coop);
+  if (env_int("GDN_PR_BAND_FIN", 0) == 1) {
+    const int cgrid = (int)std::max<int64_t>(1, std::min<int64_t>((bd.n_rows / 32 + 7) / 8, (int64_t)grid));
+    pr_band_finalize_coop<<<cgrid, 256, 0, s>>>(a, bd.rslot_ptr, bd.rslot, bd.bpartial, bd.n_fin_coop);
+  } else {
+    pr_band_finalize<<<grid, 256, 0, s>>>(a, bd.rslot_ptr, bd.rslot, bd.bpartial);
+  }
   return GDN_OK;
 }
 

@@ -489,13 +489,14 @@ __device__ __forceinline__ float pull_one(const SellArgs &a, uint32_t s_hot_addr
     return v;
   }
   const float *p = a.contrib_in + c;
+  const int32_t t = tier_id(a, c);
   uint64_t pol_norm = 0;
   if (POLICY == 2) asm volatile("createpolicy.fractional.L2::evict_unchanged.b64 %0, 1.0;" : "=l"(pol_norm));
   asm volatile(
       "{\n\t.reg .pred ph, pw, pc, ph2;\n\t"
       "setp.lt.u32 ph, %1, %2;\n\t"               // hot: 0 <= c < H   (c = -1 is 0xffffffff: never hot)
       "setp.ge.s32 pw, %1, %2;\n\t"               // not hot and not padding
-      "setp.ge.s32 pc, %1, %3;\n\t"               // cold
+      "setp.ge.s32 pc, %9, %3;\n\t"               // cold (by its position inside its rank's slice)
       "and.pred pw, pw, !pc;\n\t"
       "setp.lt.s32 ph2, %1, %8;\n\t"
       "and.pred pc, pc, ph2;\n\t"
@@ -503,7 +504,7 @@ __device__ __forceinline__ float pull_one(const SellArgs &a, uint32_t s_hot_addr
       "@pw ld.global.nc.L2::cache_hint.f32 %0, [%5], %6;\n\t"
       "@pc ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%5], %7;\n\t}"
       : "+f"(v)
-      : "r"(c), "r"(a.hot_n), "r"(a.warm), "r"(s_hot_addr + 4u * (uint32_t)c), "l"(p), "l"(POLICY == 2 ? pol_norm : pol_last), "l"(pol_first), "r"(a.skip_from));
+      : "r"(c), "r"(a.hot_n), "r"(a.warm), "r"(s_hot_addr + 4u * (uint32_t)c), "l"(p), "l"(POLICY == 2 ? pol_norm : pol_last), "l"(pol_first), "r"(a.skip_from), "r"(t));
   return v;
 }
 
@@ -1005,7 +1006,9 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
     a.n_heavy_segs = bd.n_heavy_segs; a.n_heavy_slices = bd.n_heavy_slices; a.partial = bd.partial;
     a.n_band_rows = bd.n_rows; a.acc_main = bd.acc_main;
   }
-  a.warm = (int32_t)std::min<int64_t>(warm_ids, 0x7fffffff);
+  a.P = L.P; a.inv_wc = L.Wc > 0 ? 1.0f / (float)L.Wc : 0.f;
+  // the warm budget is shared by the ranks' slices (tier_id): every rank's hottest cold ids stay L2-resident
+  a.warm = (int32_t)std::min<int64_t>(L.P > 1 ? L.H + std::max<int64_t>(warm_ids - L.H, 0) / L.P : warm_ids, 0x7fffffff);
   const char *e_skip = getenv("GDN_PR_SKIP_FROM_MB");
   a.skip_from = e_skip ? (int32_t)std::min<int64_t>((int64_t)atoi(e_skip) * (1 << 20) / 4, 0x7fffffff) : 0x7fffffff;
   a.warm = std::min(a.warm, a.skip_from);

@@ -32,7 +32,9 @@ struct SellArgs {
   double *err_partial;
   const int32_t *done;
   int32_t err_slot0;
-  int32_t warm;                // new ids below this are kept L2-resident; colder ids are gathered evict-first
+  int32_t warm;                // ids whose tier_id is below this are kept L2-resident; colder ids are gathered evict-first
+  int32_t P;                   // ranks of the row partition the id space was laid out for
+  float inv_wc;                // 1 / Wc
   int32_t skip_from;           // TIMING EXPERIMENT ONLY (GDN_PR_SKIP_FROM_MB): ids at or above this are not gathered (wrong results)
   // banded layout (band.cu): sorted rows below n_band_rows (a multiple of 32) only deposit the sum over the columns left
   // in the main array; pr_band_finalize adds their band partials and runs the row epilogue
@@ -45,6 +47,19 @@ __device__ __forceinline__ int64_t row_newid(const SellArgs &a, int64_t j) {
   return j < a.Hp ? (int64_t)a.rank * a.Hp + j : (int64_t)a.H + (int64_t)a.rank * a.Wc + (j - a.Hp);
 }
 
+// Hotness rank of a new id for the L2 residency tiers.  One GPU: the id itself (ids are sorted hottest first).  Row
+// partition: the id space is [hot prefix | cold slice of rank 0 | ... ], every slice hottest first, so the rank is the
+// position INSIDE the slice.  The float quotient may be off by one at a slice boundary: that only mislabels the cache
+// policy of a few ids, never an address.
+__device__ __forceinline__ int32_t tier_id(const SellArgs &a, int32_t c) {
+  if (a.P > 1 && c >= a.H) {
+    const uint32_t cw = (uint32_t)(c - a.H);
+    const uint32_t q = (uint32_t)__fmul_rz((float)cw, a.inv_wc);
+    return a.H + (int32_t)(cw - q * (uint32_t)a.Wc);
+  }
+  return c;
+}
+
 // scores[dst] = base + damp * sum; error += |new - old|; next contrib   (src/pr/omp_base.cc:24-25,31-33)
 __device__ __forceinline__ void pr_epilogue_pre(const SellArgs &a, int64_t j, float acc, double &err, float old_score, int32_t deg) {
   // scores / sdeg are touched once per iteration: streaming (evict-first) accesses keep them from
@@ -55,7 +70,7 @@ __device__ __forceinline__ void pr_epilogue_pre(const SellArgs &a, int64_t j, fl
   err += (double)fabsf(__fsub_rn(nw, old_score));
   const int64_t id = row_newid(a, j);
   const float cv = __fdiv_rn(nw, (float)deg);
-  if (id < a.warm) a.contrib_out[id] = cv; else __stcs(a.contrib_out + id, cv);
+  if (tier_id(a, (int32_t)id) < a.warm) a.contrib_out[id] = cv; else __stcs(a.contrib_out + id, cv);
 }
 __device__ __forceinline__ void pr_epilogue_core(const SellArgs &a, int64_t j, float acc, double &err) {
   const float old_score = __ldcs(a.scores + j);

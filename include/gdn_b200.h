@@ -145,6 +145,11 @@ int gdn_graph_info(const gdn_graph *g, int64_t info[8]);
  * info[4]=column ids served from shared-memory bands info[5]=(row, band) pairs info[6]=band work items
  * info[7]=int4 groups of the main SELL array in use */
 int gdn_graph_pull_info(const gdn_graph *g, int64_t info[8]);
+/* Host-only probe of the banded layout's id -> band map over the id space
+ * [hot prefix of H ids | P cold slices of Wc ids] (csrc/band.cu band_of / band_range): *band_out = band of new id `id`
+ * (-1: beyond the first B bands), *local_out = its 16-bit index inside the band, *start_out / *len_out = the band's id range. */
+int gdn_band_map_probe(int64_t H, int64_t Wc, int32_t P, int32_t band, int32_t B, int64_t id, int32_t *band_out,
+                       int32_t *local_out, int64_t *start_out, int32_t *len_out);
 
 /* d_* are DEVICE pointers (cudaMalloc / torch tensors) of m elements; results
  * stay on the device.  Timed with CUDA events on the library stream. */

@@ -151,3 +151,35 @@ def test_pick_sources_skip_isolated():
     s = g.pick_sources(16)
     deg = g.out_degrees()
     assert np.all(deg[s] > 0) and np.array_equal(s, g.pick_sources(16))
+
+
+@pytest.mark.parametrize("H,Wc,P,band,B", [(49152, 67059712, 1, 49152, 64), (49152, 33529856, 2, 49152, 64),
+                                            (49152, 1000, 8, 512, 96), (24576, 40000, 4, 300, 96), (1024, 0, 1, 256, 8),
+                                            (4096, 777, 3, 1000, 20)])
+def test_band_map_is_a_partition(H, Wc, P, band, B):
+    """csrc/band.cu band_of / band_range: every id of the id space [hot prefix | P cold slices] falls into at most one
+    band, at the local index the band's range says, and low band indices hold the hottest ids of EVERY rank's slice."""
+    def probe(i):
+        b, loc, st, ln = C.c_int32(), C.c_int32(), C.c_int64(), C.c_int32()
+        assert _lib.lib.gdn_band_map_probe(H, Wc, P, band, B, i, C.byref(b), C.byref(loc), C.byref(st), C.byref(ln)) == 0
+        return b.value, loc.value, st.value, ln.value
+    Mp = H + Wc * P
+    rng = np.random.default_rng(3)
+    ids = set(int(x) for x in rng.integers(0, Mp, 3000)) | {0, Mp - 1, H - 1, min(H, Mp - 1)}
+    ids |= {min(Mp - 1, H + q * Wc + d) for q in range(P) for d in (0, 1, band - 1, band, Wc - 1)}
+    seen = {}
+    for i in sorted(ids):
+        b, loc, st, ln = probe(i)
+        if b < 0:
+            continue
+        assert 0 <= b < B and 0 <= loc < ln <= min(band, 49152) and st + loc == i, (i, b, loc, st, ln)
+        seen.setdefault(b, (st, ln))
+        assert seen[b] == (st, ln)
+    rs = sorted(seen.values())
+    for (s0, l0), (s1, _) in zip(rs, rs[1:]):
+        assert s0 + l0 <= s1, "bands overlap"
+    # the first id of every rank's cold slice is banded as long as there are bands left after the hot prefix
+    n0 = -(-H // band)
+    for q in range(P):
+        if Wc > 0 and n0 + q < B:
+            assert probe(H + q * Wc)[0] == n0 + q
