@@ -33,6 +33,7 @@ constexpr int kBandSeg = 64;            // index groups (8 ids each) per lane an
 constexpr int kBandTab = kHotMax + 256; // table entries in shared memory: [band, kBandTab) is zero
 constexpr uint32_t kBandPadId = 0xC0C0; // padding id = a zero table entry; byte-uniform so cudaMemset can write it
 constexpr uint32_t kNone = 0xffffffffu;
+constexpr double kFixScale = 72057594037927936.0;          // 2^56: a row's sum is O(1), 2^63 / 2^56 = 128 of headroom
 static_assert(kBandPadId >= (uint32_t)kHotMax && kBandPadId < (uint32_t)kBandTab, "padding id must hit the zero tail");
 
 // Which band holds new id c.  The id space is [hot prefix of H ids | cold slice of rank 0 | ... | cold slice of rank
@@ -170,7 +171,9 @@ struct BandArgs {
   const int64_t *band_start;   // first new id of band b ...
   const int32_t *band_len;     // ... and how many ids it holds (<= kHotMax)
   const float *contrib_in;
-  float *bpartial;
+  float *bpartial;             // FIX = false: one partial per (item, lane)
+  const int32_t *irow;         // FIX = true: sorted row of (item, lane), -1 = no row ...
+  unsigned long long *acc_fix; // ... whose fixed-point accumulator takes the partial
   const int32_t *done;
 };
 
@@ -188,7 +191,7 @@ __device__ __forceinline__ uint4 ld_stream_u4(const uint4 *p, uint64_t pol) {
 // THREADS = 1024: the kernel has the SM to itself.  THREADS = 256 (<= 64 registers): it shares the SM with
 // pr_sell_pipe_co (pull.cu) -- eight warps already saturate the shared-memory pipe, and the main sums of the
 // iteration, which wait on the L1TEX miss path instead, run beside them.
-template <int PD, int THREADS>
+template <int PD, int THREADS, bool FIX>
 __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 1)
 pr_band_kernel(BandArgs a) {
   constexpr int kRuns = 32 / (THREADS / 32);             // warp runs of a job per warp
@@ -216,6 +219,13 @@ pr_band_kernel(BandArgs a) {
     int32_t ibase = i0, item = i0;
     uint32_t lens = len_batch(ibase), lens_next = len_batch(ibase + 32);
     uint32_t left = __shfl_sync(kFull, lens, 0);
+    // FIX: the rows of the next two items are requested ahead (an item is ~4 index groups long)
+    int32_t jrow = -1, jrow1 = -1, jrow2 = -1;
+    if (FIX) {
+      jrow = a.irow[(size_t)i0 * 32 + lane];
+      if (i0 + 1 < i1) jrow1 = a.irow[(size_t)(i0 + 1) * 32 + lane];
+      if (i0 + 2 < i1) jrow2 = a.irow[(size_t)(i0 + 2) * 32 + lane];
+    }
     uint4 q[PD];
 #pragma unroll
     for (int d = 0; d < PD; d++) q[d] = (uint32_t)d < nrows ? ld_stream_u4(p + 32 * d, pol) : padq;
@@ -231,7 +241,13 @@ pr_band_kernel(BandArgs a) {
           acc = __fadd_rn(acc, v0); acc = __fadd_rn(acc, v1); acc = __fadd_rn(acc, v2); acc = __fadd_rn(acc, v3);
           acc = __fadd_rn(acc, v4); acc = __fadd_rn(acc, v5); acc = __fadd_rn(acc, v6); acc = __fadd_rn(acc, v7);
           if (--left == 0) {
-            __stcs(a.bpartial + (size_t)item * 32 + lane, acc);
+            if (FIX) {
+              if (jrow >= 0) atomicAdd(a.acc_fix + jrow, (unsigned long long)__double2ll_rn((double)acc * kFixScale));
+              jrow = jrow1; jrow1 = jrow2;
+              jrow2 = item + 3 < i1 ? a.irow[(size_t)(item + 3) * 32 + lane] : -1;
+            } else {
+              __stcs(a.bpartial + (size_t)item * 32 + lane, acc);
+            }
             acc = 0.f;
             item++;
             if (item - ibase == 32) { ibase += 32; lens = lens_next; lens_next = len_batch(ibase + 32); }
@@ -269,76 +285,22 @@ pr_band_finalize(SellArgs a, const uint32_t *__restrict__ rslot_ptr, const uint3
   if (lane == 0) a.err_partial[a.err_slot0 + warp] = err;
 }
 
-// Alternative (GDN_PR_BAND_FIN=1): cooperative gathers.  Measured SLOWER at Kron-26 (iteration 4.42 -> 4.70 ms): the
-// thread-per-row version above already keeps 600 K gathers in flight chip-wide, and the staging pass is pure overhead.
-// One warp per 32 sorted rows (lane = row).  The partial slots of the 32 rows are one contiguous run of rslot[]: the
-// warp gathers them kFinCh at a time with coalesced index loads and 8 independent gathers per lane, parks the values
-// in shared memory, and every lane then adds ITS row's slots in slot order -- the order is fixed, the loads are not
-// serialised behind each other (a thread per row walked a hub row's thousands of slots four at a time).
-constexpr int kFinCh = 1024;
-constexpr int kFinCoop = 4 * kFinCh;     // slices with more slots than this are summed by a whole CTA
-
-// gather one chunk of slot values into `val` (coalesced index loads, 8 gathers in flight per lane)
-__device__ __forceinline__ void fin_stage(float *val, const uint32_t *__restrict__ rslot, const float *__restrict__ bpartial,
-                                          uint32_t c0, uint32_t n, int lane) {
-  for (uint32_t i = lane; i < n; i += 256) {
-    float t[8];
-#pragma unroll
-    for (int u = 0; u < 8; u++) t[u] = i + 32 * u < n ? __ldcs(bpartial + __ldcs(rslot + c0 + i + 32 * u)) : 0.f;
-#pragma unroll
-    for (int u = 0; u < 8; u++) if (i + 32 * u < n) val[i + 32 * u] = t[u];
-  }
-  __syncwarp();
-}
-
+// Default finalize (GDN_PR_BAND_FIN=0 selects the slot version above).  With FIX = true pr_band_kernel has already added
+// every band partial of row j into acc_fix[j] as a 2^-56 fixed-point integer (integer addition commutes: the order of
+// the atomics does not matter, the sum is exact and bit-reproducible), so this is one coalesced pass: main sum + band sum,
+// row epilogue, accumulator back to zero.  (Cooperative warp / CTA versions of the slot gather were measured slower than
+// one thread per row: profiles/r1_pr_band_ab.txt.)
 __global__ void __launch_bounds__(256, 4)
-pr_band_finalize_coop(SellArgs a, const uint32_t *__restrict__ rslot_ptr, const uint32_t *__restrict__ rslot,
-                 const float *__restrict__ bpartial, int32_t n_coop) {
-  __shared__ float s_val[8][kFinCh];
-  __shared__ float s_acc[8][32];
+pr_band_finalize_fix(SellArgs a, long long *__restrict__ acc_fix) {
   if (*a.done) return;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int64_t warp = (int64_t)blockIdx.x * 8 + w, nwarps = (int64_t)gridDim.x * 8;
-  const int64_t n_sl = a.n_band_rows >> 5;
-  float *val = s_val[w];
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   double err = 0.0;
-  // the hub slices (thousands of slots per row): one CTA per slice, warp w takes chunks w, w + 8, ... and keeps a
-  // per-row sum over ITS chunks in chunk order; warp 0 then adds main sum + the eight warp sums in warp order
-  for (int64_t s = blockIdx.x; s < n_coop; s += gridDim.x) {
-    const int64_t j = s * 32 + lane;
-    const uint32_t my0 = rslot_ptr[j], my1 = rslot_ptr[j + 1];
-    const uint32_t k0 = __shfl_sync(kFull, my0, 0), k1 = __shfl_sync(kFull, my1, 31);
-    float acc = 0.f;
-    for (uint32_t c0 = k0 + (uint32_t)w * kFinCh; c0 < k1; c0 += 8 * kFinCh) {
-      const uint32_t n = min((uint32_t)kFinCh, k1 - c0);
-      fin_stage(val, rslot, bpartial, c0, n, lane);
-      const uint32_t b = max(my0, c0), e = min(my1, c0 + n);
-      for (uint32_t k = b; k < e; k++) acc = __fadd_rn(acc, val[k - c0]);
-      __syncwarp();
-    }
-    s_acc[w][lane] = acc;
-    __syncthreads();
-    if (w == 0) {
-      float tot = __ldcs(a.acc_main + j);
-#pragma unroll
-      for (int u = 0; u < 8; u++) tot = __fadd_rn(tot, s_acc[u][lane]);
-      pr_epilogue_core(a, j, tot, err);
-    }
-    __syncthreads();
-  }
-  for (int64_t s = n_coop + warp; s < n_sl; s += nwarps) {
-    const int64_t j = s * 32 + lane;
-    const uint32_t my0 = rslot_ptr[j], my1 = rslot_ptr[j + 1];
-    const uint32_t k0 = __shfl_sync(kFull, my0, 0), k1 = __shfl_sync(kFull, my1, 31);
-    float acc = __ldcs(a.acc_main + j);
-    for (uint32_t c0 = k0; c0 < k1; c0 += kFinCh) {
-      const uint32_t n = min((uint32_t)kFinCh, k1 - c0);
-      fin_stage(val, rslot, bpartial, c0, n, lane);
-      const uint32_t b = max(my0, c0), e = min(my1, c0 + n);
-      for (uint32_t k = b; k < e; k++) acc = __fadd_rn(acc, val[k - c0]);
-      __syncwarp();
-    }
-    pr_epilogue_core(a, j, acc, err);                     // band rows are non-empty rows (length >= dmin)
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < a.n_band_rows; j += (int64_t)gridDim.x * blockDim.x) {
+    const long long f = acc_fix[j];
+    acc_fix[j] = 0;
+    const float acc = (float)((double)__ldcs(a.acc_main + j) + (double)f * (1.0 / kFixScale));
+    pr_epilogue_core(a, j, acc, err);
   }
   err = warp_sum(err);
   if (lane == 0) a.err_partial[a.err_slot0 + warp] = err;
@@ -377,7 +339,7 @@ static int up(gdn_graph *g, T **dptr, const T *h, size_t n) {
 }
 
 void band_free(BandLayout &b) {
-  cudaFree(b.bsell); cudaFree(b.band_start); cudaFree(b.band_len); cudaFree(b.item_ptr); cudaFree(b.job); cudaFree(b.job_first); cudaFree(b.wrun); cudaFree(b.bpartial);
+  cudaFree(b.bsell); cudaFree(b.band_start); cudaFree(b.band_len); cudaFree(b.item_ptr); cudaFree(b.job); cudaFree(b.job_first); cudaFree(b.wrun); cudaFree(b.bpartial); cudaFree(b.irow); cudaFree(b.acc_fix);
   cudaFree(b.rslot_ptr); cudaFree(b.rslot); cudaFree(b.acc_main); cudaFree(b.sell); cudaFree(b.slice_ptr);
   cudaFree(b.chunk_slice); cudaFree(b.heavy_slice); cudaFree(b.heavy_first); cudaFree(b.heavy_seg); cudaFree(b.partial);
   b = BandLayout();
@@ -491,6 +453,19 @@ int band_build(gdn_graph *g) {
   }
   item_ptr[n_items] = (uint32_t)units;
 
+  // sorted row of every (item, lane): the rows of a band slice, repeated for each of its segments
+  std::vector<int32_t> irow((size_t)n_items * 32);
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int b = 0; b < B; b++) {
+    const PerBand &q = pb[b];
+    const size_t n = q.order.size();
+    for (size_t sl = 0; sl < q.slice_item.size(); sl++) {
+      const size_t it0 = band_item0[b] + q.slice_item[sl];
+      const size_t it1 = sl + 1 < q.slice_item.size() ? band_item0[b] + q.slice_item[sl + 1] : band_item0[b + 1];
+      for (size_t it = it0; it < it1; it++)
+        for (int l = 0; l < 32; l++) irow[it * 32 + l] = sl * 32 + l < n ? (int32_t)q.order[sl * 32 + l] : -1;
+    }
+  }
   // partial slots of every row, in (band, segment) order
   std::vector<uint32_t> rslot_ptr((size_t)n_rows + 1, 0);
 #pragma omp parallel for
@@ -502,9 +477,6 @@ int band_build(gdn_graph *g) {
   uint64_t n_rslot = 0;
   for (int64_t j = 0; j < n_rows; j++) { const uint32_t n = rslot_ptr[j + 1]; rslot_ptr[j] = (uint32_t)n_rslot; n_rslot += n; }
   rslot_ptr[n_rows] = (uint32_t)n_rslot;
-  int32_t n_coop = 0;                              // leading slices whose rows own more than kFinCoop slots together
-  for (int32_t q = 0; q < nb; q++)
-    if (rslot_ptr[(size_t)q * 32 + 32] - rslot_ptr[(size_t)q * 32] > (uint32_t)kFinCoop) n_coop = q + 1;
   if (n_rslot >= 0xfffffff0ull) { cudaFree(d_cnt); cudaFree(d_remw); return GDN_OK; }
   std::vector<uint32_t> rslot(std::max<uint64_t>(n_rslot, 1));
 #pragma omp parallel for
@@ -562,7 +534,7 @@ int band_build(gdn_graph *g) {
   bd.n_units = units; bd.n_items = n_items; bd.n_jobs = (int32_t)job.size(); bd.n_cta = n_cta; bd.n_rslot = n_rslot;
   bd.n_groups = tot2; bd.n_chunks = (int32_t)chunk.size() - 1;
   bd.n_heavy_slices = (int32_t)hslice.size(); bd.n_heavy_segs = (int32_t)hseg.size();
-  bd.moved = moved; bd.pairs = pairs; bd.n_fin_coop = n_coop;
+  bd.moved = moved; bd.pairs = pairs;
   uint32_t *d_rank = d_cnt;                         // the counts are not needed on the device any more
   uint32_t *d_bslice_ptr = nullptr;
   int32_t *d_bslice_first = nullptr;
@@ -578,6 +550,9 @@ int band_build(gdn_graph *g) {
   GDN_CHECK(up(g, &bd.job, job.data(), job.size()));
   GDN_CHECK(up(g, &bd.job_first, job_first.data(), job_first.size()));
   GDN_CHECK(up(g, &bd.wrun, wrun.data(), wrun.size()));
+  GDN_CHECK(up(g, &bd.irow, irow.data(), irow.size()));
+  GDN_CUDA(cudaMalloc((void **)&bd.acc_fix, sizeof(long long) * (size_t)n_rows));
+  GDN_CUDA(cudaMemsetAsync(bd.acc_fix, 0, sizeof(long long) * (size_t)n_rows, st));
   GDN_CHECK(up(g, &bd.rslot_ptr, rslot_ptr.data(), rslot_ptr.size()));
   GDN_CHECK(up(g, &bd.rslot, rslot.data(), (size_t)n_rslot));
   GDN_CHECK(up(g, &bd.slice_ptr, sp2.data(), sp2.size()));
@@ -603,13 +578,14 @@ int band_build(gdn_graph *g) {
   GDN_CUDA(cudaStreamSynchronize(st));
   GDN_CUDA(cudaGetLastError());
   cudaFree(d_cnt); cudaFree(d_remw); cudaFree(d_bslice_ptr); cudaFree(d_bslice_first);
-  GDN_CUDA(cudaFuncSetAttribute(pr_band_kernel<4, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * kBandTab)));
-  GDN_CUDA(cudaFuncSetAttribute(pr_band_kernel<8, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * kBandTab)));
-  GDN_CUDA(cudaFuncSetAttribute(pr_band_kernel<4, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * kBandTab)));
-  GDN_CUDA(cudaFuncSetAttribute(pr_band_kernel<8, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * kBandTab)));
+  const int tab_bytes = (int)(sizeof(float) * kBandTab);
+  GDN_CUDA(cudaFuncSetAttribute(pr_band_kernel<4, 1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tab_bytes));
+  GDN_CUDA(cudaFuncSetAttribute(pr_band_kernel<4, 1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tab_bytes));
+  GDN_CUDA(cudaFuncSetAttribute(pr_band_kernel<4, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tab_bytes));
+  GDN_CUDA(cudaFuncSetAttribute(pr_band_kernel<4, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tab_bytes));
   // co-resident pair: the SM must be configured for the full 228 KB of shared memory before either CTA arrives
-  GDN_CUDA(cudaFuncSetAttribute(pr_band_kernel<4, 256>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  GDN_CUDA(cudaFuncSetAttribute(pr_band_kernel<8, 256>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  GDN_CUDA(cudaFuncSetAttribute(pr_band_kernel<4, 256, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  GDN_CUDA(cudaFuncSetAttribute(pr_band_kernel<4, 256, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   bd.built = true;
   if (getenv("GDN_TRACE"))
     fprintf(stderr, "[gdn] band layout: B=%d band=%d cmin=%d rows=%lld  moved=%llu ids (%.1f %% of nnz) in %llu pairs, %d items, "
@@ -647,13 +623,14 @@ int band_launch(gdn_graph *g, const SellArgs &sa, cudaStream_t s, bool co_reside
   a.bsell = bd.bsell; a.item_ptr = bd.item_ptr; a.job = bd.job; a.job_first = bd.job_first; a.wrun = bd.wrun;
   a.band_start = bd.band_start; a.band_len = bd.band_len; a.contrib_in = sa.contrib_in; a.bpartial = bd.bpartial; a.done = sa.done;
   const size_t smem = sizeof(float) * kBandTab;
-  const bool pd8 = env_int("GDN_PR_BAND_PD", 4) == 8;
+  a.irow = bd.irow; a.acc_fix = (unsigned long long *)bd.acc_fix;
+  const bool fix = env_int("GDN_PR_BAND_FIN", 2) == 2;
   if (co_resident) {
-    if (pd8) pr_band_kernel<8, 256><<<bd.n_cta, 256, smem, s>>>(a);
-    else pr_band_kernel<4, 256><<<bd.n_cta, 256, smem, s>>>(a);
+    if (fix) pr_band_kernel<4, 256, true><<<bd.n_cta, 256, smem, s>>>(a);
+    else pr_band_kernel<4, 256, false><<<bd.n_cta, 256, smem, s>>>(a);
   } else {
-    if (pd8) pr_band_kernel<8, 1024><<<bd.n_cta, kSellThreads, smem, s>>>(a);
-    else pr_band_kernel<4, 1024><<<bd.n_cta, kSellThreads, smem, s>>>(a);
+    if (fix) pr_band_kernel<4, 1024, true><<<bd.n_cta, kSellThreads, smem, s>>>(a);
+    else pr_band_kernel<4, 1024, false><<<bd.n_cta, kSellThreads, smem, s>>>(a);
   }
   return GDN_OK;
 }
@@ -664,12 +641,15 @@ int band_finalize_grid(const gdn_graph *g) {
 
 int band_finalize_launch(gdn_graph *g, const SellArgs &a, int grid, cudaStream_t s) {
   const BandLayout &bd = g->pull.band;
-  if (env_int("GDN_PR_BAND_FIN", 0) == 1) {
-    const int cgrid = (int)std::max<int64_t>(1, std::min<int64_t>((bd.n_rows / 32 + 7) / 8, (int64_t)grid));
-    pr_band_finalize_coop<<<cgrid, 256, 0, s>>>(a, bd.rslot_ptr, bd.rslot, bd.bpartial, bd.n_fin_coop);
-  } else {
-    pr_band_finalize<<<grid, 256, 0, s>>>(a, bd.rslot_ptr, bd.rslot, bd.bpartial);
-  }
+  if (env_int("GDN_PR_BAND_FIN", 2) == 2) pr_band_finalize_fix<<<grid, 256, 0, s>>>(a, bd.acc_fix);
+  else pr_band_finalize<<<grid, 256, 0, s>>>(a, bd.rslot_ptr, bd.rslot, bd.bpartial);
+  return GDN_OK;
+}
+
+// start of a solve: the fixed-point accumulators must be zero (pr_band_finalize_fix leaves them so; an aborted solve may not)
+int band_solve_begin(gdn_graph *g, cudaStream_t s) {
+  const BandLayout &bd = g->pull.band;
+  GDN_CUDA(cudaMemsetAsync(bd.acc_fix, 0, sizeof(long long) * (size_t)bd.n_rows, s));
   return GDN_OK;
 }
 

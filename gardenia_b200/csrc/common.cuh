@@ -106,11 +106,12 @@ struct BandLayout {
   int32_t *job_first = nullptr;    // [n_cta + 1] jobs of CTA c
   int32_t *wrun = nullptr;         // [n_jobs * 33] item boundaries of the warp runs
   int32_t n_cta = 0;
-  float *bpartial = nullptr;       // [n_items * 32] per-row partial sums of the items
+  float *bpartial = nullptr;       // [n_items * 32] per-row partial sums of the items (slot finalize, GDN_PR_BAND_FIN=0)
+  int32_t *irow = nullptr;         // [n_items * 32] sorted row of (item, lane), -1 = none
+  long long *acc_fix = nullptr;    // [n_rows] 2^-56 fixed-point sum of a row's band partials (default finalize)
   uint32_t *rslot_ptr = nullptr;   // [n_rows + 1] partial slots of sorted row j ...
   uint32_t *rslot = nullptr;       // ... in (band, segment) order
   uint64_t n_rslot = 0;
-  int32_t n_fin_coop = 0;          // leading slices that pr_band_finalize sums with a whole CTA (hub rows)
   float *acc_main = nullptr;       // [n_rows] sum over the columns left in the main array
   // the compacted main SELL array and its work tables (same meaning as the PullLayout fields)
   int4 *sell = nullptr;

@@ -1020,6 +1020,7 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
   GDN_CUDA(cudaEventRecord(lib().ev0, s));
   GDN_CUDA(cudaMemsetAsync(g->pr_done, 0, sizeof(int32_t), s));
   GDN_CUDA(cudaMemsetAsync(g->err_partial, 0, sizeof(double) * n_partial, s));
+  if (banded) GDN_CHECK(band_solve_begin(g, s));
   a.contrib_out = g->contrib[0];
   // rows without in-edges: settled by pr_sell_load (symmetric graph) or by pr_sell_isolated after the first iteration
   const bool have_iso = max_iter > 0 && L.rows > L.n_nz_rows;

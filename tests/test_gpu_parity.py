@@ -355,6 +355,13 @@ def test_pr_banded_layout(monkeypatch, kind, scale, bands, band_ids, cmin, dmin)
         st3 = dg.pagerank(s3)
         assert st3.iterations == oit and torch.equal(s3, s1), ("overlap", ovl)
     monkeypatch.delenv("GDN_PR_OVERLAP")
+    # the slot finalize (per-row gather of the band partials) instead of the fixed-point accumulators: same bar
+    monkeypatch.setenv("GDN_PR_BAND_FIN", "0")
+    s5 = torch.full((m,), float(np.float32(1.0) / np.float32(m)), dtype=torch.float32, device="cuda")
+    st5 = dg.pagerank(s5)
+    assert st5.iterations == oit
+    assert float(np.abs(s5.cpu().numpy().astype(np.float64) - oscores.astype(np.float64)).sum()) <= PR_L1_TOL
+    monkeypatch.delenv("GDN_PR_BAND_FIN")
     # switching the layout off on the same graph falls back to the plain array
     monkeypatch.setenv("GDN_PR_BANDS", "0")
     s4 = torch.full((m,), float(np.float32(1.0) / np.float32(m)), dtype=torch.float32, device="cuda")
