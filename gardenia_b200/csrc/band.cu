@@ -20,6 +20,12 @@
 // The layout is built once per resident graph (untimed, like include/segmenting.h preprocessing of the reference):
 // two device passes over the existing SELL array (count, fill) around a host pass that sorts each band's rows.
 // Every rank of a row partition bands ITS rows over the shared id space (band_of); one-shot calls keep the plain layout.
+//
+// SEGMENTED mode (graphs WITHOUT a hot set whose gathered vector does not fit L2, e.g. uniform-random scale >= 25: every
+// gather of the plain layout is then an HBM sector miss, 33 ms per iteration at urand-26): the same machinery with
+// bands the size of an L2-resident slice (40 MB), every row taking part with every id, 32-bit ids, one launch per band
+// (pr_seg_kernel) so that only ONE slice of contrib is hot in L2 at a time.  The gathers become L2 hits; the per-row
+// partials of the passes meet in the fixed-point accumulators.
 #include "pull.cuh"
 #include <omp.h>
 #include <algorithm>
@@ -109,6 +115,7 @@ band_select(uint32_t *__restrict__ cnt, int B, int64_t n_rows, uint32_t cmin, co
 // One warp per slice again.  rank[b][j] = position of row j among band b's rows (kNone: the pair stays in the main
 // array).  A lane walks ITS row in column order, so the order of a row's ids inside a band section and inside the
 // compacted main slice is the order they had before.
+template <bool WIDE>
 __global__ void __launch_bounds__(128)
 band_fill(const int4 *__restrict__ sell, const uint32_t *__restrict__ slice_ptr, int32_t nb_slices, BandMap mp,
           const uint32_t *__restrict__ rank, int64_t n_rows, const uint32_t *__restrict__ bslice_ptr,
@@ -149,7 +156,8 @@ band_fill(const int4 *__restrict__ sell, const uint32_t *__restrict__ slice_ptr,
           if (b < (uint32_t)B) bs = base[b * 32 + lane];
           if (bs != kNone) {
             const uint32_t kk = kcnt[b * 32 + lane]++;
-            bsell16[((size_t)bs + (size_t)(kk >> 3) * 32) * 8 + (kk & 7)] = (uint16_t)loc;
+            if (WIDE) reinterpret_cast<int32_t *>(bsell16)[((size_t)bs + (size_t)(kk >> 2) * 32) * 4 + (kk & 3)] = c;   // 4 global ids per unit
+            else bsell16[((size_t)bs + (size_t)(kk >> 3) * 32) * 8 + (kk & 7)] = (uint16_t)loc;
           } else {
             if (np == 0) pend.x = c; else if (np == 1) pend.y = c; else if (np == 2) pend.z = c; else pend.w = c;
             if (++np == 4) { *dst = pend; dst += 32; pend = make_int4(-1, -1, -1, -1); np = 0; }
@@ -259,6 +267,69 @@ pr_band_kernel(BandArgs a) {
   }
 }
 
+// ------------------------------------------------------------------ the iteration, SEGMENTED mode: one band per launch
+// Same item / job / warp-run structure as pr_band_kernel, but the band is an L2-resident slice of contrib (not a
+// shared-memory table): 4 global ids per unit, predicated evict-last gathers, the gathers of index group r in flight
+// while group r-1 is added; every item's per-row partial goes to the row's fixed-point accumulator.
+template <int PD>
+__global__ void __launch_bounds__(kSellThreads, 1)
+pr_seg_kernel(BandArgs a, int32_t job0) {
+  if (*a.done) return;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint64_t pol = l2_policy_evict_first(), pol_last = l2_policy_evict_last();
+  const int4 J = a.job[job0 + blockIdx.x];
+  const int32_t i0 = a.wrun[J.y + w], i1 = a.wrun[J.y + w + 1];
+  if (i0 >= i1) return;
+  const uint32_t u0 = a.item_ptr[i0], u1 = a.item_ptr[i1];
+  const int4 *p = reinterpret_cast<const int4 *>(a.bsell) + u0 + lane;
+  const uint32_t nrows = (u1 - u0) >> 5;
+  auto len_batch = [&](int32_t ib) -> uint32_t {
+    const int32_t i = ib + lane;
+    return i < i1 ? (a.item_ptr[i + 1] - a.item_ptr[i]) >> 5 : 0u;
+  };
+  int32_t ibase = i0, item = i0;
+  uint32_t lens = len_batch(ibase), lens_next = len_batch(ibase + 32);
+  uint32_t left = __shfl_sync(kFull, lens, 0);
+  int32_t jrow = a.irow[(size_t)i0 * 32 + lane], jrow1 = -1, jrow2 = -1;
+  if (i0 + 1 < i1) jrow1 = a.irow[(size_t)(i0 + 1) * 32 + lane];
+  if (i0 + 2 < i1) jrow2 = a.irow[(size_t)(i0 + 2) * 32 + lane];
+  const int4 none = make_int4(-1, -1, -1, -1);
+  int4 q[PD];
+#pragma unroll
+  for (int d = 0; d < PD; d++) q[d] = (uint32_t)d < nrows ? ld_stream_v4(p + 32 * d, pol) : none;
+  auto pull = [&](int c) -> float {
+    float v = 0.f;
+    if (c >= 0) v = ld_gather_f32(a.contrib_in + c, pol_last);
+    return v;
+  };
+  float acc = 0.f, v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+  for (uint32_t r = 0; r <= nrows; r += PD) {
+#pragma unroll
+    for (int d = 0; d < PD; d++) {
+      const uint32_t idx = r + d;
+      float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
+      if (idx < nrows) {                                   // warp-uniform: issue the gathers of group idx
+        const int4 c = q[d];
+        q[d] = idx + PD < nrows ? ld_stream_v4(p + (size_t)(idx + PD) * 32, pol) : none;
+        n0 = pull(c.x); n1 = pull(c.y); n2 = pull(c.z); n3 = pull(c.w);
+      }
+      if (idx > 0 && idx <= nrows) {                       // add group idx - 1
+        acc = __fadd_rn(acc, v0); acc = __fadd_rn(acc, v1); acc = __fadd_rn(acc, v2); acc = __fadd_rn(acc, v3);
+        if (--left == 0) {
+          if (jrow >= 0) atomicAdd(a.acc_fix + jrow, (unsigned long long)__double2ll_rn((double)acc * kFixScale));
+          jrow = jrow1; jrow1 = jrow2;
+          jrow2 = item + 3 < i1 ? a.irow[(size_t)(item + 3) * 32 + lane] : -1;
+          acc = 0.f;
+          item++;
+          if (item - ibase == 32) { ibase += 32; lens = lens_next; lens_next = len_batch(ibase + 32); }
+          left = __shfl_sync(kFull, lens, item - ibase);
+        }
+      }
+      v0 = n0; v1 = n1; v2 = n2; v3 = n3;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ the iteration: main sum + band partials -> epilogue
 __global__ void __launch_bounds__(256, 4)
 pr_band_finalize(SellArgs a, const uint32_t *__restrict__ rslot_ptr, const uint32_t *__restrict__ rslot,
@@ -316,6 +387,9 @@ static void make_work_tables(const std::vector<uint32_t> &sptr, int32_t n_slices
   int32_t s = 0;
   for (int32_t k = 0; k < n_chunks; k++) {
     while (s < n_slices && sptr[s] < (uint64_t)k * kGroupCh) s++;
+    // empty slices (rows whose ids all moved into bands) at the head of a chunk are never visited: in the segmented
+    // mode that is EVERY band slice, and one warp walking a million empty slices costs 100 ms
+    while (s < n_slices && sptr[s + 1] == sptr[s]) s++;
     chunk[k] = s;
   }
   chunk[n_chunks] = n_slices;
@@ -359,16 +433,25 @@ int band_build(gdn_graph *g) {
   bd.tried = true;
   const int B_want = env_int("GDN_PR_BANDS", 64);
   if (B_want <= 0 || !L.prepared || !L.sell || L.n_slices < 2 || L.h_slice_ptr.empty()) return GDN_OK;
-  const int band = std::min(std::max(env_int("GDN_PR_BAND_SIZE", kHotMax), 32), kHotMax);
-  const int cmin = std::max(env_int("GDN_PR_BAND_CMIN", 4), 1);
-  const int dmin = std::max(env_int("GDN_PR_BAND_DMIN", 64), 1);
+  const std::vector<uint32_t> &sp = L.h_slice_ptr;
+  // Is there a hot set?  Share of the SELL array held by the rows of the 64 hottest bands' worth of ids (rows and
+  // columns are ranked by the same degrees on a symmetric graph): 0.87 at Kronecker scale 26, 0.05 at urand-26.
+  const int64_t hot_slices = std::min<int64_t>(L.n_slices, (int64_t)64 * kHotMax / 32);
+  const double hot_share = (double)sp[hot_slices] / (double)std::max<uint32_t>(sp[L.n_slices], 1u);
+  const int e_seg = env_int("GDN_PR_SEGMENT", -1);       // -1: decide here, 0: never, 1: always
+  const bool seg = e_seg == 1 || (e_seg < 0 && hot_share < 0.4 && L.Mp * 4 > ((int64_t)64 << 20));
+  const int seg_ids = std::max(env_int("GDN_PR_SEG_IDS", (40 << 20) / 4), 64);
+  const int band = seg ? seg_ids : std::min(std::max(env_int("GDN_PR_BAND_SIZE", kHotMax), 32), kHotMax);
+  const int cmin = seg ? 1 : std::max(env_int("GDN_PR_BAND_CMIN", 4), 1);
+  const int dmin = seg ? 1 : std::max(env_int("GDN_PR_BAND_DMIN", 64), 1);
+  const uint32_t W = seg ? 4 : 8;                        // ids per 16-byte unit
   BandMap mp;
   mp.band = band; mp.P = L.P; mp.H = L.H; mp.Wc = L.Wc;
   mp.n0 = (int32_t)((L.H + band - 1) / band);
   const int B = (int)std::min<int64_t>(std::min(B_want, 96), (int64_t)mp.n0 + (L.Wc + band - 1) / band * L.P);
   mp.B = B;
   if (B <= 0) return GDN_OK;
-  const std::vector<uint32_t> &sp = L.h_slice_ptr;
+  if (seg && (int64_t)mp.n0 + (L.Wc + band - 1) / band * L.P > B) return GDN_OK;   // more than 96 slices: plain layout
   // slices whose rows are all at least dmin long: the first row of the NEXT slice is (rows sorted by length, descending)
   int32_t nb = 0;
   while (nb + 1 < L.n_slices && (int64_t)(sp[nb + 2] - sp[nb + 1]) / 32 * 4 >= dmin) nb++;
@@ -384,7 +467,8 @@ int band_build(gdn_graph *g) {
   GDN_CUDA(cudaMalloc((void **)&d_remw, sizeof(uint32_t) * (size_t)nb));
   const size_t smem1 = sizeof(uint32_t) * 4 * (size_t)B * 32, smem2 = 2 * smem1;
   GDN_CUDA(cudaFuncSetAttribute(band_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-  GDN_CUDA(cudaFuncSetAttribute(band_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+  GDN_CUDA(cudaFuncSetAttribute(band_fill<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+  GDN_CUDA(cudaFuncSetAttribute(band_fill<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
   const int grid = (int)std::min<int64_t>((nb + 3) / 4, (int64_t)sm * 16);
   band_count<<<grid, 128, smem1, st>>>(L.sell, L.slice_ptr, nb, mp, d_cnt, n_rows);
   band_select<<<(int)std::min<int64_t>((n_rows + 255) / 256, (int64_t)sm * 8), 256, 0, st>>>(d_cnt, B, n_rows, (uint32_t)cmin, L.sdeg, d_remw);
@@ -411,11 +495,35 @@ int band_build(gdn_graph *g) {
     const uint32_t *c = cnt.data() + (size_t)b * n_rows;
     uint32_t *rk = rank.data() + (size_t)b * n_rows;
     for (int64_t j = 0; j < n_rows; j++) { rk[j] = kNone; if (c[j]) { q.order.push_back((uint32_t)j); q.moved += c[j]; } }
-    std::stable_sort(q.order.begin(), q.order.end(), [&](uint32_t x, uint32_t y) { return c[x] > c[y]; });
+    if (!seg) {
+      std::stable_sort(q.order.begin(), q.order.end(), [&](uint32_t x, uint32_t y) { return c[x] > c[y]; });
+    } else {
+      // segmented mode: every row is here, so sort by count only inside windows of 64 K consecutive entries -- the rows
+      // of an item stay close together and the accumulator atomics of a pass sweep through memory instead of scattering
+      // (counting sort: the counts of a graph without hubs are small)
+      const size_t win = 65536;
+      std::vector<uint32_t> tmp(win), start;
+      for (size_t a0 = 0; a0 < q.order.size(); a0 += win) {
+        const size_t a1 = std::min(q.order.size(), a0 + win);
+        uint32_t cmax = 0;
+        for (size_t i = a0; i < a1; i++) cmax = std::max(cmax, c[q.order[i]]);
+        if (cmax > (1u << 20)) {
+          std::stable_sort(q.order.begin() + a0, q.order.begin() + a1, [&](uint32_t x, uint32_t y) { return c[x] > c[y]; });
+          continue;
+        }
+        start.assign((size_t)cmax + 2, 0);
+        for (size_t i = a0; i < a1; i++) start[cmax - c[q.order[i]] + 1]++;          // bucket = cmax - count: descending
+        for (size_t k = 1; k < start.size(); k++) start[k] += start[k - 1];
+        for (size_t i = a0; i < a1; i++) tmp[start[cmax - c[q.order[i]]]++] = q.order[i];
+        std::copy(tmp.begin(), tmp.begin() + (a1 - a0), q.order.begin() + a0);
+      }
+    }
     const size_t n = q.order.size();
     for (size_t pos = 0; pos < n; pos++) rk[q.order[pos]] = (uint32_t)pos;
     for (size_t s0 = 0; s0 < n; s0 += 32) {
-      const uint32_t ng = (c[q.order[s0]] + 7) / 8;
+      uint32_t cmx = c[q.order[s0]];                                   // (windowed order: not necessarily the first row)
+      if (seg) for (size_t i = s0; i < std::min(n, s0 + 32); i++) cmx = std::max(cmx, c[q.order[i]]);
+      const uint32_t ng = (cmx + W - 1) / W;
       q.slice_units.push_back((uint32_t)q.units);
       q.slice_item.push_back((uint32_t)q.item_ng.size());
       for (uint32_t t = 0; t < ng; t += kBandSeg) q.item_ng.push_back(std::min<uint32_t>(kBandSeg, ng - t));
@@ -466,28 +574,32 @@ int band_build(gdn_graph *g) {
         for (int l = 0; l < 32; l++) irow[it * 32 + l] = sl * 32 + l < n ? (int32_t)q.order[sl * 32 + l] : -1;
     }
   }
-  // partial slots of every row, in (band, segment) order
-  std::vector<uint32_t> rslot_ptr((size_t)n_rows + 1, 0);
-#pragma omp parallel for
-  for (int64_t j = 0; j < n_rows; j++) {
-    uint32_t n = 0;
-    for (int b = 0; b < B; b++) { const uint32_t c = cnt[(size_t)b * n_rows + j]; if (c) n += (c + 8 * kBandSeg - 1) / (8 * kBandSeg); }
-    rslot_ptr[j + 1] = n;
-  }
+  // partial slots of every row, in (band, segment) order (slot finalize only; the segmented mode always uses the
+  // fixed-point accumulators)
+  std::vector<uint32_t> rslot_ptr, rslot;
   uint64_t n_rslot = 0;
-  for (int64_t j = 0; j < n_rows; j++) { const uint32_t n = rslot_ptr[j + 1]; rslot_ptr[j] = (uint32_t)n_rslot; n_rslot += n; }
-  rslot_ptr[n_rows] = (uint32_t)n_rslot;
-  if (n_rslot >= 0xfffffff0ull) { cudaFree(d_cnt); cudaFree(d_remw); return GDN_OK; }
-  std::vector<uint32_t> rslot(std::max<uint64_t>(n_rslot, 1));
+  if (!seg) {
+    rslot_ptr.assign((size_t)n_rows + 1, 0);
 #pragma omp parallel for
-  for (int64_t j = 0; j < n_rows; j++) {
-    uint32_t k = rslot_ptr[j];
-    for (int b = 0; b < B; b++) {
-      const uint32_t c = cnt[(size_t)b * n_rows + j];
-      if (!c) continue;
-      const uint32_t r = rank[(size_t)b * n_rows + j];
-      const uint32_t it0 = bslice_item[bslice_first[b] + (r >> 5)];
-      for (uint32_t t = 0; t < (c + 8 * kBandSeg - 1) / (8 * kBandSeg); t++) rslot[k++] = (it0 + t) * 32 + (r & 31);
+    for (int64_t j = 0; j < n_rows; j++) {
+      uint32_t n = 0;
+      for (int b = 0; b < B; b++) { const uint32_t c = cnt[(size_t)b * n_rows + j]; if (c) n += (c + W * kBandSeg - 1) / (W * kBandSeg); }
+      rslot_ptr[j + 1] = n;
+    }
+    for (int64_t j = 0; j < n_rows; j++) { const uint32_t n = rslot_ptr[j + 1]; rslot_ptr[j] = (uint32_t)n_rslot; n_rslot += n; }
+    rslot_ptr[n_rows] = (uint32_t)n_rslot;
+    if (n_rslot >= 0xfffffff0ull) { cudaFree(d_cnt); cudaFree(d_remw); return GDN_OK; }
+    rslot.resize(std::max<uint64_t>(n_rslot, 1));
+#pragma omp parallel for
+    for (int64_t j = 0; j < n_rows; j++) {
+      uint32_t k = rslot_ptr[j];
+      for (int b = 0; b < B; b++) {
+        const uint32_t c = cnt[(size_t)b * n_rows + j];
+        if (!c) continue;
+        const uint32_t r = rank[(size_t)b * n_rows + j];
+        const uint32_t it0 = bslice_item[bslice_first[b] + (r >> 5)];
+        for (uint32_t t = 0; t < (c + W * kBandSeg - 1) / (W * kBandSeg); t++) rslot[k++] = (it0 + t) * 32 + (r & 31);
+      }
     }
   }
 
@@ -498,24 +610,41 @@ int band_build(gdn_graph *g) {
   auto first_at = [&](uint64_t cost) -> int32_t { return (int32_t)(std::lower_bound(pc.begin(), pc.end(), cost) - pc.begin()); };
   std::vector<int4> job;
   std::vector<int32_t> job_first((size_t)n_cta + 1, 0), wrun;
-  for (int c = 0; c < n_cta; c++) {
+  auto push_job = [&](int b, int32_t lo, int32_t e) {
+    const int32_t w0 = (int32_t)wrun.size();
+    for (int w = 0; w <= 32; w++) {
+      int32_t x = w == 32 ? e : first_at(pc[lo] + (pc[e] - pc[lo]) * w / 32);
+      x = std::max(lo, std::min(x, e));
+      wrun.push_back(x);
+    }
+    job.push_back(make_int4(b, w0, lo, e));
+  };
+  if (seg) {
+    // one launch per band: job b * n_cta + c = CTA c's equal-cost share of band b's items (possibly empty)
+    for (int b = 0; b < B; b++) {
+      const int32_t bl = (int32_t)band_item0[b], bh = (int32_t)band_item0[b + 1];
+      for (int c = 0; c < n_cta; c++) {
+        int32_t lo = bl, hi = bh;
+        if (bh > bl) {
+          lo = std::max(bl, std::min(first_at(pc[bl] + (pc[bh] - pc[bl]) * c / n_cta), bh));
+          hi = c == n_cta - 1 ? bh : std::max(bl, std::min(first_at(pc[bl] + (pc[bh] - pc[bl]) * (c + 1) / n_cta), bh));
+        }
+        push_job(b, lo, std::max(lo, hi));
+      }
+    }
+  }
+  for (int c = 0; c < n_cta && !seg; c++) {
     job_first[c] = (int32_t)job.size();
     int32_t lo = std::min(first_at(pc[n_items] * c / n_cta), n_items), hi = std::min(first_at(pc[n_items] * (c + 1) / n_cta), n_items);
     if (c == n_cta - 1) hi = n_items;
     while (lo < hi) {
       const int b = item_band[lo];
       const int32_t e = (int32_t)std::min<uint64_t>((uint64_t)hi, band_item0[b + 1]);
-      const int32_t w0 = (int32_t)wrun.size();
-      for (int w = 0; w <= 32; w++) {
-        int32_t x = w == 32 ? e : first_at(pc[lo] + (pc[e] - pc[lo]) * w / 32);
-        x = std::max(lo, std::min(x, e));
-        wrun.push_back(x);
-      }
-      job.push_back(make_int4(b, w0, lo, e));
+      push_job(b, lo, e);
       lo = e;
     }
   }
-  job_first[n_cta] = (int32_t)job.size();
+  job_first[n_cta] = seg ? 0 : (int32_t)job.size();
   trace("band_build: host tables");
 
   // compacted main array: band slices get their remaining width, the others keep theirs
@@ -530,6 +659,7 @@ int band_build(gdn_graph *g) {
   std::vector<int2> hseg;
   make_work_tables(sp2, L.n_slices, chunk, hslice, hfirst, hseg);
 
+  bd.seg = seg;
   bd.B = B; bd.band = band; bd.cmin = cmin; bd.dmin = dmin; bd.n_rows = n_rows;
   bd.n_units = units; bd.n_items = n_items; bd.n_jobs = (int32_t)job.size(); bd.n_cta = n_cta; bd.n_rslot = n_rslot;
   bd.n_groups = tot2; bd.n_chunks = (int32_t)chunk.size() - 1;
@@ -553,8 +683,10 @@ int band_build(gdn_graph *g) {
   GDN_CHECK(up(g, &bd.irow, irow.data(), irow.size()));
   GDN_CUDA(cudaMalloc((void **)&bd.acc_fix, sizeof(long long) * (size_t)n_rows));
   GDN_CUDA(cudaMemsetAsync(bd.acc_fix, 0, sizeof(long long) * (size_t)n_rows, st));
-  GDN_CHECK(up(g, &bd.rslot_ptr, rslot_ptr.data(), rslot_ptr.size()));
-  GDN_CHECK(up(g, &bd.rslot, rslot.data(), (size_t)n_rslot));
+  if (!seg) {
+    GDN_CHECK(up(g, &bd.rslot_ptr, rslot_ptr.data(), rslot_ptr.size()));
+    GDN_CHECK(up(g, &bd.rslot, rslot.data(), (size_t)n_rslot));
+  }
   GDN_CHECK(up(g, &bd.slice_ptr, sp2.data(), sp2.size()));
   GDN_CHECK(up(g, &bd.chunk_slice, chunk.data(), chunk.size()));
   if (bd.n_heavy_slices) {
@@ -565,16 +697,20 @@ int band_build(gdn_graph *g) {
   }
   GDN_CUDA(cudaMalloc((void **)&bd.bsell, sizeof(uint4) * units + 256));
   GDN_CUDA(cudaMalloc((void **)&bd.sell, sizeof(int4) * std::max<uint64_t>(tot2, 1) + 256));
-  GDN_CUDA(cudaMalloc((void **)&bd.bpartial, sizeof(float) * 32 * (size_t)n_items));
+  if (!seg) GDN_CUDA(cudaMalloc((void **)&bd.bpartial, sizeof(float) * 32 * (size_t)n_items));
   GDN_CUDA(cudaMalloc((void **)&bd.acc_main, sizeof(float) * (size_t)n_rows));
   g->device_bytes += sizeof(uint4) * units + sizeof(int4) * tot2 + sizeof(float) * (32 * (size_t)n_items + n_rows);
-  GDN_CUDA(cudaMemsetAsync(bd.bsell, (int)(kBandPadId & 0xff), sizeof(uint4) * units + 256, st));
+  GDN_CUDA(cudaMemsetAsync(bd.bsell, seg ? 0xff : (int)(kBandPadId & 0xff), sizeof(uint4) * units + 256, st));
   GDN_CUDA(cudaMemsetAsync(bd.sell, 0xff, sizeof(int4) * (size_t)sp2[nb] + (tot2 == sp2[nb] ? 256 : 0), st));
   GDN_CUDA(cudaMemsetAsync(bd.acc_main, 0, sizeof(float) * (size_t)n_rows, st));
   if (tot2 > sp2[nb])
     GDN_CUDA(cudaMemcpyAsync(bd.sell + sp2[nb], L.sell + sp[nb], sizeof(int4) * (size_t)(tot2 - sp2[nb]) + 256, cudaMemcpyDeviceToDevice, st));
-  band_fill<<<grid, 128, smem2, st>>>(L.sell, L.slice_ptr, nb, mp, d_rank, n_rows, d_bslice_ptr, d_bslice_first,
-                                      (uint16_t *)bd.bsell, bd.sell, bd.slice_ptr);
+  if (seg)
+    band_fill<true><<<grid, 128, smem2, st>>>(L.sell, L.slice_ptr, nb, mp, d_rank, n_rows, d_bslice_ptr, d_bslice_first,
+                                              (uint16_t *)bd.bsell, bd.sell, bd.slice_ptr);
+  else
+    band_fill<false><<<grid, 128, smem2, st>>>(L.sell, L.slice_ptr, nb, mp, d_rank, n_rows, d_bslice_ptr, d_bslice_first,
+                                               (uint16_t *)bd.bsell, bd.sell, bd.slice_ptr);
   GDN_CUDA(cudaStreamSynchronize(st));
   GDN_CUDA(cudaGetLastError());
   cudaFree(d_cnt); cudaFree(d_remw); cudaFree(d_bslice_ptr); cudaFree(d_bslice_first);
@@ -588,10 +724,10 @@ int band_build(gdn_graph *g) {
   GDN_CUDA(cudaFuncSetAttribute(pr_band_kernel<4, 256, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   bd.built = true;
   if (getenv("GDN_TRACE"))
-    fprintf(stderr, "[gdn] band layout: B=%d band=%d cmin=%d rows=%lld  moved=%llu ids (%.1f %% of nnz) in %llu pairs, %d items, "
+    fprintf(stderr, "[gdn] %s layout: B=%d band=%d cmin=%d rows=%lld  moved=%llu ids (%.1f %% of nnz) in %llu pairs, %d items, "
                     "%llu padded ids (x%.2f), %d jobs; main array %llu -> %llu groups\n",
-            B, band, cmin, (long long)n_rows, (unsigned long long)moved, 100.0 * (double)moved / (double)std::max<uint64_t>(g->in.nnz, 1),
-            (unsigned long long)pairs, n_items, (unsigned long long)(units * 8), (double)(units * 8) / (double)std::max<uint64_t>(moved, 1),
+            seg ? "segmented" : "band", B, band, cmin, (long long)n_rows, (unsigned long long)moved, 100.0 * (double)moved / (double)std::max<uint64_t>(g->in.nnz, 1),
+            (unsigned long long)pairs, n_items, (unsigned long long)(units * W), (double)(units * W) / (double)std::max<uint64_t>(moved, 1),
             bd.n_jobs, (unsigned long long)L.n_groups, (unsigned long long)tot2);
   trace("band_build: done");
   return GDN_OK;
@@ -624,8 +760,10 @@ int band_launch(gdn_graph *g, const SellArgs &sa, cudaStream_t s, bool co_reside
   a.band_start = bd.band_start; a.band_len = bd.band_len; a.contrib_in = sa.contrib_in; a.bpartial = bd.bpartial; a.done = sa.done;
   const size_t smem = sizeof(float) * kBandTab;
   a.irow = bd.irow; a.acc_fix = (unsigned long long *)bd.acc_fix;
-  const bool fix = env_int("GDN_PR_BAND_FIN", 2) == 2;
-  if (co_resident) {
+  const bool fix = bd.seg || env_int("GDN_PR_BAND_FIN", 2) == 2;
+  if (bd.seg) {
+    for (int b = 0; b < bd.B; b++) pr_seg_kernel<4><<<bd.n_cta, kSellThreads, 0, s>>>(a, b * bd.n_cta);
+  } else if (co_resident) {
     if (fix) pr_band_kernel<4, 256, true><<<bd.n_cta, 256, smem, s>>>(a);
     else pr_band_kernel<4, 256, false><<<bd.n_cta, 256, smem, s>>>(a);
   } else {
@@ -635,13 +773,15 @@ int band_launch(gdn_graph *g, const SellArgs &sa, cudaStream_t s, bool co_reside
   return GDN_OK;
 }
 
+int band_launches(const gdn_graph *g) { return g->pull.band.seg ? g->pull.band.B : 1; }
+
 int band_finalize_grid(const gdn_graph *g) {
   return (int)std::max<int64_t>(1, std::min<int64_t>((g->pull.band.n_rows + 255) / 256, (int64_t)lib().sm_count * 8));
 }
 
 int band_finalize_launch(gdn_graph *g, const SellArgs &a, int grid, cudaStream_t s) {
   const BandLayout &bd = g->pull.band;
-  if (env_int("GDN_PR_BAND_FIN", 2) == 2) pr_band_finalize_fix<<<grid, 256, 0, s>>>(a, bd.acc_fix);
+  if (bd.seg || env_int("GDN_PR_BAND_FIN", 2) == 2) pr_band_finalize_fix<<<grid, 256, 0, s>>>(a, bd.acc_fix);
   else pr_band_finalize<<<grid, 256, 0, s>>>(a, bd.rslot_ptr, bd.rslot, bd.bpartial);
   return GDN_OK;
 }

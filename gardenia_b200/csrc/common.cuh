@@ -93,6 +93,7 @@ struct DevCsr {
 // sums them; what stays behind (cold ids, rows with too few entries in a band) forms a compacted main SELL array.
 struct BandLayout {
   bool tried = false, built = false;
+  bool seg = false;                // segmented mode: bands are L2-sized slices, 32-bit ids, one launch per band (pr_seg_kernel)
   int32_t B = 0, band = 0, cmin = 0, dmin = 0;   // bands, ids per band, min entries of a (row, band) pair, min row length
   int64_t n_rows = 0;              // sorted rows [0, n_rows) take part (whole slices)
   uint4 *bsell = nullptr;          // 8 band-local ids (uint16) per unit; item i = units [item_ptr[i], item_ptr[i+1]), lane-interleaved

@@ -419,7 +419,7 @@ int gdn_graph_info(const gdn_graph *g, int64_t info[8]) {
 int gdn_graph_pull_info(const gdn_graph *g, int64_t info[8]) {
   if (!g || !info) return GDN_ERR_ARG;
   const gdn::BandLayout &b = g->pull.band;
-  info[0] = b.built ? 1 : 0; info[1] = b.B; info[2] = b.band; info[3] = b.n_rows;
+  info[0] = b.built ? (b.seg ? 2 : 1) : 0; info[1] = b.B; info[2] = b.band; info[3] = b.n_rows;
   info[4] = (int64_t)b.moved; info[5] = (int64_t)b.pairs; info[6] = b.n_items;
   info[7] = (int64_t)(b.built ? b.n_groups : g->pull.n_groups);
   return GDN_OK;

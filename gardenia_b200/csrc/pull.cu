@@ -966,7 +966,7 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
   // GDN_PR_OVERLAP=1 (banded layout only): the band sums run on a second stream in 256-thread CTAs that share each SM
   // with a 768-thread main CTA (pr_sell_pipe_co, 32 KB hot table)
   const char *e_ovl = getenv("GDN_PR_OVERLAP");
-  const bool overlap = banded && policy == 1 && pipe != 0 && (e_ovl ? atoi(e_ovl) > 0 : false);
+  const bool overlap = banded && !bd.seg && policy == 1 && pipe != 0 && (e_ovl ? atoi(e_ovl) > 0 : false);
   static cudaStream_t s2 = nullptr;
   static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int32_t hot_n = (int32_t)L.H;
@@ -1054,7 +1054,7 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
       } else {
         GDN_CHECK(band_launch(g, a, s, false));
       }
-      launches++;
+      launches += band_launches(g);
     }
     kern<<<sm, threads, smem, s>>>(a);
     if (!banded) kev_end();

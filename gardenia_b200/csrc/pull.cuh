@@ -88,6 +88,7 @@ void band_free(BandLayout &b);
 int band_launch(gdn_graph *g, const SellArgs &a, cudaStream_t s, bool co_resident);                       // the band partial sums of one iteration
 int band_finalize_launch(gdn_graph *g, const SellArgs &a, int grid, cudaStream_t s);    // + main sums -> row epilogue
 int band_finalize_grid(const gdn_graph *g);
+int band_launches(const gdn_graph *g);
 int band_solve_begin(gdn_graph *g, cudaStream_t s);
 
 }  // namespace gdn

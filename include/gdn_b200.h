@@ -141,7 +141,7 @@ int gdn_graph_destroy(gdn_graph *g);
  * info[5]=n_heavy_segments info[6]=device_bytes info[7]=offset_bits */
 int gdn_graph_info(const gdn_graph *g, int64_t info[8]);
 /* PageRank pull layout of a resident graph (valid after the first gdn_pagerank_resident call):
- * info[0]=banded layout in use (0/1) info[1]=bands info[2]=ids per band info[3]=rows taking part
+ * info[0]=layout in use (0 plain, 1 banded, 2 segmented) info[1]=bands info[2]=ids per band info[3]=rows taking part
  * info[4]=column ids served from shared-memory bands info[5]=(row, band) pairs info[6]=band work items
  * info[7]=int4 groups of the main SELL array in use */
 int gdn_graph_pull_info(const gdn_graph *g, int64_t info[8]);

@@ -29,8 +29,9 @@ def main():
     ok = True
     # third case: many small bands, so that the banded layout (csrc/band.cu) spreads over every rank's cold slice
     small = dict(GDN_PR_BANDS="96", GDN_PR_BAND_SIZE="512", GDN_PR_BAND_CMIN="2", GDN_PR_BAND_DMIN="8")
-    for kind, scale, env in (("g", 16, {}), ("u", 15, {}), ("g", 17, small)):
-        for k in small:
+    seg = dict(GDN_PR_SEGMENT="1", GDN_PR_SEG_IDS="3000")           # segmented mode forced on a small uniform graph
+    for kind, scale, env in (("g", 16, {}), ("u", 15, {}), ("g", 17, small), ("u", 16, seg)):
+        for k in list(small) + list(seg):
             os.environ.pop(k, None)
         os.environ.update(env)
         g = gb.Graph.generate(kind, scale, 16)
@@ -43,7 +44,9 @@ def main():
         scores = torch.full((hi - lo,), float(np.float32(1.0) / np.float32(m)), dtype=torch.float32, device=dev)
         st = dg.pagerank(scores)
         pinfo = dg.pull_info()
-        if kind == "g":
+        if env is seg:
+            assert pinfo["banded"] == 2, pinfo
+        elif kind == "g":
             assert pinfo["banded"] == 1 and pinfo["band_entries"] > 0, pinfo       # no silent fallback to the plain layout
         full = torch.zeros(w * world, dtype=torch.float32, device=dev)
         full[lo:hi] = scores

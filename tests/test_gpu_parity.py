@@ -371,6 +371,31 @@ def test_pr_banded_layout(monkeypatch, kind, scale, bands, band_ids, cmin, dmin)
     dg.close()
 
 
+@pytest.mark.parametrize("kind,scale,seg_ids", [("u", 16, 4096), ("u", 17, 20000), ("g", 16, 3000), ("u", 14, 256)])
+def test_pr_segmented_layout(monkeypatch, kind, scale, seg_ids):
+    """Segmented mode of csrc/band.cu (graphs without a hot set whose vector does not fit L2): every id of every row is
+    gathered in the pass of its L2-sized slice, the passes meet in fixed-point accumulators.  Forced on small graphs."""
+    import torch
+    monkeypatch.setenv("GDN_PR_SEGMENT", "1")
+    monkeypatch.setenv("GDN_PR_SEG_IDS", str(seg_ids))
+    g = gb.Graph.generate(kind, scale, 16)
+    m, rp, ci = g.m, g.out_rowptr(), g.out_colidx()
+    dg = gb.DeviceGraph(g)
+    s1 = torch.full((m,), float(np.float32(1.0) / np.float32(m)), dtype=torch.float32, device="cuda")
+    s2 = s1.clone()
+    st1 = dg.pagerank(s1)
+    info = dg.pull_info()
+    assert info["banded"] == 2 and info["bands"] >= 2, info
+    assert info["band_entries"] >= 0.95 * g.nnz, info            # (all but the last, partial slice of rows)
+    st2 = dg.pagerank(s2)
+    assert st1.iterations == st2.iterations and torch.equal(s1, s2), "segmented PR must be bit-reproducible run to run"
+    oscores, oit, _ = po.pr_pull(m, rp, ci, g.out_degrees())
+    assert st1.iterations == oit
+    assert float(np.abs(s1.cpu().numpy().astype(np.float64) - oscores.astype(np.float64)).sum()) <= PR_L1_TOL
+    assert po.pr_residual(m, rp, ci, s1.cpu().numpy()) < 1e-4
+    dg.close()
+
+
 def test_pr_banded_layout_directed(monkeypatch):
     """Directed graph: rows are sorted by in-degree, columns renumbered by out-degree (rowid indirection)."""
     import torch
