@@ -79,8 +79,11 @@ def load_graph(kind, scale, degree=16):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks + throttle reasons.  The sampler is started BEFORE the warm-up steps (nvidia-smi needs a few hundred
+    ms to come up, and a multi-GPU timed region lasts 0.1 s) and samples every 20 ms with a timestamp; the reported values
+    come from the samples inside the timed region [t0, t1] (`window: "timed"`), or -- if the region was too short to
+    catch one -- from the samples since the start of the warm-up (`window: "warmup+timed"`), i.e. the same kernels under load."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
@@ -88,34 +91,45 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                        "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.p = None
 
-    def stop(self):
+    @staticmethod
+    def _ts(text):
+        import datetime
+        try:
+            return datetime.datetime.strptime(text.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except Exception:
+            return None
+
+    def stop(self, t0=None, t1=None):
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.p.terminate()
         out, _ = self.p.communicate(timeout=5)
-        sm, mx, reasons = [], None, set()
+        rows, mx = [], None
         for line in out.splitlines():
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
+            if len(f) < 10:
                 continue
             try:
-                sm.append(float(f[1])); mx = float(f[2])
+                clk = float(f[2]); mx = float(f[3])
             except ValueError:
                 continue
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        # under load = upper half of the samples (idle samples before/after the region are low)
+            rs = {name for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[6:10])
+                  if v.lower().startswith("active")}
+            rows.append((self._ts(f[0]), clk, rs))
+        timed = [r for r in rows if t0 is not None and r[0] is not None and t0 - 0.02 <= r[0] <= t1 + 0.02]
+        use, window = (timed, "timed") if timed else (rows, "warmup+timed")
+        sm = sorted(r[1] for r in use)
+        reasons = set().union(*[r[2] for r in use]) if use else set()
+        # under load = upper half of the samples (a sample taken between two solves may catch an idle clock)
         load = sm[len(sm) // 2:] if sm else []
         med = load[len(load) // 2] if load else None
-        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def run_reference_binary(args_list, threads):
@@ -251,20 +265,23 @@ def main():
         scores.fill_(init)                       # src/pr/main.cc:17-18
         return dg.pagerank(scores)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         st = pr_step()
     pinfo = dg.pull_info()
-    if pinfo["banded"]:
+    if pinfo["banded"] == 2:
+        kernel_name = (f"pr_seg_kernel x{pinfo['bands']} + pr_sell_pipe + pr_band_finalize (the launches of ONE PageRank iteration over this "
+                       "rank's rows; segmented mode: one pass per L2-sized slice of the gathered vector)")
+    elif pinfo["banded"]:
         # one iteration of the banded layout (csrc/band.cu) is four launches timed as one unit
         kernel_name = ("pr_band_kernel + pr_sell_pipe + pr_sell_finalize + pr_band_finalize (the launches of ONE PageRank iteration "
                        f"over this rank's rows; {pinfo['band_entries'] / max(info['nnz_local'], 1):.1%} of their column ids are gathered from {pinfo['bands']} "
                        "shared-memory bands)")
     else:
         kernel_name = "pr_sell_pipe (one launch = one PageRank iteration over all rows)"
-    sampler = ClockSampler(local_rank)
     barrier()
-    if rank == 0:
-        sampler.start()
     w0 = time.time()
     solve_ms = kern_ms = 0.0
     kern_calls = launches = iters = 0
@@ -274,7 +291,7 @@ def main():
         launches += st.kernel_launches; iters += st.iterations
     barrier()
     wall_ms = (time.time() - w0) * 1e3
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(w0, w0 + wall_ms / 1e3) if rank == 0 else None
     solve_ms = allmax(solve_ms)
     kern_ms_max = allmax(kern_ms)
     value = iters / (solve_ms / 1e3)
