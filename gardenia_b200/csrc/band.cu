@@ -14,8 +14,9 @@
 //     sum per (band slice segment, row);
 //   * what is left (cold ids, sparse (row, band) pairs) is a compacted main SELL array that the unchanged
 //     pr_sell_pipe walks; its epilogue for these rows only deposits the main sum;
-//   * pr_band_finalize adds main sum + band partials of a row in a FIXED (band, segment) order and runs the row
-//     epilogue (score, L1 delta, next contrib).  No atomics: bit-reproducible from run to run.
+//   * the band partials of a row meet in a 64-bit FIXED-POINT accumulator (integer atomics: order-free, exact, hence
+//     bit-reproducible from run to run); pr_band_finalize_fix adds main sum + band sum and runs the row epilogue
+//     (score, L1 delta, next contrib).  (GDN_PR_BAND_FIN=0: per-row slot lists summed in a fixed (band, segment) order.)
 //
 // The layout is built once per resident graph (untimed, like include/segmenting.h preprocessing of the reference):
 // two device passes over the existing SELL array (count, fill) around a host pass that sorts each band's rows.
@@ -436,7 +437,7 @@ int band_build(gdn_graph *g) {
   const std::vector<uint32_t> &sp = L.h_slice_ptr;
   // Is there a hot set?  Share of the SELL array held by the rows of the 64 hottest bands' worth of ids (rows and
   // columns are ranked by the same degrees on a symmetric graph): 0.87 at Kronecker scale 26, 0.05 at urand-26.
-  const int64_t hot_slices = std::min<int64_t>(L.n_slices, (int64_t)64 * kHotMax / 32);
+  const int64_t hot_slices = std::min<int64_t>(L.n_slices, (int64_t)64 * kHotMax / 32 / std::max(L.P, 1));   // this rank's share of them
   const double hot_share = (double)sp[hot_slices] / (double)std::max<uint32_t>(sp[L.n_slices], 1u);
   const int e_seg = env_int("GDN_PR_SEGMENT", -1);       // -1: decide here, 0: never, 1: always
   const bool seg = e_seg == 1 || (e_seg < 0 && hot_share < 0.4 && L.Mp * 4 > ((int64_t)64 << 20));
