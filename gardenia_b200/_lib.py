@@ -84,6 +84,7 @@ SIGNATURES = {
     "gdn_graph_destroy": (C.c_int, [_vp]),
     "gdn_graph_info": (C.c_int, [_vp, C.POINTER(_i64 * 8)]),
     "gdn_graph_pull_info": (C.c_int, [_vp, C.POINTER(_i64 * 8)]),
+    "gdn_band_host_probe": (C.c_int, [C.c_int32, _i64, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, _vp, C.c_int32, _vp]),
     "gdn_band_map_probe": (C.c_int, [_i64, _i64, C.c_int32, C.c_int32, C.c_int32, _i64, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                      C.POINTER(_i64), C.POINTER(C.c_int32)]),
     "gdn_bfs_resident": (C.c_int, [_vp, _i32, _vp, _vp, _SP]),

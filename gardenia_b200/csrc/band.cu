@@ -413,6 +413,304 @@ static int up(gdn_graph *g, T **dptr, const T *h, size_t n) {
   return GDN_OK;
 }
 
+// ------------------------------------------------------------------ host: tables of the band layout (device-free)
+// Everything the host derives from the count matrix: each band's row order and ranks, band slices, items, the
+// (item, lane) -> row map, slot lists, jobs and warp runs, and the compacted main array's slice pointers and work tables.
+// No CUDA call in here: tests/test_host.py drives it through gdn_band_host_probe with synthetic counts.
+struct BandHost {
+  bool ok = false;
+  std::vector<uint32_t> rank, item_ptr, bslice_ptr, bslice_item, rslot_ptr, rslot, sp2;
+  std::vector<int32_t> bslice_first, item_band, irow, job_first, wrun, chunk, hslice, hfirst;
+  std::vector<uint64_t> band_item0;
+  std::vector<int4> job;
+  std::vector<int2> hseg;
+  uint64_t units = 0, moved = 0, pairs = 0, n_rslot = 0, tot2 = 0;
+  int32_t n_items = 0;
+};
+
+static void band_host_tables(int B, int64_t n_rows, int32_t nb, uint32_t W, bool seg, int n_cta, const std::vector<uint32_t> &cnt,
+                             const std::vector<uint32_t> &remw, const std::vector<uint32_t> &sp, int32_t n_slices, BandHost &H) {
+  // host: every band's rows sorted by their count in it; slices, items, ranks
+  struct PerBand {
+    std::vector<uint32_t> order;           // rows by (count desc, row asc)
+    std::vector<uint32_t> slice_units;     // unit offset of each band slice inside the band
+    std::vector<uint32_t> slice_item;      // first item of each band slice inside the band
+    std::vector<uint32_t> item_ng;         // index groups per lane of each item
+    uint64_t units = 0, moved = 0;
+  };
+  std::vector<PerBand> pb((size_t)B);
+  std::vector<uint32_t> rank(cnt.size());
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int b = 0; b < B; b++) {
+    PerBand &q = pb[b];
+    const uint32_t *c = cnt.data() + (size_t)b * n_rows;
+    uint32_t *rk = rank.data() + (size_t)b * n_rows;
+    for (int64_t j = 0; j < n_rows; j++) { rk[j] = kNone; if (c[j]) { q.order.push_back((uint32_t)j); q.moved += c[j]; } }
+    if (!seg) {
+      std::stable_sort(q.order.begin(), q.order.end(), [&](uint32_t x, uint32_t y) { return c[x] > c[y]; });
+    } else {
+      // segmented mode: every row is here, so sort by count only inside windows of 64 K consecutive entries -- the rows
+      // of an item stay close together and the accumulator atomics of a pass sweep through memory instead of scattering
+      // (counting sort: the counts of a graph without hubs are small)
+      const size_t win = 65536;
+      std::vector<uint32_t> tmp(win), start;
+      for (size_t a0 = 0; a0 < q.order.size(); a0 += win) {
+        const size_t a1 = std::min(q.order.size(), a0 + win);
+        uint32_t cmax = 0;
+        for (size_t i = a0; i < a1; i++) cmax = std::max(cmax, c[q.order[i]]);
+        if (cmax > (1u << 20)) {
+          std::stable_sort(q.order.begin() + a0, q.order.begin() + a1, [&](uint32_t x, uint32_t y) { return c[x] > c[y]; });
+          continue;
+        }
+        start.assign((size_t)cmax + 2, 0);
+        for (size_t i = a0; i < a1; i++) start[cmax - c[q.order[i]] + 1]++;          // bucket = cmax - count: descending
+        for (size_t k = 1; k < start.size(); k++) start[k] += start[k - 1];
+        for (size_t i = a0; i < a1; i++) tmp[start[cmax - c[q.order[i]]]++] = q.order[i];
+        std::copy(tmp.begin(), tmp.begin() + (a1 - a0), q.order.begin() + a0);
+      }
+    }
+    const size_t n = q.order.size();
+    for (size_t pos = 0; pos < n; pos++) rk[q.order[pos]] = (uint32_t)pos;
+    for (size_t s0 = 0; s0 < n; s0 += 32) {
+      uint32_t cmx = c[q.order[s0]];                                   // (windowed order: not necessarily the first row)
+      if (seg) for (size_t i = s0; i < std::min(n, s0 + 32); i++) cmx = std::max(cmx, c[q.order[i]]);
+      const uint32_t ng = (cmx + W - 1) / W;
+      q.slice_units.push_back((uint32_t)q.units);
+      q.slice_item.push_back((uint32_t)q.item_ng.size());
+      for (uint32_t t = 0; t < ng; t += kBandSeg) q.item_ng.push_back(std::min<uint32_t>(kBandSeg, ng - t));
+      q.units += 32ull * ng;
+    }
+  }
+  uint64_t units = 0, n_items64 = 0, n_bslices = 0, moved = 0, pairs = 0;
+  std::vector<uint64_t> band_unit0((size_t)B + 1), band_item0((size_t)B + 1);
+  std::vector<int32_t> bslice_first((size_t)B + 1);
+  for (int b = 0; b < B; b++) {
+    band_unit0[b] = units; band_item0[b] = n_items64; bslice_first[b] = (int32_t)n_bslices;
+    units += pb[b].units; n_items64 += pb[b].item_ng.size(); n_bslices += pb[b].slice_units.size();
+    moved += pb[b].moved; pairs += pb[b].order.size();
+  }
+  band_unit0[B] = units; band_item0[B] = n_items64; bslice_first[B] = (int32_t)n_bslices;
+  if (n_items64 == 0 || units >= 0xfffffff0ull / 8 * 8 || n_items64 * 32 >= 0xfffffff0ull) {
+    return;                                          // nothing qualifies (or 32-bit unit offsets would overflow): plain layout
+  }
+  const int32_t n_items = (int32_t)n_items64;
+  std::vector<uint32_t> item_ptr((size_t)n_items + 1), bslice_ptr(n_bslices), bslice_item(n_bslices);
+  std::vector<int32_t> item_band((size_t)n_items);
+  for (int b = 0; b < B; b++) {
+    const PerBand &q = pb[b];
+    uint64_t u = band_unit0[b];
+    for (size_t i = 0; i < q.item_ng.size(); i++) {
+      item_ptr[band_item0[b] + i] = (uint32_t)u;
+      item_band[band_item0[b] + i] = b;
+      u += 32ull * q.item_ng[i];
+    }
+    for (size_t s0 = 0; s0 < q.slice_units.size(); s0++) {
+      bslice_ptr[bslice_first[b] + s0] = (uint32_t)(band_unit0[b] + q.slice_units[s0]);
+      bslice_item[bslice_first[b] + s0] = (uint32_t)(band_item0[b] + q.slice_item[s0]);
+    }
+  }
+  item_ptr[n_items] = (uint32_t)units;
+
+  // sorted row of every (item, lane): the rows of a band slice, repeated for each of its segments
+  std::vector<int32_t> irow((size_t)n_items * 32);
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int b = 0; b < B; b++) {
+    const PerBand &q = pb[b];
+    const size_t n = q.order.size();
+    for (size_t sl = 0; sl < q.slice_item.size(); sl++) {
+      const size_t it0 = band_item0[b] + q.slice_item[sl];
+      const size_t it1 = sl + 1 < q.slice_item.size() ? band_item0[b] + q.slice_item[sl + 1] : band_item0[b + 1];
+      for (size_t it = it0; it < it1; it++)
+        for (int l = 0; l < 32; l++) irow[it * 32 + l] = sl * 32 + l < n ? (int32_t)q.order[sl * 32 + l] : -1;
+    }
+  }
+  // partial slots of every row, in (band, segment) order (slot finalize only; the segmented mode always uses the
+  // fixed-point accumulators)
+  std::vector<uint32_t> rslot_ptr, rslot;
+  uint64_t n_rslot = 0;
+  if (!seg) {
+    rslot_ptr.assign((size_t)n_rows + 1, 0);
+#pragma omp parallel for
+    for (int64_t j = 0; j < n_rows; j++) {
+      uint32_t n = 0;
+      for (int b = 0; b < B; b++) { const uint32_t c = cnt[(size_t)b * n_rows + j]; if (c) n += (c + W * kBandSeg - 1) / (W * kBandSeg); }
+      rslot_ptr[j + 1] = n;
+    }
+    for (int64_t j = 0; j < n_rows; j++) { const uint32_t n = rslot_ptr[j + 1]; rslot_ptr[j] = (uint32_t)n_rslot; n_rslot += n; }
+    rslot_ptr[n_rows] = (uint32_t)n_rslot;
+    if (n_rslot >= 0xfffffff0ull) return;
+    rslot.resize(std::max<uint64_t>(n_rslot, 1));
+#pragma omp parallel for
+    for (int64_t j = 0; j < n_rows; j++) {
+      uint32_t k = rslot_ptr[j];
+      for (int b = 0; b < B; b++) {
+        const uint32_t c = cnt[(size_t)b * n_rows + j];
+        if (!c) continue;
+        const uint32_t r = rank[(size_t)b * n_rows + j];
+        const uint32_t it0 = bslice_item[bslice_first[b] + (r >> 5)];
+        for (uint32_t t = 0; t < (c + W * kBandSeg - 1) / (W * kBandSeg); t++) rslot[k++] = (it0 + t) * 32 + (r & 31);
+      }
+    }
+  }
+
+  // jobs: equal-cost contiguous runs of items per CTA, cut at band boundaries, each cut into 32 warp runs
+  std::vector<uint64_t> pc((size_t)n_items + 1, 0);
+  for (int32_t i = 0; i < n_items; i++) pc[i + 1] = pc[i] + ((item_ptr[i + 1] - item_ptr[i]) >> 5) + 2;
+  auto first_at = [&](uint64_t cost) -> int32_t { return (int32_t)(std::lower_bound(pc.begin(), pc.end(), cost) - pc.begin()); };
+  std::vector<int4> job;
+  std::vector<int32_t> job_first((size_t)n_cta + 1, 0), wrun;
+  auto push_job = [&](int b, int32_t lo, int32_t e) {
+    const int32_t w0 = (int32_t)wrun.size();
+    for (int w = 0; w <= 32; w++) {
+      int32_t x = w == 32 ? e : first_at(pc[lo] + (pc[e] - pc[lo]) * w / 32);
+      x = std::max(lo, std::min(x, e));
+      wrun.push_back(x);
+    }
+    job.push_back(make_int4(b, w0, lo, e));
+  };
+  if (seg) {
+    // one launch per band: job b * n_cta + c = CTA c's equal-cost share of band b's items (possibly empty)
+    for (int b = 0; b < B; b++) {
+      const int32_t bl = (int32_t)band_item0[b], bh = (int32_t)band_item0[b + 1];
+      for (int c = 0; c < n_cta; c++) {
+        int32_t lo = bl, hi = bh;
+        if (bh > bl) {
+          lo = std::max(bl, std::min(first_at(pc[bl] + (pc[bh] - pc[bl]) * c / n_cta), bh));
+          hi = c == n_cta - 1 ? bh : std::max(bl, std::min(first_at(pc[bl] + (pc[bh] - pc[bl]) * (c + 1) / n_cta), bh));
+        }
+        push_job(b, lo, std::max(lo, hi));
+      }
+    }
+  }
+  for (int c = 0; c < n_cta && !seg; c++) {
+    job_first[c] = (int32_t)job.size();
+    int32_t lo = std::min(first_at(pc[n_items] * c / n_cta), n_items), hi = std::min(first_at(pc[n_items] * (c + 1) / n_cta), n_items);
+    if (c == n_cta - 1) hi = n_items;
+    while (lo < hi) {
+      const int b = item_band[lo];
+      const int32_t e = (int32_t)std::min<uint64_t>((uint64_t)hi, band_item0[b + 1]);
+      push_job(b, lo, e);
+      lo = e;
+    }
+  }
+  job_first[n_cta] = seg ? 0 : (int32_t)job.size();
+
+  // compacted main array: band slices get their remaining width, the others keep theirs
+  std::vector<uint32_t> sp2((size_t)n_slices + 1);
+  uint64_t tot2 = 0;
+  for (int32_t s = 0; s < n_slices; s++) {
+    sp2[s] = (uint32_t)tot2;
+    tot2 += s < nb ? 32ull * ((remw[s] + 3) / 4) : (uint64_t)(sp[s + 1] - sp[s]);
+  }
+  sp2[n_slices] = (uint32_t)tot2;
+  std::vector<int32_t> chunk, hslice, hfirst;
+  std::vector<int2> hseg;
+  make_work_tables(sp2, n_slices, chunk, hslice, hfirst, hseg);
+  H.rank = std::move(rank); H.item_ptr = std::move(item_ptr); H.bslice_ptr = std::move(bslice_ptr); H.bslice_item = std::move(bslice_item);
+  H.rslot_ptr = std::move(rslot_ptr); H.rslot = std::move(rslot); H.sp2 = std::move(sp2);
+  H.bslice_first = std::move(bslice_first); H.item_band = std::move(item_band); H.irow = std::move(irow);
+  H.job_first = std::move(job_first); H.wrun = std::move(wrun); H.chunk = std::move(chunk); H.hslice = std::move(hslice); H.hfirst = std::move(hfirst);
+  H.band_item0 = std::move(band_item0); H.job = std::move(job); H.hseg = std::move(hseg);
+  H.units = units; H.moved = moved; H.pairs = pairs; H.n_rslot = n_rslot; H.tot2 = tot2; H.n_items = n_items;
+  H.ok = true;
+}
+
+// Invariants of the host tables (what the kernels rely on); returns 0 or the negative number of the first one broken.
+static int band_host_check(int B, int64_t n_rows, int32_t nb, uint32_t W, bool seg, int n_cta, const std::vector<uint32_t> &cnt,
+                           const std::vector<uint32_t> &remw, const std::vector<uint32_t> &sp, int32_t n_slices, const BandHost &H) {
+  const int32_t n_items = H.n_items;
+  if ((int64_t)H.item_ptr.size() != (int64_t)n_items + 1 || H.item_ptr[0] != 0 || H.item_ptr[n_items] != H.units) return -1;
+  // 1. ranks of a band are a bijection between its rows and 0 .. n_b - 1; slices are wide enough for every row in them
+  uint64_t moved = 0, pairs = 0;
+  for (int b = 0; b < B; b++) {
+    const uint32_t *c = cnt.data() + (size_t)b * n_rows, *rk = H.rank.data() + (size_t)b * n_rows;
+    size_t n = 0;
+    for (int64_t j = 0; j < n_rows; j++) n += c[j] != 0;
+    std::vector<uint8_t> seen(n, 0);
+    const int32_t bs0 = H.bslice_first[b], bs1 = H.bslice_first[b + 1];
+    if ((size_t)(bs1 - bs0) != (n + 31) / 32) return -2;
+    for (int64_t j = 0; j < n_rows; j++) {
+      if (!c[j]) { if (rk[j] != kNone) return -3; continue; }
+      const uint32_t r = rk[j];
+      if (r >= n || seen[r]) return -4;
+      seen[r] = 1; moved += c[j]; pairs++;
+      // the slice of rank r: its items hold >= c[j] ids per lane, and (item, lane) maps back to row j
+      const uint32_t sl = bs0 + (r >> 5);
+      const uint32_t it0 = H.bslice_item[sl], it1 = sl + 1 < (uint32_t)bs1 ? H.bslice_item[sl + 1] : (uint32_t)H.band_item0[b + 1];
+      if (it0 >= it1 || H.item_ptr[it0] != H.bslice_ptr[sl]) return -5;
+      const uint64_t cap = (uint64_t)(H.item_ptr[it1] - H.item_ptr[it0]) / 32 * W;
+      if (cap < c[j]) return -6;
+      for (uint32_t it = it0; it < it1; it++) {
+        if (H.item_band[it] != b) return -7;
+        if (H.irow[(size_t)it * 32 + (r & 31)] != (int32_t)j) return -8;
+        const uint32_t ng = (H.item_ptr[it + 1] - H.item_ptr[it]) / 32;
+        if (ng == 0 || ng > (uint32_t)kBandSeg || (H.item_ptr[it + 1] - H.item_ptr[it]) % 32) return -9;
+      }
+    }
+    // lanes beyond the band's last row map to no row
+    if (n % 32) {
+      const uint32_t sl = bs1 - 1;
+      for (uint32_t it = H.bslice_item[sl]; it < (uint32_t)H.band_item0[b + 1]; it++)
+        for (uint32_t l = n % 32; l < 32; l++) if (H.irow[(size_t)it * 32 + l] != -1) return -10;
+    }
+  }
+  if (moved != H.moved || pairs != H.pairs) return -11;
+  // 2. slot lists (slot finalize): row j owns exactly the (item, its lane) slots of the segments that hold its ids
+  if (!seg) {
+    if ((int64_t)H.rslot_ptr.size() != n_rows + 1 || H.rslot_ptr[n_rows] != H.n_rslot) return -12;
+    for (int64_t j = 0; j < n_rows; j++) {
+      uint32_t k = H.rslot_ptr[j];
+      for (int b = 0; b < B; b++) {
+        const uint32_t c = cnt[(size_t)b * n_rows + j];
+        for (uint32_t t = 0; t < (c + W * kBandSeg - 1) / (W * kBandSeg); t++, k++) {
+          if (k >= H.rslot_ptr[j + 1]) return -13;
+          const uint32_t slot = H.rslot[k];
+          if (H.irow[slot] != (int32_t)j || H.item_band[slot / 32] != b) return -14;
+        }
+      }
+      if (k != H.rslot_ptr[j + 1]) return -15;
+    }
+  }
+  // 3. jobs: every item belongs to exactly one warp run of one job; a job stays inside one band; runs are ordered
+  std::vector<uint8_t> cover((size_t)n_items, 0);
+  const size_t n_jobs = H.job.size();
+  if (seg && n_jobs != (size_t)B * n_cta) return -16;
+  if (!seg && ((int)H.job_first.size() != n_cta + 1 || H.job_first[n_cta] != (int32_t)n_jobs)) return -17;
+  for (size_t q = 0; q < n_jobs; q++) {
+    const int4 J = H.job[q];
+    if (seg && J.x != (int)(q / n_cta)) return -18;
+    if (J.y < 0 || (size_t)J.y + 33 > H.wrun.size() || H.wrun[J.y] != J.z || H.wrun[J.y + 32] != J.w) return -19;
+    for (int w = 0; w < 32; w++) {
+      const int32_t i0 = H.wrun[J.y + w], i1 = H.wrun[J.y + w + 1];
+      if (i0 > i1 || i0 < 0 || i1 > n_items) return -20;
+      for (int32_t i = i0; i < i1; i++) { if (cover[i]++ || H.item_band[i] != J.x) return -21; }
+    }
+  }
+  for (int32_t i = 0; i < n_items; i++) if (!cover[i]) return -22;
+  // 4. the compacted main array: band slices are exactly as wide as their longest remainder, the others keep their width
+  if ((int32_t)H.sp2.size() != n_slices + 1 || H.sp2[0] != 0 || H.sp2[n_slices] != H.tot2) return -23;
+  for (int32_t t = 0; t < n_slices; t++) {
+    const uint32_t w2 = H.sp2[t + 1] - H.sp2[t];
+    if (t < nb ? w2 != 32 * ((remw[t] + 3) / 4) : w2 != sp[t + 1] - sp[t]) return -24;
+  }
+  // 5. work tables of the main array: chunks are ordered, every non-empty light slice is reachable, wide slices are segmented
+  const int32_t n_chunks = (int32_t)H.chunk.size() - 1;
+  if (n_chunks < 1 || H.chunk[n_chunks] != n_slices) return -25;
+  for (int32_t k = 0; k < n_chunks; k++) if (H.chunk[k] > H.chunk[k + 1]) return -26;
+  for (int32_t t = 0; t < H.chunk[0]; t++) if (H.sp2[t + 1] != H.sp2[t]) return -27;      // skipped slices must be empty
+  size_t hs = 0;
+  for (int32_t t = 0; t < n_slices; t++) {
+    const uint32_t sz = H.sp2[t + 1] - H.sp2[t];
+    if (sz > (uint32_t)kGroupCh) {
+      if (hs >= H.hslice.size() || H.hslice[hs] != t) return -28;
+      if (H.hfirst[hs + 1] - H.hfirst[hs] != (int32_t)((sz + kGroupCh - 1) / kGroupCh)) return -29;
+      hs++;
+    }
+  }
+  if (hs != H.hslice.size() || H.hfirst[hs] != (int32_t)H.hseg.size()) return -30;
+  return 0;
+}
+
 void band_free(BandLayout &b) {
   cudaFree(b.bsell); cudaFree(b.band_start); cudaFree(b.band_len); cudaFree(b.item_ptr); cudaFree(b.job); cudaFree(b.job_first); cudaFree(b.wrun); cudaFree(b.bpartial); cudaFree(b.irow); cudaFree(b.acc_fix);
   cudaFree(b.rslot_ptr); cudaFree(b.rslot); cudaFree(b.acc_main); cudaFree(b.sell); cudaFree(b.slice_ptr);
@@ -480,185 +778,21 @@ int band_build(gdn_graph *g) {
   GDN_CUDA(cudaGetLastError());
   trace("band_build: counted");
 
-  // host: every band's rows sorted by their count in it; slices, items, ranks
-  struct PerBand {
-    std::vector<uint32_t> order;           // rows by (count desc, row asc)
-    std::vector<uint32_t> slice_units;     // unit offset of each band slice inside the band
-    std::vector<uint32_t> slice_item;      // first item of each band slice inside the band
-    std::vector<uint32_t> item_ng;         // index groups per lane of each item
-    uint64_t units = 0, moved = 0;
-  };
-  std::vector<PerBand> pb((size_t)B);
-  std::vector<uint32_t> rank(cnt.size());
-#pragma omp parallel for schedule(dynamic, 1)
-  for (int b = 0; b < B; b++) {
-    PerBand &q = pb[b];
-    const uint32_t *c = cnt.data() + (size_t)b * n_rows;
-    uint32_t *rk = rank.data() + (size_t)b * n_rows;
-    for (int64_t j = 0; j < n_rows; j++) { rk[j] = kNone; if (c[j]) { q.order.push_back((uint32_t)j); q.moved += c[j]; } }
-    if (!seg) {
-      std::stable_sort(q.order.begin(), q.order.end(), [&](uint32_t x, uint32_t y) { return c[x] > c[y]; });
-    } else {
-      // segmented mode: every row is here, so sort by count only inside windows of 64 K consecutive entries -- the rows
-      // of an item stay close together and the accumulator atomics of a pass sweep through memory instead of scattering
-      // (counting sort: the counts of a graph without hubs are small)
-      const size_t win = 65536;
-      std::vector<uint32_t> tmp(win), start;
-      for (size_t a0 = 0; a0 < q.order.size(); a0 += win) {
-        const size_t a1 = std::min(q.order.size(), a0 + win);
-        uint32_t cmax = 0;
-        for (size_t i = a0; i < a1; i++) cmax = std::max(cmax, c[q.order[i]]);
-        if (cmax > (1u << 20)) {
-          std::stable_sort(q.order.begin() + a0, q.order.begin() + a1, [&](uint32_t x, uint32_t y) { return c[x] > c[y]; });
-          continue;
-        }
-        start.assign((size_t)cmax + 2, 0);
-        for (size_t i = a0; i < a1; i++) start[cmax - c[q.order[i]] + 1]++;          // bucket = cmax - count: descending
-        for (size_t k = 1; k < start.size(); k++) start[k] += start[k - 1];
-        for (size_t i = a0; i < a1; i++) tmp[start[cmax - c[q.order[i]]]++] = q.order[i];
-        std::copy(tmp.begin(), tmp.begin() + (a1 - a0), q.order.begin() + a0);
-      }
-    }
-    const size_t n = q.order.size();
-    for (size_t pos = 0; pos < n; pos++) rk[q.order[pos]] = (uint32_t)pos;
-    for (size_t s0 = 0; s0 < n; s0 += 32) {
-      uint32_t cmx = c[q.order[s0]];                                   // (windowed order: not necessarily the first row)
-      if (seg) for (size_t i = s0; i < std::min(n, s0 + 32); i++) cmx = std::max(cmx, c[q.order[i]]);
-      const uint32_t ng = (cmx + W - 1) / W;
-      q.slice_units.push_back((uint32_t)q.units);
-      q.slice_item.push_back((uint32_t)q.item_ng.size());
-      for (uint32_t t = 0; t < ng; t += kBandSeg) q.item_ng.push_back(std::min<uint32_t>(kBandSeg, ng - t));
-      q.units += 32ull * ng;
-    }
-  }
-  uint64_t units = 0, n_items64 = 0, n_bslices = 0, moved = 0, pairs = 0;
-  std::vector<uint64_t> band_unit0((size_t)B + 1), band_item0((size_t)B + 1);
-  std::vector<int32_t> bslice_first((size_t)B + 1);
-  for (int b = 0; b < B; b++) {
-    band_unit0[b] = units; band_item0[b] = n_items64; bslice_first[b] = (int32_t)n_bslices;
-    units += pb[b].units; n_items64 += pb[b].item_ng.size(); n_bslices += pb[b].slice_units.size();
-    moved += pb[b].moved; pairs += pb[b].order.size();
-  }
-  band_unit0[B] = units; band_item0[B] = n_items64; bslice_first[B] = (int32_t)n_bslices;
-  if (n_items64 == 0 || units >= 0xfffffff0ull / 8 * 8 || n_items64 * 32 >= 0xfffffff0ull) {
-    cudaFree(d_cnt); cudaFree(d_remw);
-    return GDN_OK;                                   // nothing qualifies (or 32-bit unit offsets would overflow): plain layout
-  }
-  const int32_t n_items = (int32_t)n_items64;
-  std::vector<uint32_t> item_ptr((size_t)n_items + 1), bslice_ptr(n_bslices), bslice_item(n_bslices);
-  std::vector<int32_t> item_band((size_t)n_items);
-  for (int b = 0; b < B; b++) {
-    const PerBand &q = pb[b];
-    uint64_t u = band_unit0[b];
-    for (size_t i = 0; i < q.item_ng.size(); i++) {
-      item_ptr[band_item0[b] + i] = (uint32_t)u;
-      item_band[band_item0[b] + i] = b;
-      u += 32ull * q.item_ng[i];
-    }
-    for (size_t s0 = 0; s0 < q.slice_units.size(); s0++) {
-      bslice_ptr[bslice_first[b] + s0] = (uint32_t)(band_unit0[b] + q.slice_units[s0]);
-      bslice_item[bslice_first[b] + s0] = (uint32_t)(band_item0[b] + q.slice_item[s0]);
-    }
-  }
-  item_ptr[n_items] = (uint32_t)units;
-
-  // sorted row of every (item, lane): the rows of a band slice, repeated for each of its segments
-  std::vector<int32_t> irow((size_t)n_items * 32);
-#pragma omp parallel for schedule(dynamic, 1)
-  for (int b = 0; b < B; b++) {
-    const PerBand &q = pb[b];
-    const size_t n = q.order.size();
-    for (size_t sl = 0; sl < q.slice_item.size(); sl++) {
-      const size_t it0 = band_item0[b] + q.slice_item[sl];
-      const size_t it1 = sl + 1 < q.slice_item.size() ? band_item0[b] + q.slice_item[sl + 1] : band_item0[b + 1];
-      for (size_t it = it0; it < it1; it++)
-        for (int l = 0; l < 32; l++) irow[it * 32 + l] = sl * 32 + l < n ? (int32_t)q.order[sl * 32 + l] : -1;
-    }
-  }
-  // partial slots of every row, in (band, segment) order (slot finalize only; the segmented mode always uses the
-  // fixed-point accumulators)
-  std::vector<uint32_t> rslot_ptr, rslot;
-  uint64_t n_rslot = 0;
-  if (!seg) {
-    rslot_ptr.assign((size_t)n_rows + 1, 0);
-#pragma omp parallel for
-    for (int64_t j = 0; j < n_rows; j++) {
-      uint32_t n = 0;
-      for (int b = 0; b < B; b++) { const uint32_t c = cnt[(size_t)b * n_rows + j]; if (c) n += (c + W * kBandSeg - 1) / (W * kBandSeg); }
-      rslot_ptr[j + 1] = n;
-    }
-    for (int64_t j = 0; j < n_rows; j++) { const uint32_t n = rslot_ptr[j + 1]; rslot_ptr[j] = (uint32_t)n_rslot; n_rslot += n; }
-    rslot_ptr[n_rows] = (uint32_t)n_rslot;
-    if (n_rslot >= 0xfffffff0ull) { cudaFree(d_cnt); cudaFree(d_remw); return GDN_OK; }
-    rslot.resize(std::max<uint64_t>(n_rslot, 1));
-#pragma omp parallel for
-    for (int64_t j = 0; j < n_rows; j++) {
-      uint32_t k = rslot_ptr[j];
-      for (int b = 0; b < B; b++) {
-        const uint32_t c = cnt[(size_t)b * n_rows + j];
-        if (!c) continue;
-        const uint32_t r = rank[(size_t)b * n_rows + j];
-        const uint32_t it0 = bslice_item[bslice_first[b] + (r >> 5)];
-        for (uint32_t t = 0; t < (c + W * kBandSeg - 1) / (W * kBandSeg); t++) rslot[k++] = (it0 + t) * 32 + (r & 31);
-      }
-    }
-  }
-
-  // jobs: equal-cost contiguous runs of items per CTA, cut at band boundaries, each cut into 32 warp runs
+  // host: every band's rows sorted by their count in it; slices, items, ranks, jobs, main array tables
   const int n_cta = sm;
-  std::vector<uint64_t> pc((size_t)n_items + 1, 0);
-  for (int32_t i = 0; i < n_items; i++) pc[i + 1] = pc[i] + ((item_ptr[i + 1] - item_ptr[i]) >> 5) + 2;
-  auto first_at = [&](uint64_t cost) -> int32_t { return (int32_t)(std::lower_bound(pc.begin(), pc.end(), cost) - pc.begin()); };
-  std::vector<int4> job;
-  std::vector<int32_t> job_first((size_t)n_cta + 1, 0), wrun;
-  auto push_job = [&](int b, int32_t lo, int32_t e) {
-    const int32_t w0 = (int32_t)wrun.size();
-    for (int w = 0; w <= 32; w++) {
-      int32_t x = w == 32 ? e : first_at(pc[lo] + (pc[e] - pc[lo]) * w / 32);
-      x = std::max(lo, std::min(x, e));
-      wrun.push_back(x);
-    }
-    job.push_back(make_int4(b, w0, lo, e));
-  };
-  if (seg) {
-    // one launch per band: job b * n_cta + c = CTA c's equal-cost share of band b's items (possibly empty)
-    for (int b = 0; b < B; b++) {
-      const int32_t bl = (int32_t)band_item0[b], bh = (int32_t)band_item0[b + 1];
-      for (int c = 0; c < n_cta; c++) {
-        int32_t lo = bl, hi = bh;
-        if (bh > bl) {
-          lo = std::max(bl, std::min(first_at(pc[bl] + (pc[bh] - pc[bl]) * c / n_cta), bh));
-          hi = c == n_cta - 1 ? bh : std::max(bl, std::min(first_at(pc[bl] + (pc[bh] - pc[bl]) * (c + 1) / n_cta), bh));
-        }
-        push_job(b, lo, std::max(lo, hi));
-      }
-    }
+  BandHost H;
+  band_host_tables(B, n_rows, nb, W, seg, n_cta, cnt, remw, sp, L.n_slices, H);
+  if (!H.ok) { cudaFree(d_cnt); cudaFree(d_remw); return GDN_OK; }
+  if (env_int("GDN_BAND_CHECK", 0)) {              // the same invariants the CPU test checks, on the real counts
+    const int bad = band_host_check(B, n_rows, nb, W, seg, n_cta, cnt, remw, sp, L.n_slices, H);
+    if (bad) { cudaFree(d_cnt); cudaFree(d_remw); set_error("band layout: host table invariant %d broken", bad); return GDN_ERR_GRAPH; }
   }
-  for (int c = 0; c < n_cta && !seg; c++) {
-    job_first[c] = (int32_t)job.size();
-    int32_t lo = std::min(first_at(pc[n_items] * c / n_cta), n_items), hi = std::min(first_at(pc[n_items] * (c + 1) / n_cta), n_items);
-    if (c == n_cta - 1) hi = n_items;
-    while (lo < hi) {
-      const int b = item_band[lo];
-      const int32_t e = (int32_t)std::min<uint64_t>((uint64_t)hi, band_item0[b + 1]);
-      push_job(b, lo, e);
-      lo = e;
-    }
-  }
-  job_first[n_cta] = seg ? 0 : (int32_t)job.size();
   trace("band_build: host tables");
-
-  // compacted main array: band slices get their remaining width, the others keep theirs
-  std::vector<uint32_t> sp2((size_t)L.n_slices + 1);
-  uint64_t tot2 = 0;
-  for (int32_t s = 0; s < L.n_slices; s++) {
-    sp2[s] = (uint32_t)tot2;
-    tot2 += s < nb ? 32ull * ((remw[s] + 3) / 4) : (uint64_t)(sp[s + 1] - sp[s]);
-  }
-  sp2[L.n_slices] = (uint32_t)tot2;
-  std::vector<int32_t> chunk, hslice, hfirst;
-  std::vector<int2> hseg;
-  make_work_tables(sp2, L.n_slices, chunk, hslice, hfirst, hseg);
+  auto &rank = H.rank; auto &item_ptr = H.item_ptr; auto &bslice_ptr = H.bslice_ptr; auto &rslot_ptr = H.rslot_ptr; auto &rslot = H.rslot;
+  auto &sp2 = H.sp2; auto &bslice_first = H.bslice_first; auto &irow = H.irow; auto &job_first = H.job_first; auto &wrun = H.wrun;
+  auto &chunk = H.chunk; auto &hslice = H.hslice; auto &hfirst = H.hfirst; auto &job = H.job; auto &hseg = H.hseg;
+  const uint64_t units = H.units, moved = H.moved, pairs = H.pairs, n_rslot = H.n_rslot, tot2 = H.tot2;
+  const int32_t n_items = H.n_items;
 
   bd.seg = seg;
   bd.B = B; bd.band = band; bd.cmin = cmin; bd.dmin = dmin; bd.n_rows = n_rows;
@@ -750,6 +884,27 @@ extern "C" int gdn_band_map_probe(int64_t H, int64_t Wc, int32_t P, int32_t band
   *start_out = 0; *len_out = 0;
   if (*band_out >= 0) gdn::band_range(mp, *band_out, *start_out, *len_out);
   return GDN_OK;
+}
+
+// Host-only probe of the band layout's host tables (tests/test_host.py): builds them from a caller-supplied count
+// matrix cnt[B][n_rows] (n_rows = 32 * number of band slices), the remaining widths of the band slices and the slice
+// pointers of the plain array, and checks the invariants the kernels rely on.  Returns 0, 1 (nothing qualifies) or the
+// negative number of the broken invariant.  stats[0..5] = items, units, pairs, moved ids, jobs, main groups.
+extern "C" int gdn_band_host_probe(int32_t B, int64_t n_rows, int32_t ids_per_unit, int32_t segmented, int32_t n_cta,
+                                   const uint32_t *cnt, const uint32_t *rem_w, const uint32_t *slice_ptr, int32_t n_slices,
+                                   int64_t *stats) {
+  if (B < 1 || n_rows < 32 || n_rows % 32 || (ids_per_unit != 4 && ids_per_unit != 8) || n_cta < 1 || !cnt || !rem_w || !slice_ptr ||
+      n_slices < n_rows / 32) return GDN_ERR_ARG;
+  const int32_t nb = (int32_t)(n_rows / 32);
+  std::vector<uint32_t> c(cnt, cnt + (size_t)B * n_rows), rw(rem_w, rem_w + nb), sp(slice_ptr, slice_ptr + n_slices + 1);
+  gdn::BandHost H;
+  gdn::band_host_tables(B, n_rows, nb, (uint32_t)ids_per_unit, segmented != 0, n_cta, c, rw, sp, n_slices, H);
+  if (!H.ok) return 1;
+  if (stats) {
+    stats[0] = H.n_items; stats[1] = (int64_t)H.units; stats[2] = (int64_t)H.pairs; stats[3] = (int64_t)H.moved;
+    stats[4] = (int64_t)H.job.size(); stats[5] = (int64_t)H.tot2;
+  }
+  return gdn::band_host_check(B, n_rows, nb, (uint32_t)ids_per_unit, segmented != 0, n_cta, c, rw, sp, n_slices, H);
 }
 
 namespace gdn {

@@ -148,6 +148,12 @@ int gdn_graph_pull_info(const gdn_graph *g, int64_t info[8]);
 /* Host-only probe of the banded layout's id -> band map over the id space
  * [hot prefix of H ids | P cold slices of Wc ids] (csrc/band.cu band_of / band_range): *band_out = band of new id `id`
  * (-1: beyond the first B bands), *local_out = its 16-bit index inside the band, *start_out / *len_out = the band's id range. */
+/* Host-only probe of the banded layout's host tables (csrc/band.cu band_host_tables + band_host_check): builds them from
+ * a count matrix cnt[B][n_rows], the remaining widths of the n_rows/32 band slices and the slice pointers of the plain
+ * SELL array, and checks the invariants the kernels rely on.  0 = all hold, 1 = nothing qualifies, < 0 = broken invariant. */
+int gdn_band_host_probe(int32_t B, int64_t n_rows, int32_t ids_per_unit, int32_t segmented, int32_t n_cta,
+                        const uint32_t *cnt, const uint32_t *rem_w, const uint32_t *slice_ptr, int32_t n_slices,
+                        int64_t *stats);
 int gdn_band_map_probe(int64_t H, int64_t Wc, int32_t P, int32_t band, int32_t B, int64_t id, int32_t *band_out,
                        int32_t *local_out, int64_t *start_out, int32_t *len_out);
 

@@ -183,3 +183,59 @@ def test_band_map_is_a_partition(H, Wc, P, band, B):
     for q in range(P):
         if Wc > 0 and n0 + q < B:
             assert probe(H + q * Wc)[0] == n0 + q
+
+
+def _band_probe(B, cnt, remw, sp, W, seg, n_cta):
+    n_rows = cnt.shape[1]
+    stats = np.zeros(8, dtype=np.int64)
+    cnt = np.ascontiguousarray(cnt, dtype=np.uint32); remw = np.ascontiguousarray(remw, dtype=np.uint32)
+    sp = np.ascontiguousarray(sp, dtype=np.uint32)
+    rc = _lib.lib.gdn_band_host_probe(B, n_rows, W, int(seg), n_cta, cnt.ctypes.data, remw.ctypes.data, sp.ctypes.data,
+                                      len(sp) - 1, stats.ctypes.data)
+    return rc, stats
+
+
+@pytest.mark.parametrize("seed,B,nb,extra,W,seg,n_cta,kind", [
+    (1, 7, 40, 9, 8, False, 148, "skewed"),      # banded mode: hubs with thousands of ids per band, most pairs empty
+    (2, 64, 12, 3, 8, False, 148, "skewed"),
+    (3, 1, 5, 0, 8, False, 4, "dense"),          # one band, every row in it, no other slices
+    (4, 5, 70, 1, 4, True, 148, "uniform"),      # segmented mode: every row in every band, small counts
+    (5, 3, 2100, 2, 4, True, 16, "uniform"),     # more than one 64 K-row sort window
+    (6, 9, 33, 4, 8, False, 7, "sparse"),        # a few pairs only: most CTAs get no job
+])
+def test_band_host_tables_invariants(seed, B, nb, extra, W, seg, n_cta, kind):
+    """csrc/band.cu band_host_tables on synthetic count matrices: ranks are bijections, band slices hold their rows'
+    ids, (item, lane) maps back to the row, slot lists and jobs / warp runs cover every item exactly once, the compacted
+    main array keeps the right widths (the invariants pr_band_kernel / pr_seg_kernel / pr_sell_pipe rely on)."""
+    rng = np.random.default_rng(seed)
+    n_rows = nb * 32
+    if kind == "skewed":
+        deg = np.sort((rng.pareto(0.9, n_rows) * 20 + 64).astype(np.int64))[::-1]
+        p = rng.dirichlet(np.ones(B) * 0.5)
+        cnt = rng.binomial(np.minimum(deg, 40000)[None, :], p[:, None] * 0.7).astype(np.uint32)
+        cnt[cnt < 4] = 0
+    elif kind == "dense":
+        cnt = rng.integers(1, 3000, size=(B, n_rows)).astype(np.uint32)
+    elif kind == "uniform":
+        cnt = rng.poisson(5.0, size=(B, n_rows)).astype(np.uint32)
+    else:
+        cnt = np.zeros((B, n_rows), dtype=np.uint32)
+        idx = rng.integers(0, B * n_rows, 25)
+        cnt.reshape(-1)[idx] = rng.integers(4, 900, 25)
+    remw = rng.integers(0, 5000 if kind == "skewed" else 40, nb).astype(np.uint32)
+    if seg:
+        remw[:] = 0
+    old_w = 32 * ((np.concatenate([remw + rng.integers(0, 9, nb).astype(np.uint32), rng.integers(1, 30, extra).astype(np.uint32)]) + 3) // 4)
+    sp = np.concatenate([[0], np.cumsum(old_w)]).astype(np.uint32)
+    rc, stats = _band_probe(B, cnt, remw, sp, W, seg, n_cta)
+    assert rc == 0, f"invariant {rc} broken"
+    assert stats[2] == int((cnt > 0).sum()) and stats[3] == int(cnt.sum())
+    assert stats[1] * W >= stats[3]                                     # padded ids >= ids
+    if seg:
+        assert stats[4] == B * n_cta
+
+
+def test_band_host_tables_nothing_qualifies():
+    cnt = np.zeros((4, 64), dtype=np.uint32)
+    rc, _ = _band_probe(4, cnt, np.zeros(2, np.uint32), np.array([0, 32, 64, 96], np.uint32), 8, False, 8)
+    assert rc == 1
