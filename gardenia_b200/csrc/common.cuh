@@ -8,6 +8,20 @@
 #include <vector>
 #include "../../include/gdn_b200.h"
 
+// Device allocations of the library go through the arena of pool.cu (a plain cudaMalloc / cudaFree outside one-shot calls).
+namespace gdn {
+cudaError_t pool_malloc(void **p, size_t bytes);
+cudaError_t pool_free(void *p);
+void pool_release();              // really free what the arena holds (gdn_finalize, allocation failure)
+void pool_scope(bool enter);      // a one-shot call is running: park freed blocks instead of freeing them
+struct PoolScope {
+  PoolScope() { pool_scope(true); }
+  ~PoolScope() { pool_scope(false); }
+};
+}  // namespace gdn
+#define cudaMalloc(p, n) gdn::pool_malloc((void **)(p), (n))
+#define cudaFree(p) gdn::pool_free((void *)(p))
+
 namespace gdn {
 
 // ---------------------------------------------------------------- error plumbing

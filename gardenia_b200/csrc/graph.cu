@@ -351,6 +351,7 @@ int gdn_finalize(void) {
   Lib &l = lib();
   if (!l.inited) return GDN_OK;
   cudaStreamSynchronize(l.stream);
+  pool_release();
   cudaStreamDestroy(l.stream);
   cudaStreamSynchronize(l.copy_stream);
   cudaStreamDestroy(l.copy_stream);

@@ -52,6 +52,7 @@ int bfs_oneshot(int64_t m, int64_t nnz, const OffT *orp, const int32_t *oci, con
                 int32_t source, int32_t *depth_out, int32_t *parent_out, gdn_stats *st) {
   if (!orp || !oci || !depth_out) { set_error("gdn_bfs: null argument"); return GDN_ERR_ARG; }
   GDN_CHECK(ensure_init());
+  PoolScope arena;                 // declared before every buffer of the call: they are parked, not freed, on the way out
   const double t0 = now_ms();
   GraphGuard gg;
   GDN_CHECK(create<OffT>(m, nnz, orp, oci, irp, ici, &gg.g));
@@ -78,6 +79,7 @@ int pr_oneshot(int64_t m, int64_t nnz, const OffT *irp, const int32_t *ici, cons
                float *scores, float damp, double eps, int max_iter, gdn_stats *st) {
   if (!irp || !ici || !out_degree || !scores) { set_error("gdn_pagerank_pull: null argument"); return GDN_ERR_ARG; }
   GDN_CHECK(ensure_init());
+  PoolScope arena;                 // declared before every buffer of the call: they are parked, not freed, on the way out
   const double t0 = now_ms();
   // the two small inputs go first (queued, not waited for); then the CSR, whose column array crosses PCIe in
   // pieces with the PageRank layout built behind them (Lib::stream_fill, graph.cu / pull.cu)
@@ -117,6 +119,7 @@ int spmv_oneshot(int64_t m, int64_t nnz, const OffT *Ap, const int32_t *Aj, cons
                  float *y, gdn_stats *st) {
   if (!Ap || !Aj || !Ax || !x || !y) { set_error("gdn_spmv_csr: null argument"); return GDN_ERR_ARG; }
   GDN_CHECK(ensure_init());
+  PoolScope arena;                 // declared before every buffer of the call: they are parked, not freed, on the way out
   const double t0 = now_ms();
   GraphGuard gg;
   GDN_CHECK(create<OffT>(m, nnz, nullptr, nullptr, Ap, Aj, &gg.g));

@@ -294,6 +294,49 @@ def test_resident_matches_oneshot_and_is_deterministic():
     dg.close()
 
 
+def test_oneshot_calls_reuse_the_device_arena():
+    """Repeated one-shot calls on the same graph take their device blocks back from the arena of csrc/pool.cu (no
+    cudaMalloc / cudaFree after the first call): the recycled, non-zeroed blocks must give bit-identical results."""
+    g = gb.Graph.generate("g", 18, 16)
+    m, rp, ci = g.m, g.out_rowptr(), g.out_colidx()
+    ref = None
+    for _ in range(3):
+        hs = np.full(m, np.float32(1.0) / np.float32(m), dtype=np.float32)
+        st = gb.PRSolver(g, hs, verbose=False)
+        if ref is None:
+            ref = (hs.copy(), st.iterations)
+            oscores, oit, _ = po.pr_pull(m, rp, ci, g.out_degrees())
+            assert st.iterations == oit
+            assert float(np.abs(hs.astype(np.float64) - oscores.astype(np.float64)).sum()) <= PR_L1_TOL
+        assert st.iterations == ref[1] and np.array_equal(hs, ref[0])
+    src = int(g.pick_sources(1)[0])
+    d0 = None
+    for _ in range(3):
+        dist = np.full(m, gb.MYINFINITY, dtype=np.int32)
+        gb.BFSSolver(g, src, dist, verbose=False)
+        d0 = dist.copy() if d0 is None else d0
+        assert np.array_equal(dist, d0)
+    odist, _, _ = po.bfs_do(m, rp, ci, rp, ci, src)
+    assert np.array_equal(d0, odist)
+    Ax, x = gb.fill_uniform(13, g.nnz), gb.fill_uniform(14, m)
+    y0 = None
+    for _ in range(3):
+        y = np.zeros(m, dtype=np.float32)
+        gb.SpmvSolver(g, Ax, x, y, verbose=False)
+        y0 = y.copy() if y0 is None else y0
+        assert np.array_equal(y, y0)
+    assert _rel(y0, po.spmv(m, rp, ci, Ax, x, np.zeros(m, np.float32))) <= SPMV_REL_TOL
+    # interleaved with a resident graph (allocated outside the arena) and a different one-shot size
+    dg = gb.DeviceGraph(g)
+    g2 = gb.Graph.generate("u", 15, 16)
+    h2 = np.full(g2.m, np.float32(1.0) / np.float32(g2.m), dtype=np.float32)
+    gb.PRSolver(g2, h2, verbose=False)
+    hs = np.full(m, np.float32(1.0) / np.float32(m), dtype=np.float32)
+    gb.PRSolver(g, hs, verbose=False)
+    assert np.array_equal(hs, ref[0])
+    dg.close()
+
+
 def test_resident_plain_layout_is_bit_identical_to_oneshot(monkeypatch):
     """GDN_PR_BANDS=0: the resident graph walks the same SELL array (sell_fill) as the one-shot call (sell_scatter)."""
     import torch
