@@ -84,3 +84,47 @@ def test_bfs_bad_source():
     csr, _ = load_case("4_sym")
     with pytest.raises(ValueError):
         po.bfs_do(csr["m"], csr["out_rowptr"], csr["out_colidx"], csr["in_rowptr"], csr["in_colidx"], 99)
+
+
+# ------------------------------------------------------------------ KATs recorded from the reference itself
+# (bfs_omp_beamer with its own commented printf lines re-enabled, source 0; pr_omp_base; the reference generator)
+_SCHEDULE_KATS = {
+    # kind: (m, nnz, max degree, [(direction, discovered, scout_count)], BFS iterations, PR iterations)
+    "g": (1048576, 31399374, 64637,
+          [(0, 1, 1315), (0, 1314, 2676163), (1, 339311, None), (1, 301458, None), (1, 3171, None), (0, 13, 13), (0, 0, 0)], 7, 8),
+    "u": (1048576, 33553952, 62,
+          [(0, 29, 910), (0, 880, 29325), (0, 28045, 923290), (0, 585818, 19099150), (1, 433803, None), (1, 0, None)], 6, 6),
+}
+
+
+@pytest.mark.parametrize("kind", ["g", "u"])
+def test_scale20_schedule_kats_of_the_reference(kind):
+    """Generator + oracle reproduce what the reference printed at scale 20: graph size, the direction-optimizing
+    schedule level by level (direction, next frontier, scout_count), `iterations`, and PageRank's iteration count."""
+    import gardenia_b200 as gb
+    m, nnz, maxdeg, sched, bfs_it, pr_it = _SCHEDULE_KATS[kind]
+    g = gb.Graph.generate(kind, 20, 16)
+    rp, ci = g.out_rowptr(), g.out_colidx()
+    assert (g.m, g.nnz, int(np.diff(rp).max())) == (m, nnz, maxdeg)
+    dist, it, steps = po.bfs_do(g.m, rp, ci, rp, ci, 0)
+    assert it == bfs_it and len(steps) == len(sched)
+    for s, (d, disc, scout) in zip(steps, sched):
+        assert (s["dir"], s["discovered"]) == (d, disc), (s, d, disc)
+        if scout is not None:
+            assert s["scout"] == scout
+    assert po.bfs_verify(g.m, rp, ci, 0, dist) == 0
+    _, it_pr, _ = po.pr_pull(g.m, rp, ci, g.out_degrees())
+    assert it_pr == pr_it
+
+
+def test_kron22_size_kat():
+    """Config C2 of BASELINE.json: `-g 22` has 4,194,302 vertices (m = max id + 1, include/builder.h:244-245), 128,311,436
+    directed entries and maximum degree 162,839; BFS from source 0 takes 7 levels, PageRank 7 iterations."""
+    import gardenia_b200 as gb
+    g = gb.Graph.generate("g", 22, 16)
+    rp, ci = g.out_rowptr(), g.out_colidx()
+    assert (g.m, g.nnz, int(np.diff(rp).max())) == (4194302, 128311436, 162839)
+    _, it, _ = po.bfs_do(g.m, rp, ci, rp, ci, 0)
+    assert it == 7
+    _, it_pr, _ = po.pr_pull(g.m, rp, ci, g.out_degrees())
+    assert it_pr == 7
