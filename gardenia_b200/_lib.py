@@ -40,7 +40,7 @@ class Stats(C.Structure):
     _fields_ = [("iterations", C.c_int32), ("n_steps", C.c_int32),
                 ("solve_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
                 ("kernel_launches", C.c_int64), ("kernel_ms", C.c_double), ("kernel_calls", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
-                ("edges_reached", C.c_int64), ("vertices_reached", C.c_int64),
+                ("edges_reached", C.c_int64), ("vertices_reached", C.c_int64), ("pr_layout", C.c_int64),
                 ("pr_err", C.c_double * GDN_MAX_PR_ITER),
                 ("steps", BfsStep * GDN_MAX_BFS_STEPS)]
 
@@ -72,6 +72,8 @@ SIGNATURES = {
     "gdn_init": (C.c_int, [C.c_int]),
     "gdn_finalize": (C.c_int, []),
     "gdn_device_count": (C.c_int, []),
+    "gdn_device_trim": (C.c_int, []),
+    "gdn_set_pr_exact_order": (C.c_int, [C.c_int]),
     "gdn_bfs": (C.c_int, [_i64, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _SP]),
     "gdn_bfs_i32": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _SP]),
     "gdn_pagerank_pull": (C.c_int, [_i64, _i64, _vp, _vp, _vp, _vp, _f32, _f64, C.c_int, _SP]),
@@ -84,6 +86,7 @@ SIGNATURES = {
     "gdn_graph_destroy": (C.c_int, [_vp]),
     "gdn_graph_info": (C.c_int, [_vp, C.POINTER(_i64 * 8)]),
     "gdn_graph_pull_info": (C.c_int, [_vp, C.POINTER(_i64 * 8)]),
+    "gdn_graph_prep_ms": (C.c_int, [_vp, C.POINTER(C.c_double * 4)]),
     "gdn_band_host_probe": (C.c_int, [C.c_int32, _i64, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, _vp, C.c_int32, _vp]),
     "gdn_band_map_probe": (C.c_int, [_i64, _i64, C.c_int32, C.c_int32, C.c_int32, _i64, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                      C.POINTER(_i64), C.POINTER(C.c_int32)]),

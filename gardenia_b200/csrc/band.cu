@@ -16,7 +16,8 @@
 //     pr_sell_pipe walks; its epilogue for these rows only deposits the main sum;
 //   * the band partials of a row meet in a 64-bit FIXED-POINT accumulator (integer atomics: order-free, exact, hence
 //     bit-reproducible from run to run); pr_band_finalize_fix adds main sum + band sum and runs the row epilogue
-//     (score, L1 delta, next contrib).  (GDN_PR_BAND_FIN=0: per-row slot lists summed in a fixed (band, segment) order.)
+//     (score, L1 delta, next contrib).  The scale 2^e of the accumulators follows sum |scores_0| of the solve (pull.cu
+//     fix_scale_for), so any caller-supplied start vector stays in range.
 //
 // The layout is built once per resident graph (untimed, like include/segmenting.h preprocessing of the reference):
 // two device passes over the existing SELL array (count, fill) around a host pass that sorts each band's rows.
@@ -30,6 +31,7 @@
 #include "pull.cuh"
 #include <omp.h>
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -40,7 +42,6 @@ constexpr int kBandSeg = 64;            // index groups (8 ids each) per lane an
 constexpr int kBandTab = kHotMax + 256; // table entries in shared memory: [band, kBandTab) is zero
 constexpr uint32_t kBandPadId = 0xC0C0; // padding id = a zero table entry; byte-uniform so cudaMemset can write it
 constexpr uint32_t kNone = 0xffffffffu;
-constexpr double kFixScale = 72057594037927936.0;          // 2^56: a row's sum is O(1), 2^63 / 2^56 = 128 of headroom
 static_assert(kBandPadId >= (uint32_t)kHotMax && kBandPadId < (uint32_t)kBandTab, "padding id must hit the zero tail");
 
 // Which band holds new id c.  The id space is [hot prefix of H ids | cold slice of rank 0 | ... | cold slice of rank
@@ -180,9 +181,9 @@ struct BandArgs {
   const int64_t *band_start;   // first new id of band b ...
   const int32_t *band_len;     // ... and how many ids it holds (<= kHotMax)
   const float *contrib_in;
-  float *bpartial;             // FIX = false: one partial per (item, lane)
-  const int32_t *irow;         // FIX = true: sorted row of (item, lane), -1 = no row ...
+  const int32_t *irow;         // sorted row of (item, lane), -1 = no row ...
   unsigned long long *acc_fix; // ... whose fixed-point accumulator takes the partial
+  double fix_scale;            // 2^e of the accumulators for this solve
   const int32_t *done;
 };
 
@@ -197,13 +198,9 @@ __device__ __forceinline__ uint4 ld_stream_u4(const uint4 *p, uint64_t pol) {
 // PD index groups (8 ids each) requested ahead per lane.  A warp owns a contiguous run of items = one contiguous
 // piece of the band's array: it streams through it without a bubble at item boundaries; the item lengths come 32 at a
 // time (lane i holds the length of item ibase + i) with the next batch requested one batch ahead.
-// THREADS = 1024: the kernel has the SM to itself.  THREADS = 256 (<= 64 registers): it shares the SM with
-// pr_sell_pipe_co (pull.cu) -- eight warps already saturate the shared-memory pipe, and the main sums of the
-// iteration, which wait on the L1TEX miss path instead, run beside them.
-template <int PD, int THREADS, bool FIX>
-__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 1)
+template <int PD>
+__global__ void __launch_bounds__(kSellThreads, 1)
 pr_band_kernel(BandArgs a) {
-  constexpr int kRuns = 32 / (THREADS / 32);             // warp runs of a job per warp
   extern __shared__ float tab[];
   if (*a.done) return;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -214,9 +211,9 @@ pr_band_kernel(BandArgs a) {
     __syncthreads();                                       // the previous band's readers are done
     const int64_t id0 = a.band_start[J.x];
     const int32_t len = a.band_len[J.x];
-    for (int i = threadIdx.x; i < kBandTab; i += THREADS) tab[i] = i < len ? a.contrib_in[id0 + i] : 0.f;
+    for (int i = threadIdx.x; i < kBandTab; i += kSellThreads) tab[i] = i < len ? a.contrib_in[id0 + i] : 0.f;
     __syncthreads();
-    const int32_t i0 = a.wrun[J.y + w * kRuns], i1 = a.wrun[J.y + (w + 1) * kRuns];
+    const int32_t i0 = a.wrun[J.y + w], i1 = a.wrun[J.y + w + 1];
     if (i0 >= i1) continue;
     const uint32_t u0 = a.item_ptr[i0], u1 = a.item_ptr[i1];
     const uint4 *p = a.bsell + u0 + lane;
@@ -228,13 +225,10 @@ pr_band_kernel(BandArgs a) {
     int32_t ibase = i0, item = i0;
     uint32_t lens = len_batch(ibase), lens_next = len_batch(ibase + 32);
     uint32_t left = __shfl_sync(kFull, lens, 0);
-    // FIX: the rows of the next two items are requested ahead (an item is ~4 index groups long)
-    int32_t jrow = -1, jrow1 = -1, jrow2 = -1;
-    if (FIX) {
-      jrow = a.irow[(size_t)i0 * 32 + lane];
-      if (i0 + 1 < i1) jrow1 = a.irow[(size_t)(i0 + 1) * 32 + lane];
-      if (i0 + 2 < i1) jrow2 = a.irow[(size_t)(i0 + 2) * 32 + lane];
-    }
+    // the rows of the next two items are requested ahead (an item is ~4 index groups long)
+    int32_t jrow = a.irow[(size_t)i0 * 32 + lane], jrow1 = -1, jrow2 = -1;
+    if (i0 + 1 < i1) jrow1 = a.irow[(size_t)(i0 + 1) * 32 + lane];
+    if (i0 + 2 < i1) jrow2 = a.irow[(size_t)(i0 + 2) * 32 + lane];
     uint4 q[PD];
 #pragma unroll
     for (int d = 0; d < PD; d++) q[d] = (uint32_t)d < nrows ? ld_stream_u4(p + 32 * d, pol) : padq;
@@ -250,13 +244,9 @@ pr_band_kernel(BandArgs a) {
           acc = __fadd_rn(acc, v0); acc = __fadd_rn(acc, v1); acc = __fadd_rn(acc, v2); acc = __fadd_rn(acc, v3);
           acc = __fadd_rn(acc, v4); acc = __fadd_rn(acc, v5); acc = __fadd_rn(acc, v6); acc = __fadd_rn(acc, v7);
           if (--left == 0) {
-            if (FIX) {
-              if (jrow >= 0) atomicAdd(a.acc_fix + jrow, (unsigned long long)__double2ll_rn((double)acc * kFixScale));
-              jrow = jrow1; jrow1 = jrow2;
-              jrow2 = item + 3 < i1 ? a.irow[(size_t)(item + 3) * 32 + lane] : -1;
-            } else {
-              __stcs(a.bpartial + (size_t)item * 32 + lane, acc);
-            }
+            if (jrow >= 0) atomicAdd(a.acc_fix + jrow, (unsigned long long)__double2ll_rn((double)acc * a.fix_scale));
+            jrow = jrow1; jrow1 = jrow2;
+            jrow2 = item + 3 < i1 ? a.irow[(size_t)(item + 3) * 32 + lane] : -1;
             acc = 0.f;
             item++;
             if (item - ibase == 32) { ibase += 32; lens = lens_next; lens_next = len_batch(ibase + 32); }
@@ -317,7 +307,7 @@ pr_seg_kernel(BandArgs a, int32_t job0) {
       if (idx > 0 && idx <= nrows) {                       // add group idx - 1
         acc = __fadd_rn(acc, v0); acc = __fadd_rn(acc, v1); acc = __fadd_rn(acc, v2); acc = __fadd_rn(acc, v3);
         if (--left == 0) {
-          if (jrow >= 0) atomicAdd(a.acc_fix + jrow, (unsigned long long)__double2ll_rn((double)acc * kFixScale));
+          if (jrow >= 0) atomicAdd(a.acc_fix + jrow, (unsigned long long)__double2ll_rn((double)acc * a.fix_scale));
           jrow = jrow1; jrow1 = jrow2;
           jrow2 = item + 3 < i1 ? a.irow[(size_t)(item + 3) * 32 + lane] : -1;
           acc = 0.f;
@@ -332,38 +322,12 @@ pr_seg_kernel(BandArgs a, int32_t job0) {
 }
 
 // ------------------------------------------------------------------ the iteration: main sum + band partials -> epilogue
+// pr_band_kernel has already added every band partial of row j into acc_fix[j] as a fixed-point integer (integer
+// addition commutes: the order of the atomics does not matter, the sum is exact and bit-reproducible), so this is one
+// coalesced pass: main sum + band sum, row epilogue, accumulator back to zero.  (A per-row gather of per-item partial
+// slots, and cooperative warp / CTA versions of it, were measured slower: profiles/r1_pr_band_ab.txt.)
 __global__ void __launch_bounds__(256, 4)
-pr_band_finalize(SellArgs a, const uint32_t *__restrict__ rslot_ptr, const uint32_t *__restrict__ rslot,
-                 const float *__restrict__ bpartial) {
-  if (*a.done) return;
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  double err = 0.0;
-  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < a.n_band_rows; j += (int64_t)gridDim.x * blockDim.x) {
-    float acc = __ldcs(a.acc_main + j);
-    uint32_t k = rslot_ptr[j];
-    const uint32_t k1 = rslot_ptr[j + 1];
-    for (; k + 4 <= k1; k += 4) {                          // four gathers in flight, added in slot order
-      float t[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) t[u] = __ldcs(bpartial + rslot[k + u]);
-#pragma unroll
-      for (int u = 0; u < 4; u++) acc = __fadd_rn(acc, t[u]);
-    }
-    for (; k < k1; k++) acc = __fadd_rn(acc, __ldcs(bpartial + rslot[k]));
-    if (j < a.n_nz_rows) pr_epilogue_core(a, j, acc, err);
-  }
-  err = warp_sum(err);
-  if (lane == 0) a.err_partial[a.err_slot0 + warp] = err;
-}
-
-// Default finalize (GDN_PR_BAND_FIN=0 selects the slot version above).  With FIX = true pr_band_kernel has already added
-// every band partial of row j into acc_fix[j] as a 2^-56 fixed-point integer (integer addition commutes: the order of
-// the atomics does not matter, the sum is exact and bit-reproducible), so this is one coalesced pass: main sum + band sum,
-// row epilogue, accumulator back to zero.  (Cooperative warp / CTA versions of the slot gather were measured slower than
-// one thread per row: profiles/r1_pr_band_ab.txt.)
-__global__ void __launch_bounds__(256, 4)
-pr_band_finalize_fix(SellArgs a, long long *__restrict__ acc_fix) {
+pr_band_finalize_fix(SellArgs a, long long *__restrict__ acc_fix, double inv_scale) {
   if (*a.done) return;
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -371,7 +335,7 @@ pr_band_finalize_fix(SellArgs a, long long *__restrict__ acc_fix) {
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < a.n_band_rows; j += (int64_t)gridDim.x * blockDim.x) {
     const long long f = acc_fix[j];
     acc_fix[j] = 0;
-    const float acc = (float)((double)__ldcs(a.acc_main + j) + (double)f * (1.0 / kFixScale));
+    const float acc = (float)((double)__ldcs(a.acc_main + j) + (double)f * inv_scale);
     pr_epilogue_core(a, j, acc, err);
   }
   err = warp_sum(err);
@@ -415,16 +379,16 @@ static int up(gdn_graph *g, T **dptr, const T *h, size_t n) {
 
 // ------------------------------------------------------------------ host: tables of the band layout (device-free)
 // Everything the host derives from the count matrix: each band's row order and ranks, band slices, items, the
-// (item, lane) -> row map, slot lists, jobs and warp runs, and the compacted main array's slice pointers and work tables.
+// (item, lane) -> row map, jobs and warp runs, and the compacted main array's slice pointers and work tables.
 // No CUDA call in here: tests/test_host.py drives it through gdn_band_host_probe with synthetic counts.
 struct BandHost {
   bool ok = false;
-  std::vector<uint32_t> rank, item_ptr, bslice_ptr, bslice_item, rslot_ptr, rslot, sp2;
+  std::vector<uint32_t> rank, item_ptr, bslice_ptr, bslice_item, sp2;
   std::vector<int32_t> bslice_first, item_band, irow, job_first, wrun, chunk, hslice, hfirst;
   std::vector<uint64_t> band_item0;
   std::vector<int4> job;
   std::vector<int2> hseg;
-  uint64_t units = 0, moved = 0, pairs = 0, n_rslot = 0, tot2 = 0;
+  uint64_t units = 0, moved = 0, pairs = 0, tot2 = 0;
   int32_t n_items = 0;
 };
 
@@ -524,35 +488,6 @@ static void band_host_tables(int B, int64_t n_rows, int32_t nb, uint32_t W, bool
         for (int l = 0; l < 32; l++) irow[it * 32 + l] = sl * 32 + l < n ? (int32_t)q.order[sl * 32 + l] : -1;
     }
   }
-  // partial slots of every row, in (band, segment) order (slot finalize only; the segmented mode always uses the
-  // fixed-point accumulators)
-  std::vector<uint32_t> rslot_ptr, rslot;
-  uint64_t n_rslot = 0;
-  if (!seg) {
-    rslot_ptr.assign((size_t)n_rows + 1, 0);
-#pragma omp parallel for
-    for (int64_t j = 0; j < n_rows; j++) {
-      uint32_t n = 0;
-      for (int b = 0; b < B; b++) { const uint32_t c = cnt[(size_t)b * n_rows + j]; if (c) n += (c + W * kBandSeg - 1) / (W * kBandSeg); }
-      rslot_ptr[j + 1] = n;
-    }
-    for (int64_t j = 0; j < n_rows; j++) { const uint32_t n = rslot_ptr[j + 1]; rslot_ptr[j] = (uint32_t)n_rslot; n_rslot += n; }
-    rslot_ptr[n_rows] = (uint32_t)n_rslot;
-    if (n_rslot >= 0xfffffff0ull) return;
-    rslot.resize(std::max<uint64_t>(n_rslot, 1));
-#pragma omp parallel for
-    for (int64_t j = 0; j < n_rows; j++) {
-      uint32_t k = rslot_ptr[j];
-      for (int b = 0; b < B; b++) {
-        const uint32_t c = cnt[(size_t)b * n_rows + j];
-        if (!c) continue;
-        const uint32_t r = rank[(size_t)b * n_rows + j];
-        const uint32_t it0 = bslice_item[bslice_first[b] + (r >> 5)];
-        for (uint32_t t = 0; t < (c + W * kBandSeg - 1) / (W * kBandSeg); t++) rslot[k++] = (it0 + t) * 32 + (r & 31);
-      }
-    }
-  }
-
   // jobs: equal-cost contiguous runs of items per CTA, cut at band boundaries, each cut into 32 warp runs
   std::vector<uint64_t> pc((size_t)n_items + 1, 0);
   for (int32_t i = 0; i < n_items; i++) pc[i + 1] = pc[i] + ((item_ptr[i + 1] - item_ptr[i]) >> 5) + 2;
@@ -607,11 +542,11 @@ static void band_host_tables(int B, int64_t n_rows, int32_t nb, uint32_t W, bool
   std::vector<int2> hseg;
   make_work_tables(sp2, n_slices, chunk, hslice, hfirst, hseg);
   H.rank = std::move(rank); H.item_ptr = std::move(item_ptr); H.bslice_ptr = std::move(bslice_ptr); H.bslice_item = std::move(bslice_item);
-  H.rslot_ptr = std::move(rslot_ptr); H.rslot = std::move(rslot); H.sp2 = std::move(sp2);
+  H.sp2 = std::move(sp2);
   H.bslice_first = std::move(bslice_first); H.item_band = std::move(item_band); H.irow = std::move(irow);
   H.job_first = std::move(job_first); H.wrun = std::move(wrun); H.chunk = std::move(chunk); H.hslice = std::move(hslice); H.hfirst = std::move(hfirst);
   H.band_item0 = std::move(band_item0); H.job = std::move(job); H.hseg = std::move(hseg);
-  H.units = units; H.moved = moved; H.pairs = pairs; H.n_rslot = n_rslot; H.tot2 = tot2; H.n_items = n_items;
+  H.units = units; H.moved = moved; H.pairs = pairs; H.tot2 = tot2; H.n_items = n_items;
   H.ok = true;
 }
 
@@ -655,22 +590,6 @@ static int band_host_check(int B, int64_t n_rows, int32_t nb, uint32_t W, bool s
     }
   }
   if (moved != H.moved || pairs != H.pairs) return -11;
-  // 2. slot lists (slot finalize): row j owns exactly the (item, its lane) slots of the segments that hold its ids
-  if (!seg) {
-    if ((int64_t)H.rslot_ptr.size() != n_rows + 1 || H.rslot_ptr[n_rows] != H.n_rslot) return -12;
-    for (int64_t j = 0; j < n_rows; j++) {
-      uint32_t k = H.rslot_ptr[j];
-      for (int b = 0; b < B; b++) {
-        const uint32_t c = cnt[(size_t)b * n_rows + j];
-        for (uint32_t t = 0; t < (c + W * kBandSeg - 1) / (W * kBandSeg); t++, k++) {
-          if (k >= H.rslot_ptr[j + 1]) return -13;
-          const uint32_t slot = H.rslot[k];
-          if (H.irow[slot] != (int32_t)j || H.item_band[slot / 32] != b) return -14;
-        }
-      }
-      if (k != H.rslot_ptr[j + 1]) return -15;
-    }
-  }
   // 3. jobs: every item belongs to exactly one warp run of one job; a job stays inside one band; runs are ordered
   std::vector<uint8_t> cover((size_t)n_items, 0);
   const size_t n_jobs = H.job.size();
@@ -712,8 +631,8 @@ static int band_host_check(int B, int64_t n_rows, int32_t nb, uint32_t W, bool s
 }
 
 void band_free(BandLayout &b) {
-  cudaFree(b.bsell); cudaFree(b.band_start); cudaFree(b.band_len); cudaFree(b.item_ptr); cudaFree(b.job); cudaFree(b.job_first); cudaFree(b.wrun); cudaFree(b.bpartial); cudaFree(b.irow); cudaFree(b.acc_fix);
-  cudaFree(b.rslot_ptr); cudaFree(b.rslot); cudaFree(b.acc_main); cudaFree(b.sell); cudaFree(b.slice_ptr);
+  cudaFree(b.bsell); cudaFree(b.band_start); cudaFree(b.band_len); cudaFree(b.item_ptr); cudaFree(b.job); cudaFree(b.job_first); cudaFree(b.wrun); cudaFree(b.irow); cudaFree(b.acc_fix);
+  cudaFree(b.acc_main); cudaFree(b.sell); cudaFree(b.slice_ptr);
   cudaFree(b.chunk_slice); cudaFree(b.heavy_slice); cudaFree(b.heavy_first); cudaFree(b.heavy_seg); cudaFree(b.partial);
   b = BandLayout();
 }
@@ -724,12 +643,20 @@ static int env_int(const char *name, int dflt) {
 }
 
 // Build the banded layout from the (already built) SELL array.  Leaves b.built = false -- and the plain layout in
-// use -- when the graph is too small or too flat for any (row, band) pair to qualify.
-int band_build(gdn_graph *g) {
+// use -- when the graph is too small or too flat for any (row, band) pair to qualify, and ALSO when the build itself
+// fails (out of device / host memory at the scales this layout targets): it is an optimisation, so the temporaries are
+// released, the CUDA error is cleared and the solve goes on with the plain layout.
+namespace {
+struct Tmp {                 // device temporaries of the build: freed on every way out
+  void *p = nullptr;
+  ~Tmp() { if (p) cudaFree(p); }
+  template <typename T> T *as() { return (T *)p; }
+};
+}  // namespace
+
+static int band_build_body(gdn_graph *g) {
   PullLayout &L = g->pull;
   BandLayout &bd = L.band;
-  if (bd.tried) return GDN_OK;
-  bd.tried = true;
   const int B_want = env_int("GDN_PR_BANDS", 64);
   if (B_want <= 0 || !L.prepared || !L.sell || L.n_slices < 2 || L.h_slice_ptr.empty()) return GDN_OK;
   const std::vector<uint32_t> &sp = L.h_slice_ptr;
@@ -761,9 +688,10 @@ int band_build(gdn_graph *g) {
   trace("band_build: begin");
 
   // pass 1 on the device
-  uint32_t *d_cnt = nullptr, *d_remw = nullptr;
-  GDN_CUDA(cudaMalloc((void **)&d_cnt, sizeof(uint32_t) * (size_t)B * n_rows));
-  GDN_CUDA(cudaMalloc((void **)&d_remw, sizeof(uint32_t) * (size_t)nb));
+  Tmp t_cnt, t_remw, t_bslice_ptr, t_bslice_first;
+  GDN_CUDA(cudaMalloc(&t_cnt.p, sizeof(uint32_t) * (size_t)B * n_rows));
+  GDN_CUDA(cudaMalloc(&t_remw.p, sizeof(uint32_t) * (size_t)nb));
+  uint32_t *d_cnt = t_cnt.as<uint32_t>(), *d_remw = t_remw.as<uint32_t>();
   const size_t smem1 = sizeof(uint32_t) * 4 * (size_t)B * 32, smem2 = 2 * smem1;
   GDN_CUDA(cudaFuncSetAttribute(band_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
   GDN_CUDA(cudaFuncSetAttribute(band_fill<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
@@ -771,7 +699,9 @@ int band_build(gdn_graph *g) {
   const int grid = (int)std::min<int64_t>((nb + 3) / 4, (int64_t)sm * 16);
   band_count<<<grid, 128, smem1, st>>>(L.sell, L.slice_ptr, nb, mp, d_cnt, n_rows);
   band_select<<<(int)std::min<int64_t>((n_rows + 255) / 256, (int64_t)sm * 8), 256, 0, st>>>(d_cnt, B, n_rows, (uint32_t)cmin, L.sdeg, d_remw);
-  std::vector<uint32_t> cnt((size_t)B * n_rows), remw((size_t)nb);
+  std::vector<uint32_t> cnt, remw;
+  try { cnt.resize((size_t)B * n_rows); remw.resize((size_t)nb); }
+  catch (const std::bad_alloc &) { set_error("band layout: out of host memory"); return GDN_ERR_NOMEM; }
   GDN_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, sizeof(uint32_t) * cnt.size(), cudaMemcpyDeviceToHost, st));
   GDN_CUDA(cudaMemcpyAsync(remw.data(), d_remw, sizeof(uint32_t) * remw.size(), cudaMemcpyDeviceToHost, st));
   GDN_CUDA(cudaStreamSynchronize(st));
@@ -781,31 +711,30 @@ int band_build(gdn_graph *g) {
   // host: every band's rows sorted by their count in it; slices, items, ranks, jobs, main array tables
   const int n_cta = sm;
   BandHost H;
-  band_host_tables(B, n_rows, nb, W, seg, n_cta, cnt, remw, sp, L.n_slices, H);
-  if (!H.ok) { cudaFree(d_cnt); cudaFree(d_remw); return GDN_OK; }
+  try { band_host_tables(B, n_rows, nb, W, seg, n_cta, cnt, remw, sp, L.n_slices, H); }
+  catch (const std::bad_alloc &) { set_error("band layout: out of host memory"); return GDN_ERR_NOMEM; }
+  if (!H.ok) return GDN_OK;
   if (env_int("GDN_BAND_CHECK", 0)) {              // the same invariants the CPU test checks, on the real counts
     const int bad = band_host_check(B, n_rows, nb, W, seg, n_cta, cnt, remw, sp, L.n_slices, H);
-    if (bad) { cudaFree(d_cnt); cudaFree(d_remw); set_error("band layout: host table invariant %d broken", bad); return GDN_ERR_GRAPH; }
+    if (bad) { set_error("band layout: host table invariant %d broken", bad); return GDN_ERR_GRAPH; }
   }
   trace("band_build: host tables");
-  auto &rank = H.rank; auto &item_ptr = H.item_ptr; auto &bslice_ptr = H.bslice_ptr; auto &rslot_ptr = H.rslot_ptr; auto &rslot = H.rslot;
+  auto &rank = H.rank; auto &item_ptr = H.item_ptr; auto &bslice_ptr = H.bslice_ptr;
   auto &sp2 = H.sp2; auto &bslice_first = H.bslice_first; auto &irow = H.irow; auto &job_first = H.job_first; auto &wrun = H.wrun;
   auto &chunk = H.chunk; auto &hslice = H.hslice; auto &hfirst = H.hfirst; auto &job = H.job; auto &hseg = H.hseg;
-  const uint64_t units = H.units, moved = H.moved, pairs = H.pairs, n_rslot = H.n_rslot, tot2 = H.tot2;
+  const uint64_t units = H.units, moved = H.moved, pairs = H.pairs, tot2 = H.tot2;
   const int32_t n_items = H.n_items;
 
   bd.seg = seg;
   bd.B = B; bd.band = band; bd.cmin = cmin; bd.dmin = dmin; bd.n_rows = n_rows;
-  bd.n_units = units; bd.n_items = n_items; bd.n_jobs = (int32_t)job.size(); bd.n_cta = n_cta; bd.n_rslot = n_rslot;
+  bd.n_units = units; bd.n_items = n_items; bd.n_jobs = (int32_t)job.size(); bd.n_cta = n_cta;
   bd.n_groups = tot2; bd.n_chunks = (int32_t)chunk.size() - 1;
   bd.n_heavy_slices = (int32_t)hslice.size(); bd.n_heavy_segs = (int32_t)hseg.size();
   bd.moved = moved; bd.pairs = pairs;
   uint32_t *d_rank = d_cnt;                         // the counts are not needed on the device any more
-  uint32_t *d_bslice_ptr = nullptr;
-  int32_t *d_bslice_first = nullptr;
   GDN_CUDA(cudaMemcpyAsync(d_rank, rank.data(), sizeof(uint32_t) * rank.size(), cudaMemcpyHostToDevice, st));
-  GDN_CHECK(up(g, &d_bslice_ptr, bslice_ptr.data(), bslice_ptr.size()));
-  GDN_CHECK(up(g, &d_bslice_first, bslice_first.data(), bslice_first.size()));
+  GDN_CHECK(up(g, (uint32_t **)&t_bslice_ptr.p, bslice_ptr.data(), bslice_ptr.size()));
+  GDN_CHECK(up(g, (int32_t **)&t_bslice_first.p, bslice_first.data(), bslice_first.size()));
   std::vector<int64_t> band_start((size_t)B);
   std::vector<int32_t> band_len((size_t)B);
   for (int b = 0; b < B; b++) band_range(mp, b, band_start[b], band_len[b]);
@@ -818,10 +747,6 @@ int band_build(gdn_graph *g) {
   GDN_CHECK(up(g, &bd.irow, irow.data(), irow.size()));
   GDN_CUDA(cudaMalloc((void **)&bd.acc_fix, sizeof(long long) * (size_t)n_rows));
   GDN_CUDA(cudaMemsetAsync(bd.acc_fix, 0, sizeof(long long) * (size_t)n_rows, st));
-  if (!seg) {
-    GDN_CHECK(up(g, &bd.rslot_ptr, rslot_ptr.data(), rslot_ptr.size()));
-    GDN_CHECK(up(g, &bd.rslot, rslot.data(), (size_t)n_rslot));
-  }
   GDN_CHECK(up(g, &bd.slice_ptr, sp2.data(), sp2.size()));
   GDN_CHECK(up(g, &bd.chunk_slice, chunk.data(), chunk.size()));
   if (bd.n_heavy_slices) {
@@ -832,31 +757,22 @@ int band_build(gdn_graph *g) {
   }
   GDN_CUDA(cudaMalloc((void **)&bd.bsell, sizeof(uint4) * units + 256));
   GDN_CUDA(cudaMalloc((void **)&bd.sell, sizeof(int4) * std::max<uint64_t>(tot2, 1) + 256));
-  if (!seg) GDN_CUDA(cudaMalloc((void **)&bd.bpartial, sizeof(float) * 32 * (size_t)n_items));
   GDN_CUDA(cudaMalloc((void **)&bd.acc_main, sizeof(float) * (size_t)n_rows));
-  g->device_bytes += sizeof(uint4) * units + sizeof(int4) * tot2 + sizeof(float) * (32 * (size_t)n_items + n_rows);
   GDN_CUDA(cudaMemsetAsync(bd.bsell, seg ? 0xff : (int)(kBandPadId & 0xff), sizeof(uint4) * units + 256, st));
   GDN_CUDA(cudaMemsetAsync(bd.sell, 0xff, sizeof(int4) * (size_t)sp2[nb] + (tot2 == sp2[nb] ? 256 : 0), st));
   GDN_CUDA(cudaMemsetAsync(bd.acc_main, 0, sizeof(float) * (size_t)n_rows, st));
   if (tot2 > sp2[nb])
     GDN_CUDA(cudaMemcpyAsync(bd.sell + sp2[nb], L.sell + sp[nb], sizeof(int4) * (size_t)(tot2 - sp2[nb]) + 256, cudaMemcpyDeviceToDevice, st));
   if (seg)
-    band_fill<true><<<grid, 128, smem2, st>>>(L.sell, L.slice_ptr, nb, mp, d_rank, n_rows, d_bslice_ptr, d_bslice_first,
+    band_fill<true><<<grid, 128, smem2, st>>>(L.sell, L.slice_ptr, nb, mp, d_rank, n_rows, t_bslice_ptr.as<uint32_t>(), t_bslice_first.as<int32_t>(),
                                               (uint16_t *)bd.bsell, bd.sell, bd.slice_ptr);
   else
-    band_fill<false><<<grid, 128, smem2, st>>>(L.sell, L.slice_ptr, nb, mp, d_rank, n_rows, d_bslice_ptr, d_bslice_first,
+    band_fill<false><<<grid, 128, smem2, st>>>(L.sell, L.slice_ptr, nb, mp, d_rank, n_rows, t_bslice_ptr.as<uint32_t>(), t_bslice_first.as<int32_t>(),
                                                (uint16_t *)bd.bsell, bd.sell, bd.slice_ptr);
   GDN_CUDA(cudaStreamSynchronize(st));
   GDN_CUDA(cudaGetLastError());
-  cudaFree(d_cnt); cudaFree(d_remw); cudaFree(d_bslice_ptr); cudaFree(d_bslice_first);
-  const int tab_bytes = (int)(sizeof(float) * kBandTab);
-  GDN_CUDA(cudaFuncSetAttribute(pr_band_kernel<4, 1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tab_bytes));
-  GDN_CUDA(cudaFuncSetAttribute(pr_band_kernel<4, 1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tab_bytes));
-  GDN_CUDA(cudaFuncSetAttribute(pr_band_kernel<4, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tab_bytes));
-  GDN_CUDA(cudaFuncSetAttribute(pr_band_kernel<4, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tab_bytes));
-  // co-resident pair: the SM must be configured for the full 228 KB of shared memory before either CTA arrives
-  GDN_CUDA(cudaFuncSetAttribute(pr_band_kernel<4, 256, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  GDN_CUDA(cudaFuncSetAttribute(pr_band_kernel<4, 256, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  GDN_CUDA(cudaFuncSetAttribute(pr_band_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * kBandTab)));
+  g->device_bytes += sizeof(uint4) * units + sizeof(int4) * tot2 + (sizeof(float) + sizeof(long long)) * (size_t)n_rows;
   bd.built = true;
   if (getenv("GDN_TRACE"))
     fprintf(stderr, "[gdn] %s layout: B=%d band=%d cmin=%d rows=%lld  moved=%llu ids (%.1f %% of nnz) in %llu pairs, %d items, "
@@ -865,6 +781,22 @@ int band_build(gdn_graph *g) {
             (unsigned long long)pairs, n_items, (unsigned long long)(units * W), (double)(units * W) / (double)std::max<uint64_t>(moved, 1),
             bd.n_jobs, (unsigned long long)L.n_groups, (unsigned long long)tot2);
   trace("band_build: done");
+  return GDN_OK;
+}
+
+int band_build(gdn_graph *g) {
+  BandLayout &bd = g->pull.band;
+  if (bd.tried) return GDN_OK;
+  const auto t0 = std::chrono::steady_clock::now();
+  const int rc = band_build_body(g);
+  if (rc != GDN_OK || !bd.built) {
+    // not built (nothing qualifies) or failed half-way: drop whatever was allocated and stay on the plain layout
+    band_free(bd);
+    cudaGetLastError();
+    if (rc != GDN_OK && getenv("GDN_TRACE")) fprintf(stderr, "[gdn] band layout not built (%s): plain layout in use\n", gdn_last_error());
+  }
+  bd.tried = true;
+  bd.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return GDN_OK;
 }
 
@@ -909,22 +841,16 @@ extern "C" int gdn_band_host_probe(int32_t B, int64_t n_rows, int32_t ids_per_un
 
 namespace gdn {
 
-int band_launch(gdn_graph *g, const SellArgs &sa, cudaStream_t s, bool co_resident) {
+int band_launch(gdn_graph *g, const SellArgs &sa, double fix_scale, cudaStream_t s) {
   const BandLayout &bd = g->pull.band;
   BandArgs a;
   a.bsell = bd.bsell; a.item_ptr = bd.item_ptr; a.job = bd.job; a.job_first = bd.job_first; a.wrun = bd.wrun;
-  a.band_start = bd.band_start; a.band_len = bd.band_len; a.contrib_in = sa.contrib_in; a.bpartial = bd.bpartial; a.done = sa.done;
-  const size_t smem = sizeof(float) * kBandTab;
-  a.irow = bd.irow; a.acc_fix = (unsigned long long *)bd.acc_fix;
-  const bool fix = bd.seg || env_int("GDN_PR_BAND_FIN", 2) == 2;
+  a.band_start = bd.band_start; a.band_len = bd.band_len; a.contrib_in = sa.contrib_in; a.done = sa.done;
+  a.irow = bd.irow; a.acc_fix = (unsigned long long *)bd.acc_fix; a.fix_scale = fix_scale;
   if (bd.seg) {
     for (int b = 0; b < bd.B; b++) pr_seg_kernel<4><<<bd.n_cta, kSellThreads, 0, s>>>(a, b * bd.n_cta);
-  } else if (co_resident) {
-    if (fix) pr_band_kernel<4, 256, true><<<bd.n_cta, 256, smem, s>>>(a);
-    else pr_band_kernel<4, 256, false><<<bd.n_cta, 256, smem, s>>>(a);
   } else {
-    if (fix) pr_band_kernel<4, 1024, true><<<bd.n_cta, kSellThreads, smem, s>>>(a);
-    else pr_band_kernel<4, 1024, false><<<bd.n_cta, kSellThreads, smem, s>>>(a);
+    pr_band_kernel<4><<<bd.n_cta, kSellThreads, sizeof(float) * kBandTab, s>>>(a);
   }
   return GDN_OK;
 }
@@ -935,10 +861,8 @@ int band_finalize_grid(const gdn_graph *g) {
   return (int)std::max<int64_t>(1, std::min<int64_t>((g->pull.band.n_rows + 255) / 256, (int64_t)lib().sm_count * 8));
 }
 
-int band_finalize_launch(gdn_graph *g, const SellArgs &a, int grid, cudaStream_t s) {
-  const BandLayout &bd = g->pull.band;
-  if (bd.seg || env_int("GDN_PR_BAND_FIN", 2) == 2) pr_band_finalize_fix<<<grid, 256, 0, s>>>(a, bd.acc_fix);
-  else pr_band_finalize<<<grid, 256, 0, s>>>(a, bd.rslot_ptr, bd.rslot, bd.bpartial);
+int band_finalize_launch(gdn_graph *g, const SellArgs &a, double fix_scale, int grid, cudaStream_t s) {
+  pr_band_finalize_fix<<<grid, 256, 0, s>>>(a, g->pull.band.acc_fix, 1.0 / fix_scale);
   return GDN_OK;
 }
 

@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include <cstdlib>
 #include <algorithm>
+#include <chrono>
 
 namespace gdn {
 
@@ -646,11 +647,13 @@ static int bfs_prepare(gdn_graph *g) {
   if (g->col_bu || !g->deg_class || g->one_shot || getenv("GDN_BFS_NO_REORDER")) return GDN_OK;
   const DevCsr &ci = g->symmetric ? g->out : g->in;
   if (ci.nnz == 0) return GDN_OK;
+  const auto t0 = std::chrono::steady_clock::now();
   GDN_CUDA(cudaMalloc((void **)&g->col_bu, sizeof(int32_t) * ci.nnz + 256));
   g->device_bytes += sizeof(int32_t) * ci.nnz;
   hubs_first<OffT><<<lib().sm_count * 8, 256, 0, lib().stream>>>((const OffT *)ci.rowptr, ci.col, g->deg_class, g->col_bu, ci.rows);
   GDN_CUDA(cudaStreamSynchronize(lib().stream));
   GDN_CUDA(cudaGetLastError());
+  g->prep_ms[3] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return GDN_OK;
 }
 

@@ -10,10 +10,11 @@
 // loads (and the host-only entry points work) on machines without NCCL/GPUs.
 // When the process already has torch's bundled libnccl.so.2 mapped, dlopen
 // returns that copy.
-#include "common.cuh"
+#include "pull.cuh"
 #include <dlfcn.h>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 namespace gdn {
 
@@ -160,6 +161,213 @@ int allreduce_i64(long long *d_p, int cnt) {
   return GDN_OK;
 }
 
+
+// ------------------------------------------------------------------ peer-mapped exchange (PageRank)
+// The contrib vector of a row partition is exchanged WITHOUT a collective: every GPU maps the vectors of the others
+// (CUDA IPC between the one-process-per-GPU ranks) and the row epilogues store each new value into all of them over
+// NVLink while the iteration is still running (pull.cuh contrib_store).  What is left between two iterations is a barrier
+// over the box and the sum of P deltas: one single-block kernel per GPU on device-side flags in a peer-mapped mailbox.
+//   mailbox (per GPU):  flags[8]   flags[q] = last epoch GPU q has arrived at (written by q)
+//                       vals[2][8] vals[e & 1][q] = the value GPU q published in epoch e
+// Epochs only grow (one per pull_peer_sync call, the same sequence on every rank), so nothing is ever reset.
+struct PeerBox {
+  bool ready = false, failed = false;
+  unsigned long long *mail = nullptr;          // this GPU's mailbox (device memory, exported)
+  unsigned long long *peer_mail[8] = {};       // every GPU's mailbox as mapped here ([rank] = mail)
+  unsigned long long epoch = 0;
+  int *timeout_flag = nullptr;                 // device: a barrier gave up waiting (a peer died)
+};
+static PeerBox &box() { static PeerBox b; return b; }
+constexpr size_t kMailBytes = 2u << 20;        // a whole 2 MB block: small cudaMalloc blocks are sub-allocated and not exportable alone
+
+struct PeerMailArgs {
+  unsigned long long *mail[8];
+};
+
+// Exchange one device pointer per rank: mine[rank] = local; the others are the peers' allocations mapped into this
+// process.  The 64-byte IPC handles travel through one ncclAllGather.
+static int ipc_exchange(void *local, void **mapped) {
+  Nccl &n = nccl();
+  cudaStream_t st = lib().stream;
+  cudaIpcMemHandle_t mine;
+  GDN_CUDA(cudaIpcGetMemHandle(&mine, local));
+  unsigned char *d_h = nullptr;
+  GDN_CUDA(cudaMalloc((void **)&d_h, sizeof(cudaIpcMemHandle_t) * n.size));
+  GDN_CUDA(cudaMemcpyAsync(d_h + sizeof(cudaIpcMemHandle_t) * n.rank, &mine, sizeof(mine), cudaMemcpyHostToDevice, st));
+  GDN_NCCL(n.AllGather(d_h + sizeof(cudaIpcMemHandle_t) * n.rank, d_h, sizeof(cudaIpcMemHandle_t), ncclUint8, n.comm, st));
+  std::vector<cudaIpcMemHandle_t> all((size_t)n.size);
+  GDN_CUDA(cudaMemcpyAsync(all.data(), d_h, sizeof(cudaIpcMemHandle_t) * n.size, cudaMemcpyDeviceToHost, st));
+  GDN_CUDA(cudaStreamSynchronize(st));
+  cudaFree(d_h);
+  for (int p = 0; p < n.size; p++) {
+    if (p == n.rank) { mapped[p] = local; continue; }
+    GDN_CUDA(cudaIpcOpenMemHandle(&mapped[p], all[p], cudaIpcMemLazyEnablePeerAccess));
+  }
+  return GDN_OK;
+}
+
+static int comm_barrier_host() {          // every rank has reached this point (and its stream has drained)
+  Nccl &n = nccl();
+  if (n.size == 1 || !n.comm) return GDN_OK;
+  int *d = nullptr;
+  GDN_CUDA(cudaMalloc((void **)&d, sizeof(int)));
+  GDN_CUDA(cudaMemsetAsync(d, 0, sizeof(int), lib().stream));
+  GDN_NCCL(n.AllReduce(d, d, 1, ncclInt32, ncclSum, n.comm, lib().stream));
+  GDN_CUDA(cudaStreamSynchronize(lib().stream));
+  cudaFree(d);
+  return GDN_OK;
+}
+
+static int peer_box_setup() {
+  PeerBox &b = box();
+  Nccl &n = nccl();
+  if (b.ready || b.failed) return GDN_OK;
+  if (n.size > 8) { b.failed = true; return GDN_OK; }
+  b.failed = true;                           // until everything below has worked
+  GDN_CUDA(cudaMalloc((void **)&b.mail, kMailBytes));
+  GDN_CUDA(cudaMemsetAsync(b.mail, 0, kMailBytes, lib().stream));
+  GDN_CUDA(cudaMalloc((void **)&b.timeout_flag, sizeof(int)));
+  GDN_CUDA(cudaMemsetAsync(b.timeout_flag, 0, sizeof(int), lib().stream));
+  GDN_CUDA(cudaStreamSynchronize(lib().stream));
+  void *mapped[8] = {};
+  GDN_CHECK(ipc_exchange(b.mail, mapped));
+  for (int p = 0; p < n.size; p++) b.peer_mail[p] = (unsigned long long *)mapped[p];
+  GDN_CHECK(comm_barrier_host());            // nobody signals into a mailbox that is not zeroed yet
+  b.epoch = 0;
+  b.failed = false;
+  b.ready = true;
+  return GDN_OK;
+}
+
+static void peer_box_teardown() {
+  PeerBox &b = box();
+  Nccl &n = nccl();
+  if (b.mail) {
+    for (int p = 0; p < n.size; p++)
+      if (p != n.rank && b.peer_mail[p]) cudaIpcCloseMemHandle(b.peer_mail[p]);
+    comm_barrier_host();                     // the peers have unmapped this mailbox before it is freed
+    cudaFree(b.mail);
+    cudaFree(b.timeout_flag);
+  }
+  b = PeerBox();
+}
+
+// Map the two contrib vectors of every other GPU (once per graph; collective: all ranks solve the same graph together).
+int pull_peer_setup(gdn_graph *g) {
+  Nccl &n = nccl();
+  if (n.size == 1 || g->peer_ready || g->peer_failed) return GDN_OK;
+  GDN_CHECK(peer_box_setup());
+  if (!box().ready) { g->peer_failed = true; return GDN_OK; }
+  for (int k = 0; k < 2; k++) {
+    void *mapped[8] = {};
+    const int rc = ipc_exchange(g->contrib[k], mapped);
+    if (rc != GDN_OK) { g->peer_failed = true; return rc; }
+    for (int p = 0; p < n.size; p++) g->peer_contrib[k][p] = (float *)mapped[p];
+  }
+  g->peer_ready = true;
+  return GDN_OK;
+}
+bool pull_peer_ready(const gdn_graph *g) { return g->peer_ready; }
+
+// Unmap the peers' vectors; the owner frees its own only after every rank has done so.
+int pull_peer_release(gdn_graph *g) {
+  Nccl &n = nccl();
+  if (!g->peer_ready) return GDN_OK;
+  for (int k = 0; k < 2; k++)
+    for (int p = 0; p < n.size; p++)
+      if (p != n.rank && g->peer_contrib[k][p]) { cudaIpcCloseMemHandle(g->peer_contrib[k][p]); g->peer_contrib[k][p] = nullptr; }
+  g->peer_ready = false;
+  return comm_barrier_host();
+}
+
+void pull_peer_args(const gdn_graph *g, int buf_out, SellArgs &a) {
+  Nccl &n = nccl();
+  a.n_peers = 0;
+  for (int p = 0; p < n.size; p++) {
+    if (p == n.rank) continue;
+    a.peer_out[a.n_peers] = g->peer_contrib[buf_out][p];
+    a.peer_other[a.n_peers] = g->peer_contrib[buf_out ^ 1][p];
+    a.n_peers++;
+  }
+}
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// One block per GPU.  (1) fixed-order sum of this GPU's partials, (2) publish it into slot [epoch & 1][rank] of every
+// mailbox, (3) release-store the epoch into flag [rank] of every mailbox -- the stores of the kernels that ran before
+// this one on the stream (the row epilogues' remote contrib values) are ordered before it -- (4) wait until all P flags
+// of the own mailbox have reached the epoch, (5) add the P published values in rank order: every GPU gets the same bits.
+__global__ void __launch_bounds__(256)
+peer_sync_kernel(const double *__restrict__ partial, int n_partial, PeerMailArgs pm, int rank, int P,
+                 unsigned long long epoch, double *out, int iter, double eps, int32_t *done, int *timeout_flag) {
+  __shared__ double s[256];
+  if (done && *done) return;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n_partial; i += 256) acc += partial[i];
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  const int t = threadIdx.x;
+  if (t < P) {
+    double *vals = reinterpret_cast<double *>(pm.mail[t] + 8);
+    vals[(epoch & 1) * 8 + rank] = s[0];
+    __threadfence_system();
+    st_release_sys(pm.mail[t] + rank, epoch);
+  }
+  if (t < P) {
+    const unsigned long long *flag = pm.mail[rank] + t;
+    const unsigned long long t0 = globaltimer_ns();
+    while (ld_acquire_sys(flag) < epoch) {
+      if (globaltimer_ns() - t0 > 20000000000ull) { atomicExch(timeout_flag, 1); break; }   // 20 s: a peer is gone
+    }
+  }
+  __syncthreads();
+  if (t == 0 && out) {
+    const double *vals = reinterpret_cast<const double *>(pm.mail[rank] + 8) + (epoch & 1) * 8;
+    double tot = 0.0;
+    for (int q = 0; q < P; q++) tot += vals[q];
+    out[iter] = tot;
+    if (done && tot < eps) *done = iter + 1;
+  }
+}
+
+int pull_peer_sync(gdn_graph *g, const double *partial, int n_partial, double *err_out, int iter, double eps, int32_t *done,
+                   cudaStream_t s) {
+  PeerBox &b = box();
+  Nccl &n = nccl();
+  (void)g;
+  PeerMailArgs pm = {};
+  for (int p = 0; p < n.size; p++) pm.mail[p] = b.peer_mail[p];
+  b.epoch++;
+  peer_sync_kernel<<<1, 256, 0, s>>>(partial, n_partial, pm, n.rank, n.size, b.epoch, err_out, iter, eps, done, b.timeout_flag);
+  return GDN_OK;
+}
+
+// after a solve: did any barrier give up?
+int pull_peer_check() {
+  PeerBox &b = box();
+  if (!b.ready) return GDN_OK;
+  int h = 0;
+  GDN_CUDA(cudaMemcpy(&h, b.timeout_flag, sizeof(int), cudaMemcpyDeviceToHost));
+  if (h) { set_error("peer barrier timed out (a rank of the row partition stopped)"); return GDN_ERR_NCCL; }
+  return GDN_OK;
+}
+
 }  // namespace gdn
 
 using namespace gdn;
@@ -197,7 +405,7 @@ int gdn_comm_init(int rank, int nranks, const uint8_t id[128]) {
 
 int gdn_comm_destroy(void) {
   Nccl &n = nccl();
-  if (n.comm) { n.CommDestroy(n.comm); n.comm = nullptr; }
+  if (n.comm) { peer_box_teardown(); n.CommDestroy(n.comm); n.comm = nullptr; }
   n.rank = 0;
   n.size = 1;
   return GDN_OK;

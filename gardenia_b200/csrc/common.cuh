@@ -33,7 +33,9 @@ struct Lib {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;   // chunked host->device copies that kernels on `stream` consume chunk by chunk
   bool stream_fill = false;             // hint set by the one-shot PageRank entry point: build the pull layout WHILE the CSR uploads
+  bool pr_exact = false;                // gdn_set_pr_exact_order: graphs created from now on sum every PageRank row in column order
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t pr_ev[4] = {};            // PageRank: one per iteration in flight (the host runs ahead of the device, pull.cu)
   void *pinned = nullptr;          // small pinned mailbox for per-step counters
   size_t pinned_bytes = 0;
   // grow-only page-locked scratch of the layout preprocessing (degree array, row order): no page faults on reuse, and
@@ -50,10 +52,11 @@ Lib &lib();
 inline void kev_reset() { lib().n_kev = 0; }
 inline void kev_begin() { Lib &l = lib(); if (l.n_kev < Lib::kMaxKev) cudaEventRecord(l.kev[2 * l.n_kev], l.stream); }
 inline void kev_end() { Lib &l = lib(); if (l.n_kev < Lib::kMaxKev) { cudaEventRecord(l.kev[2 * l.n_kev + 1], l.stream); l.n_kev++; } }
-inline void kev_collect(gdn_stats *st) {
+inline void kev_collect(gdn_stats *st, int n_valid = 1 << 30) {
   if (!st) return;
   Lib &l = lib();
   double tot = 0;
+  if (l.n_kev > n_valid) l.n_kev = n_valid;
   for (int i = 0; i < l.n_kev; i++) { float ms = 0; if (cudaEventElapsedTime(&ms, l.kev[2 * i], l.kev[2 * i + 1]) == cudaSuccess) tot += ms; }
   st->kernel_ms = tot;
   st->kernel_calls = l.n_kev;
@@ -121,12 +124,9 @@ struct BandLayout {
   int32_t *job_first = nullptr;    // [n_cta + 1] jobs of CTA c
   int32_t *wrun = nullptr;         // [n_jobs * 33] item boundaries of the warp runs
   int32_t n_cta = 0;
-  float *bpartial = nullptr;       // [n_items * 32] per-row partial sums of the items (slot finalize, GDN_PR_BAND_FIN=0)
   int32_t *irow = nullptr;         // [n_items * 32] sorted row of (item, lane), -1 = none
-  long long *acc_fix = nullptr;    // [n_rows] 2^-56 fixed-point sum of a row's band partials (default finalize)
-  uint32_t *rslot_ptr = nullptr;   // [n_rows + 1] partial slots of sorted row j ...
-  uint32_t *rslot = nullptr;       // ... in (band, segment) order
-  uint64_t n_rslot = 0;
+  long long *acc_fix = nullptr;    // [n_rows] fixed-point sum of a row's band partials (scale chosen per solve, pull.cu fix_scale_for)
+  double build_ms = 0;             // wall time of band_build (reported by gdn_graph_pull_info)
   float *acc_main = nullptr;       // [n_rows] sum over the columns left in the main array
   // the compacted main SELL array and its work tables (same meaning as the PullLayout fields)
   int4 *sell = nullptr;
@@ -144,6 +144,8 @@ struct BandLayout {
 // Degree-sorted SELL-32 layout of the pull (in-) CSR used by PageRank (pull.cu).
 struct PullLayout {
   bool prepared = false;       // host part done (orders, ids, slice pointers, work items)
+  bool exact = false;          // exact-order mode: no wide-slice segments, no bands (every row summed in column order by one lane)
+  uint32_t group_ch = 1024;    // int4 groups per work item (pull.cuh kGroupCh; 0xffffffff in exact-order mode)
   bool symmetric_order = true; // row order == column order (row new-ids are two contiguous runs)
   int P = 1, R = 0;            // communicator size / rank the ids were laid out for
   int64_t W = 0, H = 0, Hp = 0, Wc = 0, Mp = 0;   // slice width, hot ids (total / per rank), cold width, id space
@@ -180,11 +182,16 @@ struct gdn_graph {
   float *contrib[2] = {nullptr, nullptr};
   int32_t *out_degree = nullptr;     // int32[rows]; for PR on directed graphs
   double *err_partial = nullptr;     // per-warp partial L1 deltas
-  double *err_trace = nullptr;       // double[GDN_MAX_PR_ITER] on device
+  double *err_trace = nullptr;       // double[GDN_MAX_PR_ITER + 8] on device (the tail slot takes sum |scores_0|)
+  double *abs_partial = nullptr;     // per-warp partials of sum |scores_0| (pr_sell_load)
   int32_t *pr_done = nullptr;        // device flag: converged
   int n_err_partial = 0;
   gdn::PullLayout pull;
   float *scores_sorted = nullptr;    // PR scores in sorted row order during a solve
+  // row partition: the contrib vectors of the other GPUs mapped here (comm.cu pull_peer_setup); [k][own rank] = contrib[k]
+  bool peer_ready = false, peer_failed = false;
+  float *peer_contrib[2][8] = {};
+  double prep_ms[4] = {0, 0, 0, 0};  // wall time of: create (upload + host layout), SELL build, band build, BFS hubs-first copy
   // BFS scratch
   uint32_t *visited = nullptr, *front = nullptr, *next = nullptr;
   uint32_t *iso = nullptr;           // static: vertices without in-edges (+ pad bits), pre-set in `visited`

@@ -58,8 +58,6 @@ struct GatherArgs {
   double *err_partial;
   const int32_t *done;    // device flag set once converged: later launches are no-ops
   int err_slot0;          // first err_partial slot of this kernel
-  // column window of this pass (SpMV column passes, see spmv_t): entries outside [col_lo, col_hi) add +0.0f
-  int32_t col_lo, col_hi;
 };
 
 template <int MODE>
@@ -98,7 +96,7 @@ __device__ __forceinline__ float stream_gather(const GatherArgs &a, const int32_
     }
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-      const bool ok = (i + j >= b) && (i + j < e) && (MODE != kModeSpmv || (q[j] >= a.col_lo && q[j] < a.col_hi));
+      const bool ok = (i + j >= b) && (i + j < e);
       float g = 0.f;
       if (ok) g = ld_gather_f32(a.vec + q[j], pol);
       v[j] = (MODE == kModeSpmv) ? (ok ? __fmul_rn(g, ax[j]) : 0.f) : g;
@@ -196,170 +194,6 @@ finalize_heavy(const OffT *__restrict__ rowptr, GatherArgs a) {
     if (lane == 0) a.err_partial[a.err_slot0 + warp] = err;
   }
 }
-
-// ---------------------------------------------------------------- SpMV with TMA-staged row segments
-// Same schedule, same arithmetic, different data movement: the column indices and matrix values of a
-// work item are brought into shared memory by ONE elected lane with two 1-D bulk copies
-// (cp.async.bulk -> SASS UBLKCP, completion on a per-warp mbarrier), double-buffered so the copy of
-// item k+1 overlaps the gathers of item k.  The LSU then carries only the x gathers: ncu r1 showed the
-// register-staged kernel latency-bound with a third of its in-flight sectors being the (always
-// HBM-latency) stream.  Products are staged in place over the values.
-constexpr int kTmaWarps = 4;
-constexpr int kTmaCap = 1040;            // >= 2*kChunk + alignment slack, multiple of 4
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// global -> shared bulk copy (TMA, 1-D); dst/src 16-byte aligned, bytes a multiple of 16
-__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t pol) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
-}
-
-struct TmaStage {
-  int32_t col[kTmaCap];
-  float val[kTmaCap];
-};
-
-template <typename OffT>
-struct ItemDesc {
-  OffT b, e;          // non-zero range
-  int32_t r0, r1;     // light block rows, or {row, -1 - segment} for a heavy segment
-};
-
-// Describe work item `item` (warp-uniform loads; cheap next to the copy they precede).
-template <typename OffT>
-__device__ __forceinline__ bool describe(const OffT *__restrict__ rowptr, const GatherArgs &a, int64_t item, ItemDesc<OffT> &d) {
-  if (item < a.n_chunks) {
-    int32_t r0 = a.chunk_row[item], r1 = a.chunk_row[item + 1];
-    if (r1 > r0) {
-      const OffT lb = rowptr[r1 - 1], le = rowptr[r1];
-      if (le - lb > (OffT)kChunk) r1--;
-    }
-    if (r1 <= r0) return false;
-    d.r0 = r0; d.r1 = r1; d.b = rowptr[r0]; d.e = rowptr[r1];
-  } else {
-    const int32_t h = (int32_t)(item - a.n_chunks);
-    const int2 hs = a.heavy_seg[h];
-    const OffT rb = rowptr[hs.x], re = rowptr[hs.x + 1];
-    d.b = rb + (OffT)hs.y * kSeg;
-    d.e = (re - d.b > (OffT)kSeg) ? d.b + kSeg : re;
-    d.r0 = h; d.r1 = -1;
-  }
-  return true;
-}
-
-template <typename OffT>
-__global__ void __launch_bounds__(kTmaWarps * 32, 3)
-spmv_tma_kernel(const OffT *__restrict__ rowptr, const int32_t *__restrict__ col, GatherArgs a) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  TmaStage *stages = reinterpret_cast<TmaStage *>(smem_raw) + 2 * wib;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + sizeof(TmaStage) * 2 * kTmaWarps) + 2 * wib;
-  if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  __syncwarp();
-  const int64_t warp = (int64_t)blockIdx.x * kTmaWarps + wib, nwarps = (int64_t)gridDim.x * kTmaWarps;
-  const int64_t n_items = (int64_t)a.n_chunks + a.n_heavy_segs;
-  const uint64_t pol_stream = l2_policy_evict_first(), pol = l2_policy_evict_last();
-  const uint64_t nnz4 = a.nnz & ~3ull;
-
-  // issue the copies of one item into stage st (lane 0); a0 = first staged non-zero
-  auto issue = [&](const ItemDesc<OffT> &d, int st) {
-    if (lane == 0) {
-      const uint64_t a0 = (uint64_t)d.b & ~3ull, a1 = ((uint64_t)d.e + 3) & ~3ull;
-      const uint64_t v1 = a1 < nnz4 ? a1 : (nnz4 > a0 ? nnz4 : a0);      // Ax has no slack past nnz: tail is patched by hand
-      const uint32_t cb = (uint32_t)(a1 - a0) * 4, vb = (uint32_t)(v1 - a0) * 4;
-      mbar_expect_tx(&bars[st], cb + vb);
-      if (cb) tma_load_1d(stages[st].col, col + a0, cb, &bars[st], pol_stream);
-      if (vb) tma_load_1d(stages[st].val, a.Ax + a0, vb, &bars[st], pol_stream);
-    }
-  };
-
-  ItemDesc<OffT> cur, nxt;
-  int64_t item = warp;
-  bool have = false;
-  while (item < n_items && !(have = describe(rowptr, a, item, cur))) item += nwarps;
-  uint32_t ph0 = 0, ph1 = 0;
-  int st = 0;
-  if (have) issue(cur, 0);
-  while (have) {
-    // find and launch the next non-empty item into the other stage
-    int64_t nitem = item + nwarps;
-    bool have_n = false;
-    while (nitem < n_items && !(have_n = describe(rowptr, a, nitem, nxt))) nitem += nwarps;
-    if (have_n) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // our generic-proxy accesses to that stage are done
-      __syncwarp();
-      issue(nxt, st ^ 1);
-    }
-    mbar_wait(&bars[st], st ? ph1 : ph0);
-    if (st) ph1 ^= 1; else ph0 ^= 1;
-    int32_t *sc = stages[st].col;
-    float *sv = stages[st].val;
-    const uint64_t a0 = (uint64_t)cur.b & ~3ull;
-    const int32_t s_b = (int32_t)((uint64_t)cur.b - a0), s_e = (int32_t)((uint64_t)cur.e - a0);
-    if ((uint64_t)cur.e > nnz4) {                     // the last <= 3 values of the matrix
-      const uint64_t i = nnz4 + lane;
-      if (lane < 3 && i < (uint64_t)cur.e && i >= (uint64_t)cur.b) sv[i - a0] = a.Ax[i];
-      __syncwarp();
-    }
-    if (cur.r1 >= 0) {
-      // ---- light block: products in place, then one lane per row sums in the reference's order
-      for (int32_t j0 = s_b; j0 < s_e; j0 += 256) {
-        float g[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-          const int32_t j = j0 + u * 32 + lane;
-          g[u] = (j < s_e) ? ld_gather_f32(a.vec + sc[j], pol) : 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-          const int32_t j = j0 + u * 32 + lane;
-          if (j < s_e) sv[j] = __fmul_rn(g[u], sv[j]);
-        }
-      }
-      __syncwarp();
-      for (int32_t r = cur.r0 + lane; r < cur.r1; r += 32) {
-        const int32_t s = (int32_t)((uint64_t)rowptr[r] - a0), t = (int32_t)((uint64_t)rowptr[r + 1] - a0);
-        float acc = a.y[r];
-        for (int32_t j = s; j < t; j++) acc = __fadd_rn(acc, sv[j]);
-        a.y[r] = acc;
-      }
-    } else {
-      // ---- heavy segment -> one partial
-      float acc0 = 0.f, acc1 = 0.f;
-      for (int32_t j0 = s_b; j0 < s_e; j0 += 256) {
-        float g[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-          const int32_t j = j0 + u * 32 + lane;
-          g[u] = (j < s_e) ? __fmul_rn(ld_gather_f32(a.vec + sc[j], pol), sv[j]) : 0.f;
-        }
-        acc0 += (g[0] + g[1]) + (g[2] + g[3]);
-        acc1 += (g[4] + g[5]) + (g[6] + g[7]);
-      }
-      const float acc = warp_sum(acc0 + acc1);
-      if (lane == 0) a.heavy_partial[cur.r0] = acc;
-    }
-    __syncwarp();
-    cur = nxt; item = nitem; have = have_n; st ^= 1;
-  }
-}
-
 
 // ---------------------------------------------------------------- SpMV, software-pipelined (default: 384 threads x 2 CTAs per SM)
 // Same schedule and the same arithmetic as gather_kernel<., kModeSpmv> (products staged per warp, one lane per light
@@ -680,60 +514,20 @@ static int spmv_t(gdn_graph *g, const float *d_Ax, const float *d_x, float *d_y,
   const OffT *rp = (const OffT *)c.rowptr;
   kev_reset();
   GDN_CUDA(cudaEventRecord(lib().ev0, s));
-  // The TMA-staged variant is correct but measured 2.6x SLOWER than the register-staged kernel on urand-24
-  // (8.4 vs 3.2 ms, profiles/r1_ncu_summary.md): 12 warps/SM of per-warp 1 K-entry items cannot cover the
-  // describe -> copy -> gather -> row-sum chain.  Kept selectable for the next round's rework.
-  const bool legacy = getenv("GDN_SPMV_TMA") == nullptr;
-  const size_t tma_smem = sizeof(TmaStage) * 2 * kTmaWarps + sizeof(uint64_t) * 2 * kTmaWarps;
-  // Column passes (experiment, GDN_SPMV_PASSES=P): pass p gathers only the columns of window p (a prefix / middle /
-  // suffix of every sorted row) so that the window stays L2-resident; the other entries add +0.0f and y carries the
-  // running sum from pass to pass -- the fp32 addition order of a light row is still exactly the reference's
-  // (src/spmv/omp_base.cc:26-31).  Measured (profiles/r1_spmv_column_passes.txt): urand-24 3.16 -> 3.03 ms at P=2,
-  // slower everywhere else (col/Ax are streamed once per pass): the kernel is not bound by the gather's L2 misses.
-  // Default: one pass.
-  const char *e_pass = getenv("GDN_SPMV_PASSES"), *e_win = getenv("GDN_SPMV_WINDOW_MB");
-  const int64_t win_ids = (int64_t)(e_win ? atoi(e_win) : 40) * (1 << 20) / 4;
-  int passes = e_pass ? atoi(e_pass) : (e_win ? (int)std::min<int64_t>(4, (g->m + win_ids - 1) / win_ids) : 1);
-  if (passes < 1 || !legacy) passes = 1;
-  a.col_lo = 0; a.col_hi = 0x7fffffff;
-  // GDN_SPMV_PIPE: 0 = gather_kernel (one trip at a time); 10*T + C = spmv_pipe with T threads per CTA, C CTAs per SM
-  const char *e_pipe = getenv("GDN_SPMV_PIPE");
-  const int pipe = (legacy && passes == 1) ? (e_pipe ? atoi(e_pipe) : 3842) : 0;
+  // 24 warps per SM at 76-80 registers measured best on urand-24 (profiles/r1_spmv_pipe_sweep.txt): 32 warps force 64
+  // registers and spill (4.2 ms), 16 warps are short of gathers in flight (2.8 ms).  Negative results kept in profiles/:
+  // a TMA-staged index/value stream (cp.async.bulk per 1 K-entry item: 2.6x slower), column passes over an L2-sized
+  // window (r1_spmv_column_passes.txt), the one-trip-at-a-time kernel (+18 %).
+  constexpr int kPipeThreads = 384, kPipeCtas = 2;
+  const size_t smem = sizeof(float) * (size_t)kCap * (kPipeThreads / 32);
+  GDN_CUDA(cudaFuncSetAttribute(spmv_pipe<OffT, kPipeThreads, kPipeCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kev_begin();
-  if (pipe) {
-    // measured on urand-24 (profiles/r1_spmv_pipe_sweep.txt): 24 warps per SM at 76-80 registers win; 32 warps force 64
-    // registers and spill (4.2 ms), 16 warps are short of gathers in flight (2.8 ms)
-    void (*kern)(const OffT *, const int32_t *, GatherArgs) = spmv_pipe<OffT, 384, 2>;
-    int threads = 384, ctas = 2;
-    switch (pipe) {
-      case 10241: kern = spmv_pipe<OffT, 1024, 1>; threads = 1024; ctas = 1; break;
-      case 5122: kern = spmv_pipe<OffT, 512, 2>; threads = 512; ctas = 2; break;
-      case 2563: kern = spmv_pipe<OffT, 256, 3>; threads = 256; ctas = 3; break;
-      case 2562: kern = spmv_pipe<OffT, 256, 2>; threads = 256; ctas = 2; break;     // 128 registers
-      case 2564: kern = spmv_pipe<OffT, 256, 4>; threads = 256; ctas = 4; break;
-      default: break;
-    }
-    const size_t smem = sizeof(float) * (size_t)kCap * (threads / 32);
-    GDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<lib().sm_count * ctas, threads, smem, s>>>(rp, c.col, a);
-  } else if (legacy) {
-    for (int p = 0; p < passes; p++) {
-      a.col_lo = (int32_t)(g->m * p / passes);
-      a.col_hi = p + 1 == passes ? 0x7fffffff : (int32_t)(g->m * (p + 1) / passes);
-      gather_kernel<OffT, kModeSpmv><<<gather_grid(c), kThreads, 0, s>>>(rp, c.col, a);
-      if (c.n_heavy_rows > 0 && p + 1 < passes) finalize_heavy<OffT, kModeSpmv><<<heavy_grid(c), kThreads, 0, s>>>(rp, a);
-    }
-  } else {
-    GDN_CUDA(cudaFuncSetAttribute(spmv_tma_kernel<OffT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem));
-    const int64_t items = (int64_t)c.n_chunks + c.n_heavy_segs;
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((items + kTmaWarps - 1) / kTmaWarps, (int64_t)lib().sm_count * 3));
-    spmv_tma_kernel<OffT><<<grid, kTmaWarps * 32, tma_smem, s>>>(rp, c.col, a);
-  }
+  spmv_pipe<OffT, kPipeThreads, kPipeCtas><<<lib().sm_count * kPipeCtas, kPipeThreads, smem, s>>>(rp, c.col, a);
   kev_end();
-  int launches = passes;
+  int launches = 1;
   if (c.n_heavy_rows > 0) {
     finalize_heavy<OffT, kModeSpmv><<<heavy_grid(c), kThreads, 0, s>>>(rp, a);
-    launches += passes;
+    launches++;
   }
   GDN_CUDA(cudaEventRecord(lib().ev1, s));
   GDN_CUDA(cudaStreamSynchronize(s));

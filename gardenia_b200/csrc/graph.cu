@@ -72,6 +72,7 @@ int pull_prepare(gdn_graph *g, const HostOffT *row_off, const HostOffT *key_off)
 int bfs_run(gdn_graph *g, int32_t source, int32_t *d_depth, int32_t *d_parent, gdn_stats *st);
 int pr_run(gdn_graph *g, float *d_scores, float damp, double eps, int max_iter, gdn_stats *st);
 int spmv_run(gdn_graph *g, const float *d_Ax, const float *d_x, float *d_y, gdn_stats *st);
+int pull_peer_release(gdn_graph *g);       // comm.cu
 
 // in[i] - base -> out[i]
 template <typename InT, typename OutT>
@@ -226,6 +227,7 @@ static int graph_create_t(int64_t m, int64_t nnz, const HostOffT *out_rowptr, co
   gdn_graph *g = new gdn_graph();
   g->m = m; g->row_lo = row_lo; g->row_hi = row_hi;
   int rc = GDN_OK;
+  const auto t_create = std::chrono::steady_clock::now();
   trace("graph_create: begin");
   PendingUpload pu_out, pu_in;
   const bool sym = out_rowptr && (!in_rowptr || (in_rowptr == out_rowptr && in_colidx == out_colidx));
@@ -296,6 +298,7 @@ static int graph_create_t(int64_t m, int64_t nnz, const HostOffT *out_rowptr, co
   }
   trace("graph_create: uploads finished");
   if (rc != GDN_OK) { gdn_graph_destroy(g); return rc; }
+  g->prep_ms[0] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_create).count();
   *out = g;
   return GDN_OK;
 }
@@ -343,6 +346,7 @@ int gdn_init(int device) {
   for (int i = 0; i < 2 * Lib::kMaxKev; i++) GDN_CUDA(cudaEventCreate(&l.kev[i]));
   l.pinned_bytes = 4096;
   GDN_CUDA(cudaHostAlloc(&l.pinned, l.pinned_bytes, cudaHostAllocDefault));
+  { const char *e = getenv("GDN_PR_EXACT"); if (e) l.pr_exact = atoi(e) != 0; }
   l.inited = true;
   return GDN_OK;
 }
@@ -357,6 +361,7 @@ int gdn_finalize(void) {
   cudaStreamDestroy(l.copy_stream);
   cudaEventDestroy(l.ev0);
   cudaEventDestroy(l.ev1);
+  for (cudaEvent_t e : l.pr_ev) if (e) cudaEventDestroy(e);
   for (int i = 0; i < 2 * Lib::kMaxKev; i++) cudaEventDestroy(l.kev[i]);
   cudaFreeHost(l.pinned);
   for (int i = 0; i < 2; i++) if (l.arena[i]) cudaFreeHost(l.arena[i]);
@@ -389,11 +394,12 @@ int gdn_graph_set_out_degree(gdn_graph *g, const int32_t *h_out_degree) {
 
 int gdn_graph_destroy(gdn_graph *g) {
   if (!g) return GDN_OK;
+  pull_peer_release(g);          // row partition: the peers unmap this graph's vectors before they are freed
   for (cudaEvent_t ev : g->col_ev) cudaEventDestroy(ev);
   if (g->symmetric) { free_csr(g->out); g->in = DevCsr(); }
   else { free_csr(g->out); free_csr(g->in); }
   cudaFree(g->contrib[0]); cudaFree(g->contrib[1]); cudaFree(g->out_degree); cudaFree(g->err_partial);
-  cudaFree(g->err_trace); cudaFree(g->pr_done);
+  cudaFree(g->err_trace); cudaFree(g->pr_done); cudaFree(g->abs_partial);
   cudaFree(g->visited); cudaFree(g->front); cudaFree(g->next); cudaFree(g->iso); cudaFree(g->queue[0]); cudaFree(g->queue[1]);
   cudaFree(g->heavy_queue); cudaFree(g->heavy_off); cudaFree(g->deg_class); cudaFree(g->col_bu);
   cudaFree(g->counters); cudaFree(g->xbuf);
@@ -423,6 +429,23 @@ int gdn_graph_pull_info(const gdn_graph *g, int64_t info[8]) {
   info[0] = b.built ? (b.seg ? 2 : 1) : 0; info[1] = b.B; info[2] = b.band; info[3] = b.n_rows;
   info[4] = (int64_t)b.moved; info[5] = (int64_t)b.pairs; info[6] = b.n_items;
   info[7] = (int64_t)(b.built ? b.n_groups : g->pull.n_groups);
+  return GDN_OK;
+}
+
+int gdn_graph_prep_ms(const gdn_graph *g, double ms[4]) {
+  if (!g || !ms) return GDN_ERR_ARG;
+  for (int i = 0; i < 4; i++) ms[i] = g->prep_ms[i];
+  ms[2] = g->pull.band.build_ms;
+  return GDN_OK;
+}
+
+int gdn_set_pr_exact_order(int on) {
+  lib().pr_exact = on != 0;
+  return GDN_OK;
+}
+
+int gdn_device_trim(void) {
+  pool_release();
   return GDN_OK;
 }
 

@@ -31,6 +31,8 @@
 // contiguous slices of contrib (two in-place NCCL allgathers per iteration).
 #include "pull.cuh"
 #include <omp.h>
+#include <chrono>
+#include <cmath>
 #include <cstdlib>
 #include <algorithm>
 #include <vector>
@@ -142,6 +144,10 @@ int pull_prepare(gdn_graph *g, const HostOffT *row_off, const HostOffT *key_off)
   L.Mp = L.H + L.Wc * P;
   L.rows = rows;
   L.symmetric_order = (key_off == row_off);
+  // exact-order mode (gdn_set_pr_exact_order / GDN_PR_EXACT=1): no slice is ever cut into segments, so EVERY row is summed
+  // sequentially in column order by one lane -- bit-identical to src/pr/omp_base.cc:28-30 whatever the row length
+  L.exact = lib().pr_exact;
+  L.group_ch = L.exact ? 0xffffffffu : (uint32_t)kGroupCh;
 
   trace("pull_prepare: begin");
   // degree array and row order live in the library's page-locked scratch (reused from call to call)
@@ -153,7 +159,7 @@ int pull_prepare(gdn_graph *g, const HostOffT *row_off, const HostOffT *key_off)
 #pragma omp parallel for reduction(+ : bad)
   for (int64_t v = 0; v < m; v++) {
     rdeg[v] = (int32_t)(row_off[v + 1] - row_off[v]);
-    bad += row_off[v + 1] < row_off[v];
+    bad += row_off[v + 1] < row_off[v] || (uint64_t)(row_off[v + 1] - row_off[v]) > 0x7fffffffull;
   }
   const int32_t *kd = rdeg;
   if (!L.symmetric_order) {
@@ -161,7 +167,7 @@ int pull_prepare(gdn_graph *g, const HostOffT *row_off, const HostOffT *key_off)
 #pragma omp parallel for reduction(+ : bad)
     for (int64_t v = 0; v < m; v++) {
       kdeg[v] = (int32_t)(key_off[v + 1] - key_off[v]);
-      bad += key_off[v + 1] < key_off[v];
+      bad += key_off[v + 1] < key_off[v] || (uint64_t)(key_off[v + 1] - key_off[v]) > 0x7fffffffull;
     }
     kd = kdeg.data();
   }
@@ -213,12 +219,13 @@ int pull_prepare(gdn_graph *g, const HostOffT *row_off, const HostOffT *key_off)
   for (int32_t s = 0; s < L.n_slices; s++) {
     sptr[s] = (uint32_t)tot;
     tot += 32ull * ((width[s] + 3) / 4);
-    if (tot >= 0xffff0000ull) { set_error("pull layout: too many non-zeros for 32-bit group offsets"); return GDN_ERR_ARG; }
+    if (tot >= 0xffff0000ull) { L.prepared = false; return GDN_OK; }   // 32-bit group offsets would overflow: plain CSR path (gather.cu pr_t)
   }
   sptr[L.n_slices] = (uint32_t)tot;
   L.n_groups = tot;
   L.h_slice_ptr = sptr;
   // work items: chunk k owns the light slices that START in [k*CH,(k+1)*CH); wide slices are cut into segments
+  // (the chunk grid stays kGroupCh in exact-order mode; only the cut of wide slices into segments is disabled)
   L.n_chunks = (int32_t)(tot / kGroupCh + 1);
   std::vector<int32_t> chunk((size_t)L.n_chunks + 1);
   {
@@ -233,7 +240,7 @@ int pull_prepare(gdn_graph *g, const HostOffT *row_off, const HostOffT *key_off)
   std::vector<int2> hseg;
   for (int32_t s = 0; s < L.n_slices; s++) {
     const uint32_t sz = sptr[s + 1] - sptr[s];
-    if (sz <= (uint32_t)kGroupCh) break;                 // widths are non-increasing
+    if (sz <= L.group_ch) break;                         // widths are non-increasing
     hslice.push_back(s);
     hfirst.push_back((int32_t)hseg.size());
     for (uint32_t q = 0; q < (sz + kGroupCh - 1) / kGroupCh; q++) hseg.push_back(make_int2(s, (int)q));
@@ -455,6 +462,7 @@ static int pull_stream_fill(gdn_graph *g) {
 int pull_build_sell(gdn_graph *g) {
   PullLayout &L = g->pull;
   if (L.sell || !L.prepared) return GDN_OK;
+  const auto t0 = std::chrono::steady_clock::now();
   const DevCsr &c = g->in;
   GDN_CUDA(cudaMalloc((void **)&L.sell, sizeof(int4) * std::max<uint64_t>(L.n_groups, 1) + 256));
   g->device_bytes += sizeof(int4) * L.n_groups;
@@ -470,6 +478,7 @@ int pull_build_sell(gdn_graph *g) {
   GDN_CUDA(cudaStreamSynchronize(lib().stream));
   GDN_CUDA(cudaGetLastError());
   trace("pull_build_sell: done");
+  g->prep_ms[1] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return GDN_OK;
 }
 
@@ -480,120 +489,35 @@ int pull_build_sell(gdn_graph *g) {
 // their one-touch sectors do not push the warm part out of L2.  Written as three PREDICATED loads (no
 // branches): the compiler's branchy version spent a fifth of its issue slots on reconvergence and left
 // the 16 loads of a trip interleaved with them (ncu r1: stall_mio 18 %, short scoreboard 30 %).
-template <int POLICY>
-__device__ __forceinline__ float pull_one(const SellArgs &a, uint32_t s_hot_addr, const float *s_hot, int c, uint64_t pol_first, uint64_t pol_last) {
+__device__ __forceinline__ float pull_one(const SellArgs &a, uint32_t s_hot_addr, int c, uint64_t pol_first, uint64_t pol_last) {
   float v = 0.f;
-  if (POLICY == 0) {
-    if ((unsigned)c < (unsigned)a.hot_n) v = s_hot[c];
-    else if (c >= 0) v = __ldg(a.contrib_in + c);
-    return v;
-  }
   const float *p = a.contrib_in + c;
   const int32_t t = tier_id(a, c);
-  uint64_t pol_norm = 0;
-  if (POLICY == 2) asm volatile("createpolicy.fractional.L2::evict_unchanged.b64 %0, 1.0;" : "=l"(pol_norm));
   asm volatile(
-      "{\n\t.reg .pred ph, pw, pc, ph2;\n\t"
+      "{\n\t.reg .pred ph, pw, pc;\n\t"
       "setp.lt.u32 ph, %1, %2;\n\t"               // hot: 0 <= c < H   (c = -1 is 0xffffffff: never hot)
       "setp.ge.s32 pw, %1, %2;\n\t"               // not hot and not padding
-      "setp.ge.s32 pc, %9, %3;\n\t"               // cold (by its position inside its rank's slice)
+      "setp.ge.s32 pc, %8, %3;\n\t"               // cold (by its position inside its rank's slice); never true for c = -1
       "and.pred pw, pw, !pc;\n\t"
-      "setp.lt.s32 ph2, %1, %8;\n\t"
-      "and.pred pc, pc, ph2;\n\t"
       "@ph ld.shared.f32 %0, [%4];\n\t"
       "@pw ld.global.nc.L2::cache_hint.f32 %0, [%5], %6;\n\t"
       "@pc ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%5], %7;\n\t}"
       : "+f"(v)
-      : "r"(c), "r"(a.hot_n), "r"(a.warm), "r"(s_hot_addr + 4u * (uint32_t)c), "l"(p), "l"(POLICY == 2 ? pol_norm : pol_last), "l"(pol_first), "r"(a.skip_from), "r"(t));
+      : "r"(c), "r"(a.hot_n), "r"(a.warm), "r"(s_hot_addr + 4u * (uint32_t)c), "l"(p), "l"(pol_last), "l"(pol_first), "r"(t));
   return v;
 }
 
-// Sum groups [g0, g1) (multiples of 32 groups; lane = row) sequentially per lane, in column order.
-// Software-pipelined: the NEXT four index groups are requested before the current 16 gathers are
-// issued, so a lane keeps 16 gathers + 4 index loads in flight (the kernel is latency-bound otherwise:
-// ncu r1 showed 90 % of issue slots with no eligible warp at 8 dependent gathers per trip).
-// Missing groups are padded with -1 = "add 0.0f", which leaves the fp32 sum bit-identical.
-template <int POLICY>
-__device__ __forceinline__ float sell_sum(const SellArgs &a, const float *s_hot, uint32_t g0, uint32_t g1, int lane,
-                                          float acc, uint64_t pol, uint64_t pol_last) {
-  const int4 *p = a.sell + g0 + lane;
-  const uint32_t s_hot_addr = (uint32_t)__cvta_generic_to_shared(s_hot);
-  const int n = (int)((g1 - g0) >> 5);            // groups per lane (warp-uniform)
-  const int4 none = make_int4(-1, -1, -1, -1);
-  int4 c0 = 0 < n ? ld_stream_v4(p, pol) : none;
-  int4 c1 = 1 < n ? ld_stream_v4(p + 32, pol) : none;
-  int4 c2 = 2 < n ? ld_stream_v4(p + 64, pol) : none;
-  int4 c3 = 3 < n ? ld_stream_v4(p + 96, pol) : none;
-  for (int k = 0; k < n; k += 4) {
-    p += 128;
-    const int4 n0 = k + 4 < n ? ld_stream_v4(p, pol) : none;
-    const int4 n1 = k + 5 < n ? ld_stream_v4(p + 32, pol) : none;
-    const int4 n2 = k + 6 < n ? ld_stream_v4(p + 64, pol) : none;
-    const int4 n3 = k + 7 < n ? ld_stream_v4(p + 96, pol) : none;
-    float v[16];
-    v[0] = pull_one<POLICY>(a, s_hot_addr, s_hot, c0.x, pol, pol_last); v[1] = pull_one<POLICY>(a, s_hot_addr, s_hot, c0.y, pol, pol_last);
-    v[2] = pull_one<POLICY>(a, s_hot_addr, s_hot, c0.z, pol, pol_last); v[3] = pull_one<POLICY>(a, s_hot_addr, s_hot, c0.w, pol, pol_last);
-    v[4] = pull_one<POLICY>(a, s_hot_addr, s_hot, c1.x, pol, pol_last); v[5] = pull_one<POLICY>(a, s_hot_addr, s_hot, c1.y, pol, pol_last);
-    v[6] = pull_one<POLICY>(a, s_hot_addr, s_hot, c1.z, pol, pol_last); v[7] = pull_one<POLICY>(a, s_hot_addr, s_hot, c1.w, pol, pol_last);
-    v[8] = pull_one<POLICY>(a, s_hot_addr, s_hot, c2.x, pol, pol_last); v[9] = pull_one<POLICY>(a, s_hot_addr, s_hot, c2.y, pol, pol_last);
-    v[10] = pull_one<POLICY>(a, s_hot_addr, s_hot, c2.z, pol, pol_last); v[11] = pull_one<POLICY>(a, s_hot_addr, s_hot, c2.w, pol, pol_last);
-    v[12] = pull_one<POLICY>(a, s_hot_addr, s_hot, c3.x, pol, pol_last); v[13] = pull_one<POLICY>(a, s_hot_addr, s_hot, c3.y, pol, pol_last);
-    v[14] = pull_one<POLICY>(a, s_hot_addr, s_hot, c3.z, pol, pol_last); v[15] = pull_one<POLICY>(a, s_hot_addr, s_hot, c3.w, pol, pol_last);
-#pragma unroll
-    for (int q = 0; q < 16; q++) acc = __fadd_rn(acc, v[q]);
-    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-  }
-  return acc;
-}
-
-template <int POLICY>
-__global__ void __launch_bounds__(kSellThreads, 1)
-pr_sell_kernel(SellArgs a) {
-  extern __shared__ float s_hot[];
-  if (*a.done) return;
-  for (int i = threadIdx.x; i < a.hot_n; i += kSellThreads) s_hot[i] = a.contrib_in[i];
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = (int64_t)blockIdx.x * (kSellThreads / 32) + (threadIdx.x >> 5);
-  const int64_t nwarps = (int64_t)gridDim.x * (kSellThreads / 32);
-  const int64_t n_items = (int64_t)a.n_chunks + a.n_heavy_segs;
-  const uint64_t pol = l2_policy_evict_first(), pol_last = l2_policy_evict_last();
-  double err = 0.0;
-  // heavy segments first (they are the longest items), then the chunks
-  for (int64_t item = warp; item < n_items; item += nwarps) {
-    if (item < a.n_heavy_segs) {
-      const int2 hs = a.heavy_seg[item];
-      const uint32_t s0 = a.slice_ptr[hs.x], s1 = a.slice_ptr[hs.x + 1];
-      const uint32_t g0 = s0 + (uint32_t)hs.y * kGroupCh;
-      const uint32_t g1 = (s1 - g0 > (uint32_t)kGroupCh) ? g0 + kGroupCh : s1;
-      a.partial[(size_t)item * 32 + lane] = sell_sum<POLICY>(a, s_hot, g0, g1, lane, 0.f, pol, pol_last);
-    } else {
-      const int64_t k = item - a.n_heavy_segs;
-      const int32_t sa = a.chunk_slice[k], sb = a.chunk_slice[k + 1];
-      for (int32_t s = sa; s < sb; s++) {
-        const uint32_t g0 = a.slice_ptr[s], g1 = a.slice_ptr[s + 1];
-        if (g1 - g0 > (uint32_t)kGroupCh) continue;          // wide slice: handled as segments
-        const float acc = sell_sum<POLICY>(a, s_hot, g0, g1, lane, 0.f, pol, pol_last);
-        const int64_t j = (int64_t)s * 32 + lane;
-        if (j < a.n_nz_rows) pr_epilogue(a, j, acc, err);
-      }
-    }
-  }
-  err = warp_sum(err);
-  if (lane == 0) a.err_partial[a.err_slot0 + warp] = err;
-}
-
 // ------------------------------------------------------------------ the pipelined iteration kernel
-// pr_sell_kernel above keeps ONE trip (16 gathers per lane) in flight and then waits for it.  Measured
-// (profiles/r1_pr_tier_probe.txt): its time is the SUM of a 3.3 ms "stream + shared-table" floor and the L2-tier
+// A kernel that keeps ONE trip (16 gathers per lane) in flight and then waits for it was measured
+// (profiles/r1_pr_tier_probe.txt) at the SUM of a 3.3 ms "stream + shared-table" floor and the L2-tier
 // gathers at exactly the 1 sector/clk/SM miss-path rate -- the two never overlap, because all warps of an SM queue
 // their gathers behind each other, drain together, and then wait together for the next index groups (a convoy; L1TEX
 // 53 % busy).  Here a warp's work is flattened into one sequence of trips that crosses slice and item boundaries, and
 // the loop is software-pipelined two trips deep:
 //      request index groups of trip t+2  |  issue the gathers of trip t+1  |  add the values of trip t
 // so the L1TEX miss path always holds gathers of this warp while it waits, adds and runs epilogues.  The row epilogue's
-// inputs (old score, degree) are requested with the last trip of their slice.  The per-row addition order is unchanged
-// (column order, sequential fp32): results are bit-identical to pr_sell_kernel.
+// inputs (old score, degree) are requested with the last trip of their slice.  The per-row addition order is column
+// order, sequential fp32 (src/pr/omp_base.cc:28-30).
 struct TripDesc {
   uint32_t g;      // first int4 unit of the trip (lane 0's)
   int32_t n;       // index groups per lane (0: this warp has no work left)
@@ -633,7 +557,7 @@ struct TripIter {
         const uint32_t g0 = __shfl_sync(kFull, lo, s - sa), g1 = __shfl_sync(kFull, hi, s - sa);
         ref = s;
         s++;
-        if (g1 - g0 > (uint32_t)kGroupCh) continue;          // wide slice: handled as segments
+        if (g1 - g0 > a.group_ch) continue;                  // wide slice: handled as segments
         g = g0; g_end = g1; kind = 1;
         continue;
       }
@@ -642,8 +566,8 @@ struct TripIter {
       if (item < a.n_heavy_segs) {
         const int2 hs = a.heavy_seg[item];
         const uint32_t s0 = a.slice_ptr[hs.x], s1 = a.slice_ptr[hs.x + 1];
-        g = s0 + (uint32_t)hs.y * kGroupCh;
-        g_end = (s1 - g > (uint32_t)kGroupCh) ? g + kGroupCh : s1;
+        g = s0 + (uint32_t)hs.y * a.group_ch;
+        g_end = (s1 - g > a.group_ch) ? g + a.group_ch : s1;
         kind = 2; ref = item; s = s_end = 0;
       } else {
         const int32_t k = item - a.n_heavy_segs;
@@ -656,7 +580,7 @@ struct TripIter {
 };
 
 // G index groups (4 G gathers) per lane and trip, D trips of gathers in flight per warp, THREADS / 32 warps per SM.
-template <int POLICY, int G, int D, int THREADS>
+template <int G, int D, int THREADS>
 __device__ __forceinline__ void pr_sell_pipe_body(const SellArgs &a) {
   extern __shared__ float s_hot[];
   if (*a.done) return;
@@ -689,10 +613,10 @@ __device__ __forceinline__ void pr_sell_pipe_body(const SellArgs &a) {
   auto gather = [&](float (&W)[4 * G], const int4 (&X)[G], const TripDesc &d, float &Sc, int32_t &Dc) {
 #pragma unroll
     for (int u = 0; u < G; u++) {
-      W[4 * u + 0] = pull_one<POLICY>(a, s_hot_addr, s_hot, X[u].x, pol, pol_last);
-      W[4 * u + 1] = pull_one<POLICY>(a, s_hot_addr, s_hot, X[u].y, pol, pol_last);
-      W[4 * u + 2] = pull_one<POLICY>(a, s_hot_addr, s_hot, X[u].z, pol, pol_last);
-      W[4 * u + 3] = pull_one<POLICY>(a, s_hot_addr, s_hot, X[u].w, pol, pol_last);
+      W[4 * u + 0] = pull_one(a, s_hot_addr, X[u].x, pol, pol_last);
+      W[4 * u + 1] = pull_one(a, s_hot_addr, X[u].y, pol, pol_last);
+      W[4 * u + 2] = pull_one(a, s_hot_addr, X[u].z, pol, pol_last);
+      W[4 * u + 3] = pull_one(a, s_hot_addr, X[u].w, pol, pol_last);
     }
     if (d.fin == 1) {
       const int64_t j = (int64_t)d.ref * 32 + lane;
@@ -747,15 +671,9 @@ __device__ __forceinline__ void pr_sell_pipe_body(const SellArgs &a) {
   if (lane == 0) a.err_partial[a.err_slot0 + warp] = err;
 }
 
-template <int POLICY, int G, int D, int THREADS>
+template <int G, int D, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
-pr_sell_pipe(SellArgs a) { pr_sell_pipe_body<POLICY, G, D, THREADS>(a); }
-
-// The same iteration kernel sized to share an SM with pr_band_kernel<256> (band.cu): 768 threads at <= 64 registers
-// (49152 of the SM's 65536; the band CTA takes the other 16384) and a small hot table, so that the shared-memory-bound
-// band sums and the L1TEX-miss-path-bound main sums of an iteration overlap instead of running back to back.
-__global__ void __maxnreg__(64)
-pr_sell_pipe_co(SellArgs a) { pr_sell_pipe_body<1, 1, 2, 768>(a); }
+pr_sell_pipe(SellArgs a) { pr_sell_pipe_body<G, D, THREADS>(a); }
 
 // wide slices: the per-row partials of a slice's segments are added in a FIXED order -- the eight warps of a CTA each
 // add a contiguous run of segments in column order, warp 0 then adds the eight run sums in run order.  (One warp per
@@ -820,8 +738,8 @@ pr_sell_isolated(SellArgs a, float *contrib_other) {
     const float cv = deg != 0 ? __fdiv_rn(nw, (float)deg)
                               : (nw > 0.f ? __int_as_float(0x7f800000) : nw < 0.f ? __int_as_float(0xff800000) : __int_as_float(0x7fc00000));
     const int64_t id = row_newid(a, j);
-    __stcs(a.contrib_out + id, cv);
-    __stcs(contrib_other + id, cv);
+    contrib_store(a, id, cv, false);
+    contrib_store_other(a, contrib_other, id, cv);
   }
   err = warp_sum(err);
   if (lane == 0) a.err_partial[a.err_slot0 + warp] = err;
@@ -831,34 +749,39 @@ pr_sell_isolated(SellArgs a, float *contrib_other) {
 // once per solve: score = base (:28-32 with an empty sum) is their fixed point from the first iteration on (L1 delta
 // exactly 0 afterwards), so their |base - old| goes into the FIRST iteration's error partials and their constant
 // contrib into both buffers; the iteration kernels never touch them.  (Not when max_iter = 0: no iteration runs.)
+// abs_partial[warp] = sum |score| over the warp's rows: it bounds every partial sum of the solve (pr_run_sell) and so
+// fixes the scale of the banded layout's fixed-point accumulators.
 __global__ void __launch_bounds__(256, 4)
 pr_sell_load(const float *__restrict__ scores_user, const int32_t *__restrict__ perm, SellArgs a, float *contrib_other,
-             int settle_isolated) {
+             int settle_isolated, double *__restrict__ abs_partial) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  double err = 0.0;
+  double err = 0.0, tsum = 0.0;
   const float nw = __fadd_rn(a.base, __fmul_rn(a.damp, 0.f));
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < a.rows; j += (int64_t)gridDim.x * blockDim.x) {
     const float sc = scores_user[perm[j]];
     const int32_t deg = a.sout ? __ldcs(a.sout + j) : __ldcs(a.sdeg + j);
     const int64_t id = row_newid(a, j);
+    tsum += (double)fabsf(sc);
     if (j < a.n_nz_rows || !settle_isolated) {
       a.scores[j] = sc;
-      a.contrib_out[id] = __fdiv_rn(sc, (float)deg);
+      contrib_store(a, id, __fdiv_rn(sc, (float)deg), true);
     } else {
       __stcs(a.scores + j, nw);
       err += (double)fabsf(__fsub_rn(nw, sc));
       // x / 0 without the division slow path (symmetric graphs: every such row has out-degree 0 too)
       const float cv = deg != 0 ? __fdiv_rn(nw, (float)deg)
                                 : (nw > 0.f ? __int_as_float(0x7f800000) : nw < 0.f ? __int_as_float(0xff800000) : __int_as_float(0x7fc00000));
-      __stcs(a.contrib_out + id, cv);
-      __stcs(contrib_other + id, cv);
+      contrib_store(a, id, cv, false);
+      contrib_store_other(a, contrib_other, id, cv);
     }
   }
   if (settle_isolated) {
     err = warp_sum(err);
     if (lane == 0) a.err_partial[a.err_slot0 + warp] = err;
   }
+  tsum = warp_sum(tsum);
+  if (lane == 0) abs_partial[warp] = tsum;
 }
 __global__ void pr_sell_store(float *__restrict__ scores_user, const int32_t *__restrict__ perm,
                               const float *__restrict__ scores_sorted, int64_t rows) {
@@ -896,31 +819,76 @@ pr_reduce_err2(const double *__restrict__ partial, int n, double *err_trace, int
   }
 }
 
-int pull_exchange(gdn_graph *g, float *contrib, double *err_slot);   // comm.cu
+// fixed-order sum of n partials -> *out (one block)
+__global__ void __launch_bounds__(256)
+pr_reduce_sum(const double *__restrict__ partial, int n, double *out) {
+  __shared__ double s[256];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) acc += partial[i];
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = s[0];
+}
+// multi-GPU over NCCL: the stop test on the all-reduced delta
+__global__ void pr_check_done(const double *err_trace, int iter, double eps, int32_t *done) {
+  if (!*done && err_trace[iter] < eps) *done = iter + 1;
+}
+
+// comm.cu
+int pull_exchange(gdn_graph *g, float *contrib, double *err_slot);        // NCCL: two allgathers + allreduce of one double
+int pull_peer_setup(gdn_graph *g);                                        // map the other GPUs' vectors (IPC / peer access)
+bool pull_peer_ready(const gdn_graph *g);
+void pull_peer_args(const gdn_graph *g, int buf_out, SellArgs &a);        // a.n_peers, a.peer_out, a.peer_other
+// one block: reduce this GPU's partials, publish the sum to every GPU, barrier over the box (device-side flags), add the
+// sums in rank order -> err_trace[iter] (and the stop flag when eps >= 0); with partial == nullptr only the barrier
+int pull_peer_sync(gdn_graph *g, const double *partial, int n_partial, double *err_out, int iter, double eps, int32_t *done,
+                   cudaStream_t s);
+int pull_peer_check();
+
+// Scale of the banded layout's fixed-point accumulators (band.cu).  Every partial sum of the solve is bounded by
+// T = max(1, sum |scores_0|): sum_v |s_v^{k+1}| <= (1 - d) + d * sum_v |s_v^k| (src/pr/omp_base.cc:24-33 with every
+// gathered vertex of out-degree >= 1) and a row sums a subset of contrib = s / deg.  2^e with T * 2^e <= 2^62 keeps the
+// 64-bit accumulators in range; e is capped at 56 (the resolution round 1 shipped: 1.4e-17).  Returns 0 when the scores are
+// not finite or so large that fewer than 30 fraction bits are left: the caller then runs the solve on the plain layout.
+static double fix_scale_for(double tsum) {
+  if (!(tsum >= 0.0) || !(tsum < 1e300)) return 0.0;
+  const double bound = std::max(1.0, tsum) * 1.001;
+  int e = 0;
+  (void)frexp(bound, &e);                    // bound = f * 2^e, 0.5 <= f < 1  =>  bound < 2^e
+  const int bits = std::min(56, 62 - e);
+  if (bits < 30) return 0.0;
+  return ldexp(1.0, bits);
+}
 
 int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_iter, gdn_stats *st) {
   PullLayout &L = g->pull;
   GDN_CHECK(pull_build_sell(g));
   // banded shared-memory layout of the heavy rows (band.cu): resident graphs; GDN_PR_BANDS=0 turns it off
   const char *e_bands = getenv("GDN_PR_BANDS");
-  const bool bands_off = e_bands && atoi(e_bands) <= 0;
+  const bool bands_off = (e_bands && atoi(e_bands) <= 0) || L.exact;
   if (!g->one_shot && !bands_off) GDN_CHECK(band_build(g));
-  const bool banded = L.band.built && !bands_off;
+  bool banded = L.band.built && !bands_off;
   const BandLayout &bd = L.band;
   cudaStream_t s = lib().stream;
   const int sm = lib().sm_count;
-  const int wpc = kSellThreads / 32;             // err_partial slots per CTA (the pipelined variants use fewer warps)
-  const int32_t n_heavy_slices = banded ? bd.n_heavy_slices : L.n_heavy_slices;
-  const int fgrid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)n_heavy_slices, (int64_t)sm * 8));   // one CTA per wide slice
+  const int wpc = kSellThreads / 32;             // err_partial slots per CTA
+  const bool multi = L.P > 1;
+  const int32_t max_heavy_slices = std::max(L.n_heavy_slices, L.band.built ? bd.n_heavy_slices : 0);
+  const int fgrid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)max_heavy_slices, (int64_t)sm * 8));   // one CTA per wide slice
   const int igrid = sm * 8;                        // pr_sell_load's grid: its warps own the error partials of the settled rows
-  const int bgrid = banded ? band_finalize_grid(g) : 0;
+  const int bgrid = L.band.built ? band_finalize_grid(g) : 0;
   const int n_partial = sm * wpc + fgrid * 8 + igrid * 8 + bgrid * 8;
   if (!g->contrib[0]) {
     GDN_CUDA(cudaMalloc((void **)&g->contrib[0], sizeof(float) * (L.Mp + 64)));
     GDN_CUDA(cudaMalloc((void **)&g->contrib[1], sizeof(float) * (L.Mp + 64)));
     GDN_CUDA(cudaMalloc((void **)&g->scores_sorted, sizeof(float) * std::max<int64_t>(L.rows, 1)));
-    GDN_CUDA(cudaMalloc((void **)&g->err_trace, sizeof(double) * GDN_MAX_PR_ITER));
+    GDN_CUDA(cudaMalloc((void **)&g->err_trace, sizeof(double) * (GDN_MAX_PR_ITER + 8)));
     GDN_CUDA(cudaMalloc((void **)&g->pr_done, sizeof(int32_t)));
+    GDN_CUDA(cudaMalloc((void **)&g->abs_partial, sizeof(double) * igrid * 8));
     GDN_CUDA(cudaMemsetAsync(g->contrib[0], 0, sizeof(float) * (L.Mp + 64), s));
     GDN_CUDA(cudaMemsetAsync(g->contrib[1], 0, sizeof(float) * (L.Mp + 64), s));
     g->device_bytes += sizeof(float) * (2 * L.Mp + L.rows);
@@ -929,67 +897,22 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
       gather_i32<<<sm * 8, 256, 0, s>>>(g->out_degree, L.perm, L.sout, L.rows);
     }
   }
+  // row partition: map the other GPUs' vectors once per graph (GDN_PR_NCCL=1 keeps the NCCL collectives instead; they are
+  // also what runs when the mapping is not possible)
+  if (multi && !getenv("GDN_PR_NCCL") && pull_peer_setup(g) != GDN_OK) cudaGetLastError();
+  const bool peer = multi && pull_peer_ready(g);
   if (g->n_err_partial < n_partial) {
     if (g->err_partial) GDN_CUDA(cudaFree(g->err_partial));
     GDN_CUDA(cudaMalloc((void **)&g->err_partial, sizeof(double) * n_partial));
     g->n_err_partial = n_partial;
   }
   if (max_iter > GDN_MAX_PR_ITER - 1) max_iter = GDN_MAX_PR_ITER - 1;
-  size_t smem = sizeof(float) * (size_t)L.H;
-  // L2 residency tiers of the gathered vector (see pull_one); tunables for the profiling scripts
-  const char *e_pol = getenv("GDN_PR_POLICY"), *e_warm = getenv("GDN_PR_WARM_MB");
-  const int policy = e_pol ? atoi(e_pol) : 1;
-  const int64_t warm_ids = (int64_t)(e_warm ? atoi(e_warm) : 48) * (1 << 20) / 4;   // 48 MB measured best at Kron-26 (32: +4 %, 64: +5 %, 96: +17 %)
-  void (*kern)(SellArgs) = policy == 0 ? pr_sell_kernel<0> : policy == 2 ? pr_sell_kernel<2> : pr_sell_kernel<1>;
-  int threads = kSellThreads;
-  // GDN_PR_PIPE: 0 = one-trip kernel above; GDT = pipelined kernel, G index groups per trip, D trips in flight, T threads per SM
-  const char *e_pipe = getenv("GDN_PR_PIPE");
-  const int pipe = e_pipe ? atoi(e_pipe) : 121024;
-  if (policy == 1 && pipe != 0) {
-    switch (pipe) {     // GDT
-      case 22512: kern = pr_sell_pipe<1, 2, 2, 512>; threads = 512; break;
-      case 22640: kern = pr_sell_pipe<1, 2, 2, 640>; threads = 640; break;
-      case 22896: kern = pr_sell_pipe<1, 2, 2, 896>; threads = 896; break;
-      case 221024: kern = pr_sell_pipe<1, 2, 2, 1024>; threads = 1024; break;
-      case 42512: kern = pr_sell_pipe<1, 4, 2, 512>; threads = 512; break;
-      case 23768: kern = pr_sell_pipe<1, 2, 3, 768>; threads = 768; break;
-      case 23640: kern = pr_sell_pipe<1, 2, 3, 640>; threads = 640; break;
-      case 24512: kern = pr_sell_pipe<1, 2, 4, 512>; threads = 512; break;
-      case 131024: kern = pr_sell_pipe<1, 1, 3, 1024>; threads = 1024; break;
-      case 141024: kern = pr_sell_pipe<1, 1, 4, 1024>; threads = 1024; break;
-      case 13896: kern = pr_sell_pipe<1, 1, 3, 896>; threads = 896; break;
-      case 14768: kern = pr_sell_pipe<1, 1, 4, 768>; threads = 768; break;
-      case 22768: kern = pr_sell_pipe<1, 2, 2, 768>; threads = 768; break;
-      default: kern = pr_sell_pipe<1, 1, 2, 1024>; threads = 1024; break;   // measured best of the sweep (profiles/r1_pr_pipe_sweep.txt)
-    }
-  }
-  // GDN_PR_OVERLAP=1 (banded layout only): the band sums run on a second stream in 256-thread CTAs that share each SM
-  // with a 768-thread main CTA (pr_sell_pipe_co, 32 KB hot table)
-  const char *e_ovl = getenv("GDN_PR_OVERLAP");
-  const bool overlap = banded && !bd.seg && policy == 1 && pipe != 0 && (e_ovl ? atoi(e_ovl) > 0 : false);
-  static cudaStream_t s2 = nullptr;
-  static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  int32_t hot_n = (int32_t)L.H;
-  if (overlap) {
-    if (!s2) {
-      GDN_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
-      GDN_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-      GDN_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
-    }
-    const char *e_hot = getenv("GDN_PR_CO_HOT");
-    hot_n = (int32_t)std::min<int64_t>(L.H, e_hot ? atoi(e_hot) : 8192);
-    kern = pr_sell_pipe_co; threads = 768;
-    GDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  }
-  const char *e_persist = getenv("GDN_PR_PERSIST");
-  const int persist_mb = e_persist ? atoi(e_persist) : 0;
-  const bool persist = persist_mb > 0;
-  if (persist) {
-    cudaDeviceProp prop;
-    GDN_CUDA(cudaGetDeviceProperties(&prop, lib().device));
-    GDN_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize));
-  }
-  if (overlap) smem = sizeof(float) * (size_t)hot_n;
+  const size_t smem = sizeof(float) * (size_t)L.H;
+  // L2 residency tiers of the gathered vector (see pull_one): 48 MB measured best at Kron-26 (32: +4 %, 64: +5 %, 96: +17 %)
+  const char *e_warm = getenv("GDN_PR_WARM_MB");
+  const int64_t warm_ids = (int64_t)(e_warm ? atoi(e_warm) : 48) * (1 << 20) / 4;
+  // one index group per trip, two trips of gathers in flight, 32 warps per SM: best of the sweep (profiles/r1_pr_pipe_sweep.txt)
+  void (*kern)(SellArgs) = pr_sell_pipe<1, 2, kSellThreads>;
   GDN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
   SellArgs a = {};
@@ -997,73 +920,77 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
   a.heavy_seg = L.heavy_seg; a.heavy_slice = L.heavy_slice; a.heavy_first = L.heavy_first;
   a.n_heavy_segs = L.n_heavy_segs; a.n_heavy_slices = L.n_heavy_slices; a.partial = L.partial;
   a.scores = g->scores_sorted; a.sdeg = L.sdeg; a.sout = L.sout; a.rowid = L.rowid;
-  a.n_nz_rows = L.n_nz_rows; a.rows = L.rows; a.H = (int32_t)L.H; a.hot_n = hot_n; a.Hp = L.Hp; a.Wc = L.Wc; a.rank = L.R;
+  a.n_nz_rows = L.n_nz_rows; a.rows = L.rows; a.H = (int32_t)L.H; a.hot_n = (int32_t)L.H; a.Hp = L.Hp; a.Wc = L.Wc; a.rank = L.R;
   a.base = (1.0f - damp) / (float)(int32_t)g->m;            // src/pr/omp_base.cc:16
   a.damp = damp; a.err_partial = g->err_partial; a.done = g->pr_done;
-  if (banded) {
-    a.sell = bd.sell; a.slice_ptr = bd.slice_ptr; a.chunk_slice = bd.chunk_slice; a.n_chunks = bd.n_chunks;
-    a.heavy_seg = bd.heavy_seg; a.heavy_slice = bd.heavy_slice; a.heavy_first = bd.heavy_first;
-    a.n_heavy_segs = bd.n_heavy_segs; a.n_heavy_slices = bd.n_heavy_slices; a.partial = bd.partial;
-    a.n_band_rows = bd.n_rows; a.acc_main = bd.acc_main;
-  }
+  a.group_ch = L.group_ch;
   a.P = L.P; a.inv_wc = L.Wc > 0 ? 1.0f / (float)L.Wc : 0.f;
   // the warm budget is shared by the ranks' slices (tier_id): every rank's hottest cold ids stay L2-resident
   a.warm = (int32_t)std::min<int64_t>(L.P > 1 ? L.H + std::max<int64_t>(warm_ids - L.H, 0) / L.P : warm_ids, 0x7fffffff);
-  const char *e_skip = getenv("GDN_PR_SKIP_FROM_MB");
-  a.skip_from = e_skip ? (int32_t)std::min<int64_t>((int64_t)atoi(e_skip) * (1 << 20) / 4, 0x7fffffff) : 0x7fffffff;
-  a.warm = std::min(a.warm, a.skip_from);
-  double *h_err = (double *)lib().pinned;
+  double *h_err = (double *)lib().pinned;          // [GDN_MAX_PR_ITER]: one slot per iteration; the last one takes sum |scores_0|
+  double *h_tsum = h_err + (GDN_MAX_PR_ITER - 1);
   int64_t launches = 0;
-  const bool multi = L.P > 1;
 
   kev_reset();
   GDN_CUDA(cudaEventRecord(lib().ev0, s));
   GDN_CUDA(cudaMemsetAsync(g->pr_done, 0, sizeof(int32_t), s));
   GDN_CUDA(cudaMemsetAsync(g->err_partial, 0, sizeof(double) * n_partial, s));
-  if (banded) GDN_CHECK(band_solve_begin(g, s));
   a.contrib_out = g->contrib[0];
+  if (peer) pull_peer_args(g, 0, a);
   // rows without in-edges: settled by pr_sell_load (symmetric graph) or by pr_sell_isolated after the first iteration
   const bool have_iso = max_iter > 0 && L.rows > L.n_nz_rows;
   const int settle = (have_iso && !a.sout) ? 1 : 0;
   a.err_slot0 = sm * wpc + fgrid * 8;
-  pr_sell_load<<<igrid, 256, 0, s>>>(d_scores, L.perm, a, g->contrib[1], settle);
+  pr_sell_load<<<igrid, 256, 0, s>>>(d_scores, L.perm, a, g->contrib[1], settle, g->abs_partial);
   launches++;
-  GDN_CHECK(pull_exchange(g, g->contrib[0], nullptr));
-  int iter, cur = 0;
-  for (iter = 0; iter < max_iter; iter++) {
+  double fix_scale = 0.0;
+  if (banded) {
+    // the fixed-point range of the band accumulators follows the caller's scores (src/pr/omp_base.cc:24 accepts any vector)
+    double *d_tsum = g->err_trace + GDN_MAX_PR_ITER;
+    pr_reduce_sum<<<1, 256, 0, s>>>(g->abs_partial, igrid * 8, d_tsum);
+    launches++;
+    if (peer) GDN_CHECK(pull_peer_sync(g, d_tsum, 1, d_tsum, 0, -1.0, nullptr, s));
+    else GDN_CHECK(pull_exchange(g, g->contrib[0], d_tsum));
+    GDN_CUDA(cudaMemcpyAsync(h_tsum, d_tsum, sizeof(double), cudaMemcpyDeviceToHost, s));
+    GDN_CUDA(cudaStreamSynchronize(s));
+    fix_scale = fix_scale_for(*h_tsum);
+    if (fix_scale == 0.0) banded = false;          // out of range for the accumulators: this solve walks the plain layout
+  } else {
+    if (peer) GDN_CHECK(pull_peer_sync(g, nullptr, 0, nullptr, 0, -1.0, nullptr, s));
+    else GDN_CHECK(pull_exchange(g, g->contrib[0], nullptr));
+  }
+  const int32_t n_heavy_slices = banded ? bd.n_heavy_slices : L.n_heavy_slices;
+  if (banded) {
+    a.sell = bd.sell; a.slice_ptr = bd.slice_ptr; a.chunk_slice = bd.chunk_slice; a.n_chunks = bd.n_chunks;
+    a.heavy_seg = bd.heavy_seg; a.heavy_slice = bd.heavy_slice; a.heavy_first = bd.heavy_first;
+    a.n_heavy_segs = bd.n_heavy_segs; a.n_heavy_slices = bd.n_heavy_slices; a.partial = bd.partial;
+    a.n_band_rows = bd.n_rows; a.acc_main = bd.acc_main;
+    GDN_CHECK(band_solve_begin(g, s));
+  }
+  if (st) st->pr_layout = banded ? (bd.seg ? 2 : 1) : 0;
+
+  // The host runs kLook iterations ahead of the device: iteration k + kLook is queued before the delta of iteration k is
+  // read (the kernels of an iteration queued after convergence return at once on the device-side `done` flag), so the
+  // stream never drains between iterations.  Over NCCL the stop test needs the all-reduced delta and the collectives of a
+  // dead iteration would still run: no look-ahead there.
+  const int kLook = (multi && !peer) ? 0 : 2;
+  constexpr int kRing = 4;
+  if (!lib().pr_ev[0])
+    for (int i = 0; i < kRing; i++) GDN_CUDA(cudaEventCreateWithFlags(&lib().pr_ev[i], cudaEventDisableTiming));
+  auto enqueue = [&](int iter) -> int {
+    const int cur = iter & 1;
     a.contrib_in = g->contrib[cur];
     a.contrib_out = g->contrib[cur ^ 1];
+    if (peer) pull_peer_args(g, cur ^ 1, a);
     a.err_slot0 = 0;
-    if (persist) {
-      // L2 set-aside for the warm prefix of the vector being gathered (experiment, GDN_PR_PERSIST=1)
-      cudaStreamAttrValue av = {};
-      av.accessPolicyWindow.base_ptr = (void *)(g->contrib[cur] + L.H);
-      av.accessPolicyWindow.num_bytes = (size_t)std::min<int64_t>((int64_t)persist_mb << 20, (L.Mp - L.H) * 4);
-      av.accessPolicyWindow.hitRatio = 1.0f;
-      av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-      av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-      GDN_CUDA(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av));
-    }
     kev_begin();
     if (banded) {
-      if (overlap) {
-        GDN_CUDA(cudaEventRecord(ev_fork, s));
-        GDN_CUDA(cudaStreamWaitEvent(s2, ev_fork, 0));
-        GDN_CHECK(band_launch(g, a, s2, true));
-        GDN_CUDA(cudaEventRecord(ev_join, s2));
-      } else {
-        GDN_CHECK(band_launch(g, a, s, false));
-      }
+      GDN_CHECK(band_launch(g, a, fix_scale, s));
       launches += band_launches(g);
     }
-    kern<<<sm, threads, smem, s>>>(a);
+    kern<<<sm, kSellThreads, smem, s>>>(a);
     if (!banded) kev_end();
     launches++;
-    if (persist) {
-      cudaStreamAttrValue av = {};
-      av.accessPolicyWindow.num_bytes = 0;
-      GDN_CUDA(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av));
-    }
     if (n_heavy_slices > 0) {
       a.err_slot0 = sm * wpc;
       pr_sell_finalize<<<fgrid, 256, 0, s>>>(a);
@@ -1072,8 +999,7 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
     if (banded) {
       // the iteration of the banded layout is band sums + main sums + the two finalize launches: timed as one
       a.err_slot0 = sm * wpc + fgrid * 8 + igrid * 8;
-      if (overlap) GDN_CUDA(cudaStreamWaitEvent(s, ev_join, 0));
-      GDN_CHECK(band_finalize_launch(g, a, bgrid, s));
+      GDN_CHECK(band_finalize_launch(g, a, fix_scale, bgrid, s));
       kev_end();
       launches++;
     }
@@ -1084,14 +1010,31 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
     } else if (have_iso && iter == 1) {            // the settled rows' deltas belonged to the first iteration
       GDN_CUDA(cudaMemsetAsync(g->err_partial + sm * wpc + fgrid * 8, 0, sizeof(double) * igrid * 8, s));
     }
-    pr_reduce_err2<<<1, 256, 0, s>>>(g->err_partial, n_partial, g->err_trace, iter, multi ? -1.0 : eps, g->pr_done);
-    launches++;
-    GDN_CHECK(pull_exchange(g, g->contrib[cur ^ 1], g->err_trace + iter));
-    GDN_CUDA(cudaMemcpyAsync(h_err, g->err_trace + iter, sizeof(double), cudaMemcpyDeviceToHost, s));
-    GDN_CUDA(cudaStreamSynchronize(s));
-    if (st) st->pr_err[iter] = *h_err;
-    cur ^= 1;
-    if (*h_err < eps) break;                                 // src/pr/omp_base.cc:36
+    if (peer) {
+      GDN_CHECK(pull_peer_sync(g, g->err_partial, n_partial, g->err_trace, iter, eps, g->pr_done, s));
+      launches++;
+    } else {
+      pr_reduce_err2<<<1, 256, 0, s>>>(g->err_partial, n_partial, g->err_trace, iter, multi ? -1.0 : eps, g->pr_done);
+      launches++;
+      if (multi) {
+        GDN_CHECK(pull_exchange(g, g->contrib[cur ^ 1], g->err_trace + iter));
+        pr_check_done<<<1, 1, 0, s>>>(g->err_trace, iter, eps, g->pr_done);
+        launches++;
+      }
+    }
+    GDN_CUDA(cudaMemcpyAsync(h_err + iter, g->err_trace + iter, sizeof(double), cudaMemcpyDeviceToHost, s));
+    GDN_CUDA(cudaEventRecord(lib().pr_ev[iter % kRing], s));
+    return GDN_OK;
+  };
+  int queued = 0, checked = 0, last = max_iter;      // last = index of the iteration that met the stop test (max_iter: none did)
+  for (;;) {
+    while (queued < max_iter && queued - checked <= kLook) { GDN_CHECK(enqueue(queued)); queued++; }
+    if (checked == queued) break;
+    GDN_CUDA(cudaEventSynchronize(lib().pr_ev[checked % kRing]));
+    const double err = h_err[checked];
+    if (st) st->pr_err[checked] = err;
+    if (err < eps) { last = checked; break; }                // src/pr/omp_base.cc:36
+    checked++;
   }
   if (L.P == 1 && L.symmetric_order && L.rows == g->m && !L.rowid)
     pr_sell_store_gather<<<sm * 8, 256, 0, s>>>(d_scores, L.newid, g->scores_sorted, g->m, L.n_nz_rows,
@@ -1102,13 +1045,14 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
   GDN_CUDA(cudaEventRecord(lib().ev1, s));
   GDN_CUDA(cudaStreamSynchronize(s));
   GDN_CUDA(cudaGetLastError());
+  if (peer) GDN_CHECK(pull_peer_check());
   if (st) {
     float ms = 0;
     GDN_CUDA(cudaEventElapsedTime(&ms, lib().ev0, lib().ev1));
     st->solve_ms = ms;
     st->kernel_launches = launches;
-    st->iterations = iter + 1;                               // printf("iterations = %d", iter+1), :38
-    kev_collect(st);
+    st->iterations = last + 1;                               // printf("iterations = %d", iter+1), :38
+    kev_collect(st, std::min(last + 1, max_iter));           // (iterations queued past the stop test were no-ops)
   }
   return GDN_OK;
 }

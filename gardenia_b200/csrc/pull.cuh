@@ -7,6 +7,7 @@ namespace gdn {
 constexpr int kHotMax = 49152;          // fp32 entries in the shared-memory table (192 KB)
 constexpr int kGroupCh = 1024;          // int4 groups per work item (= 4096 column ids)
 constexpr int kSellThreads = 1024;      // one CTA per SM
+constexpr int kMaxPeers = 7;            // other GPUs of one box whose vectors a row epilogue writes
 
 struct SellArgs {
   const int4 *sell;
@@ -35,11 +36,15 @@ struct SellArgs {
   int32_t warm;                // ids whose tier_id is below this are kept L2-resident; colder ids are gathered evict-first
   int32_t P;                   // ranks of the row partition the id space was laid out for
   float inv_wc;                // 1 / Wc
-  int32_t skip_from;           // TIMING EXPERIMENT ONLY (GDN_PR_SKIP_FROM_MB): ids at or above this are not gathered (wrong results)
+  uint32_t group_ch;           // int4 groups per work item; slices wider than this are cut into segments (0xffffffff: never, exact order)
   // banded layout (band.cu): sorted rows below n_band_rows (a multiple of 32) only deposit the sum over the columns left
   // in the main array; pr_band_finalize adds their band partials and runs the row epilogue
   int64_t n_band_rows;
   float *acc_main;
+  // row partition with peer-mapped vectors: contrib_out / the other buffer of the n_peers OTHER GPUs
+  int32_t n_peers;
+  float *peer_out[kMaxPeers];
+  float *peer_other[kMaxPeers];
 };
 
 __device__ __forceinline__ int64_t row_newid(const SellArgs &a, int64_t j) {
@@ -60,6 +65,23 @@ __device__ __forceinline__ int32_t tier_id(const SellArgs &a, int32_t c) {
   return c;
 }
 
+// New contrib of the row that owns new id `id`: into this GPU's vector and, in a row partition with peer-mapped
+// vectors (comm.cu pull_peer_setup), straight into every other GPU's copy over NVLink -- the exchange of SURVEY 8(e)
+// fused into the row epilogue, no collective afterwards.  Lanes of a warp own consecutive ids: 128-byte stores.
+__device__ __forceinline__ void contrib_store(const SellArgs &a, int64_t id, float cv, bool warm) {
+  if (warm) a.contrib_out[id] = cv; else __stcs(a.contrib_out + id, cv);
+#pragma unroll
+  for (int p = 0; p < kMaxPeers; p++)
+    if (p < a.n_peers) a.peer_out[p][id] = cv;
+}
+// (rows settled once per solve also seed the OTHER buffer of the double-buffered vector, on every GPU)
+__device__ __forceinline__ void contrib_store_other(const SellArgs &a, float *contrib_other, int64_t id, float cv) {
+  __stcs(contrib_other + id, cv);
+#pragma unroll
+  for (int p = 0; p < kMaxPeers; p++)
+    if (p < a.n_peers) a.peer_other[p][id] = cv;
+}
+
 // scores[dst] = base + damp * sum; error += |new - old|; next contrib   (src/pr/omp_base.cc:24-25,31-33)
 __device__ __forceinline__ void pr_epilogue_pre(const SellArgs &a, int64_t j, float acc, double &err, float old_score, int32_t deg) {
   // scores / sdeg are touched once per iteration: streaming (evict-first) accesses keep them from
@@ -70,7 +92,7 @@ __device__ __forceinline__ void pr_epilogue_pre(const SellArgs &a, int64_t j, fl
   err += (double)fabsf(__fsub_rn(nw, old_score));
   const int64_t id = row_newid(a, j);
   const float cv = __fdiv_rn(nw, (float)deg);
-  if (tier_id(a, (int32_t)id) < a.warm) a.contrib_out[id] = cv; else __stcs(a.contrib_out + id, cv);
+  contrib_store(a, id, cv, tier_id(a, (int32_t)id) < a.warm);
 }
 __device__ __forceinline__ void pr_epilogue_core(const SellArgs &a, int64_t j, float acc, double &err) {
   const float old_score = __ldcs(a.scores + j);
@@ -85,8 +107,8 @@ __device__ __forceinline__ void pr_epilogue(const SellArgs &a, int64_t j, float 
 // band.cu
 int band_build(gdn_graph *g);
 void band_free(BandLayout &b);
-int band_launch(gdn_graph *g, const SellArgs &a, cudaStream_t s, bool co_resident);                       // the band partial sums of one iteration
-int band_finalize_launch(gdn_graph *g, const SellArgs &a, int grid, cudaStream_t s);    // + main sums -> row epilogue
+int band_launch(gdn_graph *g, const SellArgs &a, double fix_scale, cudaStream_t s);    // the band partial sums of one iteration
+int band_finalize_launch(gdn_graph *g, const SellArgs &a, double fix_scale, int grid, cudaStream_t s);    // + main sums -> row epilogue
 int band_finalize_grid(const gdn_graph *g);
 int band_launches(const gdn_graph *g);
 int band_solve_begin(gdn_graph *g, cudaStream_t s);

@@ -149,6 +149,12 @@ class DeviceGraph:
         keys = ["banded", "bands", "band_ids", "band_rows", "band_entries", "band_pairs", "band_items", "main_groups"]
         return dict(zip(keys, list(a)))
 
+    def prep_ms(self):
+        """Wall time of the once-per-graph preprocessing (untimed by the solves): create, SELL build, band build, BFS copy."""
+        a = (C.c_double * 4)()
+        check(lib.gdn_graph_prep_ms(self._h, C.byref(a)))
+        return dict(zip(["create", "sell_build", "band_build", "bfs_hubs_first"], [float(x) for x in a]))
+
     def close(self):
         if getattr(self, "_h", None):
             lib.gdn_graph_destroy(self._h)

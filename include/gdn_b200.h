@@ -75,6 +75,7 @@ typedef struct {
   int64_t h2d_bytes, d2h_bytes;
   int64_t edges_reached;    /* BFS: sum of out-degree over reached vertices (directed entries) */
   int64_t vertices_reached; /* BFS */
+  int64_t pr_layout;        /* PR: layout this solve walked (0 plain SELL / CSR, 1 banded, 2 segmented) */
   double pr_err[GDN_MAX_PR_ITER];          /* PR: per-iteration L1 delta (the reference's printed trace) */
   gdn_bfs_step steps[GDN_MAX_BFS_STEPS];   /* BFS */
 } gdn_stats;
@@ -90,6 +91,15 @@ const char *gdn_last_error(void);
 int gdn_init(int device);
 int gdn_finalize(void);
 int gdn_device_count(void);   /* 0 when no driver / device */
+/* One-shot calls park their device blocks (>= 1 MB) in a bounded arena instead of freeing them, so that the next
+ * call on the same graph allocates nothing (csrc/pool.cu).  A process that shares the device with another allocator
+ * calls this to hand the parked memory back; GDN_DEVICE_ARENA=0 in the environment turns the arena off. */
+int gdn_device_trim(void);
+/* PageRank summation order.  0 (default): rows are summed in the layout's order (heavy rows band by band / segment by
+ * segment: within the 1e-6 L1 bar, not bit-identical).  1: graphs created from now on sum EVERY row sequentially in
+ * column order, bit-identical to src/pr/omp_base.cc:28-30 (slower on skewed graphs: a hub row is one lane's work).
+ * GDN_PR_EXACT=1 in the environment sets the default. */
+int gdn_set_pr_exact_order(int on);
 
 /* ---- one-shot solvers: HOST pointers, drop-in for the reference solvers ------
  * Upload, solve, download and free inside the call (ownership as in
@@ -145,6 +155,9 @@ int gdn_graph_info(const gdn_graph *g, int64_t info[8]);
  * info[4]=column ids served from shared-memory bands info[5]=(row, band) pairs info[6]=band work items
  * info[7]=int4 groups of the main SELL array in use */
 int gdn_graph_pull_info(const gdn_graph *g, int64_t info[8]);
+/* Wall time of the (untimed, once per graph) preprocessing: ms[0] = gdn_graph_create (upload + host layout tables),
+ * ms[1] = SELL array build, ms[2] = banded / segmented layout build, ms[3] = BFS hubs-first copy. */
+int gdn_graph_prep_ms(const gdn_graph *g, double ms[4]);
 /* Host-only probe of the banded layout's id -> band map over the id space
  * [hot prefix of H ids | P cold slices of Wc ids] (csrc/band.cu band_of / band_range): *band_out = band of new id `id`
  * (-1: beyond the first B bands), *local_out = its 16-bit index inside the band, *start_out / *len_out = the band's id range. */

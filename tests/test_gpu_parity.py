@@ -174,12 +174,21 @@ def test_edge_shapes(shape):
     if shape in ("star", "heavy_rows"):
         # Thousands of (near-)EQUAL addends summed sequentially in fp32 (src/pr/omp_base.cc:28-30)
         # carry a systematic rounding bias that keeps the reference's own L1 delta above 1e-4 for
-        # all 100 iterations (it prints `iterations = 101`); our segment-wise sum of a heavy row
-        # is more accurate and converges.  Not reproducible without serialising the row, so the
-        # bar here is the reference's own acceptance test (PRVerifier residual,
-        # src/pr/verifier.cc:40-54).  See DESIGN.md "known deviations".
+        # all 100 iterations (it prints `iterations = 101`); the default layout sums a heavy row
+        # segment by segment, which is more accurate and converges (reference's own acceptance
+        # test, PRVerifier residual, src/pr/verifier.cc:40-54, holds).  The exact-order mode sums
+        # every row in column order in one lane and reproduces the reference bit for bit,
+        # including its 101 iterations.
         assert oit == 101 and st.iterations < 101
         assert po.pr_residual(m, rp, ci, scores) < 1e-4
+        _lib.check(_lib.lib.gdn_set_pr_exact_order(1))
+        try:
+            ex = np.full(m, np.float32(1.0) / np.float32(m), dtype=np.float32)
+            st_ex = gb.PRSolver(g, ex, verbose=False)
+        finally:
+            _lib.check(_lib.lib.gdn_set_pr_exact_order(0))
+        assert st_ex.iterations == oit == 101
+        assert np.array_equal(ex, oscores), "exact-order mode must be bit-identical to pr_omp_base"
     else:
         assert st.iterations == oit
         assert float(np.abs(scores.astype(np.float64) - oscores.astype(np.float64)).sum()) <= PR_L1_TOL
@@ -384,27 +393,6 @@ def test_pr_banded_layout(monkeypatch, kind, scale, bands, band_ids, cmin, dmin)
     l1 = float(np.abs(s1.cpu().numpy().astype(np.float64) - oscores.astype(np.float64)).sum())
     assert l1 <= PR_L1_TOL, l1
     assert po.pr_residual(m, rp, ci, s1.cpu().numpy()) < 1e-4                       # PRVerifier
-    # the other pipe variants and the one-trip kernel walk the same banded layout
-    for pipe in ("0", "22768"):
-        monkeypatch.setenv("GDN_PR_PIPE", pipe)
-        s3 = torch.full((m,), float(np.float32(1.0) / np.float32(m)), dtype=torch.float32, device="cuda")
-        st3 = dg.pagerank(s3)
-        assert st3.iterations == oit and torch.equal(s3, s1), pipe
-    monkeypatch.delenv("GDN_PR_PIPE")
-    # band sums and main sums on two streams, sharing each SM (pr_band_kernel<.,256> + pr_sell_pipe_co): same sums
-    for ovl in ("1", "0"):
-        monkeypatch.setenv("GDN_PR_OVERLAP", ovl)
-        s3 = torch.full((m,), float(np.float32(1.0) / np.float32(m)), dtype=torch.float32, device="cuda")
-        st3 = dg.pagerank(s3)
-        assert st3.iterations == oit and torch.equal(s3, s1), ("overlap", ovl)
-    monkeypatch.delenv("GDN_PR_OVERLAP")
-    # the slot finalize (per-row gather of the band partials) instead of the fixed-point accumulators: same bar
-    monkeypatch.setenv("GDN_PR_BAND_FIN", "0")
-    s5 = torch.full((m,), float(np.float32(1.0) / np.float32(m)), dtype=torch.float32, device="cuda")
-    st5 = dg.pagerank(s5)
-    assert st5.iterations == oit
-    assert float(np.abs(s5.cpu().numpy().astype(np.float64) - oscores.astype(np.float64)).sum()) <= PR_L1_TOL
-    monkeypatch.delenv("GDN_PR_BAND_FIN")
     # switching the layout off on the same graph falls back to the plain array
     monkeypatch.setenv("GDN_PR_BANDS", "0")
     s4 = torch.full((m,), float(np.float32(1.0) / np.float32(m)), dtype=torch.float32, device="cuda")
@@ -469,22 +457,66 @@ def test_pr_banded_layout_directed(monkeypatch):
     dg.close()
 
 
-def test_spmv_tma_variant(monkeypatch):
-    """The TMA-staged SpMV (cp.async.bulk + mbarrier) computes the same rows as the register-staged kernel."""
+def test_pr_exact_order_mode_is_bit_identical():
+    """gdn_set_pr_exact_order(1): every row -- hub rows included -- is summed sequentially in column order by one lane
+    (no wide-slice segments, no bands), so scores are bit-identical to src/pr/omp_base.cc:28-33 and the L1 trace agrees
+    to the last printed digit; one-shot and resident entry points alike."""
     import torch
-    for kind, scale in (("u", 16), ("g", 16)):
-        g = gb.Graph.generate(kind, scale, 16)
-        m = g.m
-        dg = gb.DeviceGraph(g)
-        Ax = torch.from_numpy(gb.fill_uniform(13, g.nnz)).cuda()
-        x = torch.from_numpy(gb.fill_uniform(14, m)).cuda()
-        y0 = torch.from_numpy(gb.fill_uniform(15, m)).cuda()
-        ya, yb = y0.clone(), y0.clone()
-        dg.spmv(Ax, x, ya)
-        monkeypatch.setenv("GDN_SPMV_TMA", "1")
-        dg.spmv(Ax, x, yb)
-        monkeypatch.delenv("GDN_SPMV_TMA")
-        oy = po.spmv(m, g.out_rowptr(), g.out_colidx(), Ax.cpu().numpy(), x.cpu().numpy(), y0.cpu().numpy())
-        assert _rel(yb.cpu().numpy(), oy) <= SPMV_REL_TOL
-        assert _rel(ya.cpu().numpy(), oy) <= SPMV_REL_TOL
-        dg.close()
+    _lib.check(_lib.lib.gdn_set_pr_exact_order(1))
+    try:
+        for kind, scale in (("g", 16), ("u", 14), ("g", 18)):
+            g = gb.Graph.generate(kind, scale, 16)
+            m, rp, ci = g.m, g.out_rowptr(), g.out_colidx()
+            oscores, oit, otrace = po.pr_pull(m, rp, ci, g.out_degrees())
+            hs = np.full(m, np.float32(1.0) / np.float32(m), dtype=np.float32)
+            st = gb.PRSolver(g, hs, verbose=False)
+            assert st.iterations == oit and np.array_equal(hs, oscores), (kind, scale)
+            dg = gb.DeviceGraph(g)
+            ds = torch.full((m,), float(np.float32(1.0) / np.float32(m)), dtype=torch.float32, device="cuda")
+            st2 = dg.pagerank(ds)
+            assert st2.pr_layout == 0 and dg.pull_info()["banded"] == 0
+            assert st2.iterations == oit and np.array_equal(ds.cpu().numpy(), oscores), (kind, scale)
+            np.testing.assert_allclose(st2.pr_trace(), otrace[:oit], rtol=1e-9, atol=1e-12)
+            dg.close()
+    finally:
+        _lib.check(_lib.lib.gdn_set_pr_exact_order(0))
+
+
+@pytest.mark.parametrize("start", ["ones", "large", "tiny", "signed", "huge", "inf"])
+def test_pr_banded_accepts_any_start_vector(start):
+    """src/pr/omp_base.cc:24-33 accepts any initial vector.  The banded layout's fixed-point accumulators take their
+    scale from sum |scores_0| of the solve, so un-normalised vectors stay in range (a hub row of a star / Kronecker graph
+    sums far more than 128 when every score is 1.0); vectors the accumulators cannot hold run on the plain layout."""
+    import torch
+    g = gb.Graph.generate("g", 16, 16)
+    m, rp, ci = g.m, g.out_rowptr(), g.out_colidx()
+    rng = np.random.default_rng(3)
+    s0 = {"ones": np.ones(m, np.float32),
+          "large": (rng.random(m) * 1000).astype(np.float32),
+          "tiny": np.full(m, 1e-12, np.float32),
+          "signed": (rng.random(m) - 0.5).astype(np.float32),
+          "huge": np.full(m, 1e30, np.float32),
+          "inf": np.where(np.arange(m) == 5, np.inf, 1.0 / m).astype(np.float32)}[start]
+    dg = gb.DeviceGraph(g)
+    ds = torch.from_numpy(s0.copy()).cuda()
+    st = dg.pagerank(ds, max_iter=5)
+    assert dg.pull_info()["banded"] == 1
+    assert st.pr_layout == (0 if start in ("huge", "inf") else 1), st.pr_layout
+    oscores, oit, _ = po.pr_pull(m, rp, ci, g.out_degrees(), scores=s0.copy(), max_iter=5)
+    got = ds.cpu().numpy()
+    assert st.iterations == oit
+    if start == "inf":
+        assert np.array_equal(np.isfinite(got), np.isfinite(oscores))
+        fin = np.isfinite(oscores)
+        assert np.allclose(got[fin], oscores[fin], rtol=1e-5, atol=0)
+    else:
+        # same relative bar as the normalised case: 1e-6 of the vector's own L1 mass
+        scale = max(float(np.abs(oscores.astype(np.float64)).sum()), 1e-300)
+        assert float(np.abs(got.astype(np.float64) - oscores.astype(np.float64)).sum()) / scale <= PR_L1_TOL
+    # a second solve with a normalised vector on the same graph is back on the banded layout
+    ds2 = torch.full((m,), float(np.float32(1.0) / np.float32(m)), dtype=torch.float32, device="cuda")
+    st2 = dg.pagerank(ds2)
+    o2, oit2, _ = po.pr_pull(m, rp, ci, g.out_degrees())
+    assert st2.pr_layout == 1 and st2.iterations == oit2
+    assert float(np.abs(ds2.cpu().numpy().astype(np.float64) - o2.astype(np.float64)).sum()) <= PR_L1_TOL
+    dg.close()

@@ -29,10 +29,19 @@ def test_header_symbols_exported():
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
 
 
-def test_stats_struct_layout_matches_header():
-    # sizeof(gdn_stats): 2*4 + 3*8 + 8 + 8 + 8 + 4*8 + 128*8 + 256*48
-    assert C.sizeof(_lib.Stats) == 8 + 24 + 24 + 32 + 128 * 8 + 256 * 48
-    assert C.sizeof(_lib.BfsStep) == 48
+def test_stats_struct_layout_matches_header(tmp_path):
+    """The ctypes mirror of gdn_stats has the size and field offsets the C compiler gives include/gdn_b200.h."""
+    import subprocess
+    fields = [n for n, _ in _lib.Stats._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "gdn_b200.h"\nint main(void){\n'
+                   'printf("%zu %zu\\n", sizeof(gdn_stats), sizeof(gdn_bfs_step));\n'
+                   + "".join(f'printf("%zu\\n", offsetof(gdn_stats, {f}));\n' for f in fields) + "return 0;}\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert [C.sizeof(_lib.Stats), C.sizeof(_lib.BfsStep)] == [int(out[0]), int(out[1])]
+    assert [getattr(_lib.Stats, f).offset for f in fields] == [int(x) for x in out[2:]]
 
 
 @pytest.mark.skipif(_lib.lib.gdn_device_count() > 0, reason="a GPU is present")
