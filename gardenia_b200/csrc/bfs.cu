@@ -20,9 +20,11 @@
 //    packed edge-by-edge onto lanes via a warp prefix sum; queue appends are
 //    warp-aggregated (one atomicAdd per warp per round).
 #include "common.cuh"
+#include <cooperative_groups.h>
 #include <cstdlib>
 #include <algorithm>
 #include <chrono>
+namespace cg = cooperative_groups;
 
 namespace gdn {
 
@@ -41,6 +43,25 @@ struct BfsCounters {
   long long bu_edges;   // BU: in-edges probed; TD: edges of the frontier (roofline accounting)
   long long bu_scanned; // BU: unvisited vertices swept
   unsigned long long heavy_pack;   // high 32: deferred rows, low 32: their 128-edge pieces (ONE atomic allocates both)
+  int b2q_tail;         // queue length produced by a bitmap -> queue conversion (device-side controller)
+  unsigned int ticket;  // blocks that have finished the current phase (device-side controller)
+};
+
+// Device-resident state of the direction-optimizing controller (src/bfs/omp_beamer.cc:129-160) -- bfs_persist below.
+enum { kModeTD = 0, kModeBU = 1, kModeDone = 2 };
+enum { kConvNone = 0, kConvQ2B = 1, kConvB2Q = 2 };
+struct BfsCtrl {
+  long long edges_to_check, scout_count, old_awake;
+  long long reached, reached_deg;
+  long long bu_ns;        // time spent in bottom-up sweeps (globaltimer), for the roofline's kernel share
+  int n_front;            // |frontier| about to be expanded
+  int mode, convert;
+  int cur;                // queue holding the frontier
+  int fb;                 // bitmap holding the frontier
+  int level, iter, n_steps;
+  int aborted;            // safety net: more steps than vertices
+  int pad;
+  gdn_bfs_step steps[GDN_MAX_BFS_STEPS];
 };
 
 struct BfsState {
@@ -154,10 +175,8 @@ __device__ __forceinline__ long long td_visit4(const OffT *__restrict__ rowptr, 
 
 // TDStep, src/bfs/omp_beamer.cc:35-58.
 template <typename OffT>
-__global__ void __launch_bounds__(256, 4)
-td_expand(const OffT *__restrict__ rowptr, const int32_t *__restrict__ col, const int32_t *__restrict__ q_in,
-          int n_in, BfsState s, int32_t *heavy_q, uint32_t *heavy_off, uint32_t heavy_cut, int level) {
-  if (n_in < 0) n_in = s.cnt->tail;       // partitioned mode: queue length lives on the device
+__device__ __forceinline__ void td_expand_dev(const OffT *__restrict__ rowptr, const int32_t *__restrict__ col, const int32_t *q_in,
+                                              int n_in, const BfsState &s, int32_t *heavy_q, uint32_t *heavy_off, uint32_t heavy_cut, int level) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -218,21 +237,26 @@ td_expand(const OffT *__restrict__ rowptr, const int32_t *__restrict__ col, cons
   if (lane == 0 && scout) atomicAdd((unsigned long long *)&s.cnt->scout, (unsigned long long)scout);
   if (lane == 0 && edges) atomicAdd((unsigned long long *)&s.cnt->bu_edges, (unsigned long long)edges);
 }
+template <typename OffT>
+__global__ void __launch_bounds__(256, 4)
+td_expand(const OffT *__restrict__ rowptr, const int32_t *__restrict__ col, const int32_t *__restrict__ q_in,
+          int n_in, BfsState s, int32_t *heavy_q, uint32_t *heavy_off, uint32_t heavy_cut, int level) {
+  if (n_in < 0) n_in = s.cnt->tail;       // partitioned mode: queue length lives on the device
+  td_expand_dev<OffT>(rowptr, col, q_in, n_in, s, heavy_q, heavy_off, heavy_cut, level);
+}
 
 // Deferred rows: the (row, 128-edge piece) pairs form one flat list (heavy_off[slot] = first piece of
 // row slot, monotone in slot because slot and pieces come from the same 64-bit atomic).  Every warp
 // takes a contiguous range of pieces: one binary search, then a walk.  A frontier of five hubs is
 // expanded by the whole grid instead of five warps.
 template <typename OffT>
-__global__ void __launch_bounds__(256, 4)
-td_heavy(const OffT *__restrict__ rowptr, const int32_t *__restrict__ col, BfsState s,
-         const int32_t *__restrict__ heavy_q, const uint32_t *__restrict__ heavy_off, int level) {
-  __shared__ int s_stage[8][kTdStage];
-  const unsigned long long pack = s.cnt->heavy_pack;
+__device__ __forceinline__ void td_heavy_dev(const OffT *__restrict__ rowptr, const int32_t *__restrict__ col, const BfsState &s,
+                                             const int32_t *heavy_q, const uint32_t *heavy_off, int level, int *s_stage /* [8][kTdStage] */) {
+  const unsigned long long pack = *(volatile unsigned long long *)&s.cnt->heavy_pack;
   const uint32_t nh = (uint32_t)(pack >> 32), np = (uint32_t)pack;
   if (nh == 0) return;
   const int lane = threadIdx.x & 31;
-  int *buf = s_stage[threadIdx.x >> 5];
+  int *buf = s_stage + (threadIdx.x >> 5) * kTdStage;
   int nbuf = 0;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -267,6 +291,13 @@ td_heavy(const OffT *__restrict__ rowptr, const int32_t *__restrict__ col, BfsSt
   if (!s.mark) td_flush(s, buf, nbuf, lane);
   scout = warp_sum(scout);
   if (lane == 0 && scout) atomicAdd((unsigned long long *)&s.cnt->scout, (unsigned long long)scout);
+}
+template <typename OffT>
+__global__ void __launch_bounds__(256, 4)
+td_heavy(const OffT *__restrict__ rowptr, const int32_t *__restrict__ col, BfsState s,
+         const int32_t *__restrict__ heavy_q, const uint32_t *__restrict__ heavy_off, int level) {
+  __shared__ int s_stage[8 * kTdStage];
+  td_heavy_dev<OffT>(rowptr, col, s, heavy_q, heavy_off, level, s_stage);
 }
 
 // Hubs-first copy of the bottom-up CSR.  BFS depths (and the alpha/beta schedule, which only counts
@@ -348,7 +379,7 @@ hubs_first(const OffT *__restrict__ rowptr, const int32_t *__restrict__ col, con
 // A lane probes up to kBuSerial in-neighbours alone; rows that have not hit by then are scanned by the
 // whole warp with a ballot early exit.  `next` is assembled in shared memory; no global atomics.
 template <typename OffT>
-__device__ __forceinline__ int bu_warp_scan(const int32_t *__restrict__ col, const uint32_t *__restrict__ front,
+__device__ __forceinline__ int bu_warp_scan(const int32_t *__restrict__ col, const uint32_t *front,
                                             OffT bb, OffT ee, int lane, long long &probed) {
   for (OffT i = bb; i < ee; i += 32) {
     const OffT k = i + lane;
@@ -362,21 +393,18 @@ __device__ __forceinline__ int bu_warp_scan(const int32_t *__restrict__ col, con
 }
 
 template <typename OffT>
-__global__ void __launch_bounds__(256, 4)
-bu_sweep(const OffT *__restrict__ rowptr, const int32_t *__restrict__ col, const OffT *__restrict__ out_rowptr,
-         const uint32_t *__restrict__ front, uint32_t *__restrict__ next, uint32_t *visited, int32_t *depth,
-         int32_t *parent, int64_t word_lo, int64_t word_hi, int64_t row_lo, bool update_visited, int level,
-         BfsCounters *cnt) {
-  __shared__ uint16_t s_list[8][1024];
-  __shared__ uint32_t s_next[8][32];
+__device__ __forceinline__ void bu_sweep_dev(const OffT *__restrict__ rowptr, const int32_t *__restrict__ col, const OffT *__restrict__ out_rowptr,
+                                             const uint32_t *front, uint32_t *next, uint32_t *visited, int32_t *depth,
+                                             int32_t *parent, int64_t word_lo, int64_t word_hi, int64_t row_lo, bool update_visited, int level,
+                                             BfsCounters *cnt, uint16_t *s_list /* [8][1024] */, uint32_t *s_next /* [8][32] */) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int64_t g_lo = word_lo >> 5, g_hi = word_hi >> 5;   // word ranges are multiples of 32
   rowptr -= row_lo;                                          // rows are addressed by global vertex id
   out_rowptr -= row_lo;
-  uint16_t *list = s_list[wib];
-  uint32_t *nx = s_next[wib];
+  uint16_t *list = s_list + wib * 1024;
+  uint32_t *nx = s_next + wib * 32;
   long long awake = 0, degsum = 0, probed = 0, swept = 0;
   for (int64_t g = g_lo + warp; g < g_hi; g += nwarps) {
     const int64_t widx = g * 32 + lane;
@@ -471,6 +499,17 @@ bu_sweep(const OffT *__restrict__ rowptr, const int32_t *__restrict__ col, const
     atomicAdd((unsigned long long *)&cnt->degsum, (unsigned long long)degsum);
   }
 }
+template <typename OffT>
+__global__ void __launch_bounds__(256, 4)
+bu_sweep(const OffT *__restrict__ rowptr, const int32_t *__restrict__ col, const OffT *__restrict__ out_rowptr,
+         const uint32_t *__restrict__ front, uint32_t *__restrict__ next, uint32_t *visited, int32_t *depth,
+         int32_t *parent, int64_t word_lo, int64_t word_hi, int64_t row_lo, bool update_visited, int level,
+         BfsCounters *cnt) {
+  __shared__ uint16_t s_list[8 * 1024];
+  __shared__ uint32_t s_next[8 * 32];
+  bu_sweep_dev<OffT>(rowptr, col, out_rowptr, front, next, visited, depth, parent, word_lo, word_hi, row_lo, update_visited, level, cnt,
+                     s_list, s_next);
+}
 
 // Vertices without in-edges can never be discovered (omp_beamer.cc:17-26 finds no neighbour, TDStep never
 // sees them as a destination): their bits are pre-set in `visited` so that the sweeps skip them.  Static per
@@ -491,17 +530,17 @@ __global__ void iso_bitmap(const OffT *__restrict__ in_rowptr, int64_t row_lo, i
 }
 
 // QueueToBitmap, src/bfs/omp_beamer.cc:60-67
-__global__ void queue_to_bitmap(const int32_t *__restrict__ q, int n, uint32_t *bm) {
+__device__ __forceinline__ void queue_to_bitmap_dev(const int32_t *q, int n, uint32_t *bm) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int v = q[i];
     atomicOr(&bm[(uint32_t)v >> 5], 1u << (v & 31));
   }
 }
+__global__ void queue_to_bitmap(const int32_t *__restrict__ q, int n, uint32_t *bm) { queue_to_bitmap_dev(q, n, bm); }
 
 // BitmapToQueue, src/bfs/omp_beamer.cc:69-79: ballot-free popc compaction, one
 // atomicAdd per 1024 vertices.
-__global__ void __launch_bounds__(256, 4)
-bitmap_to_queue(const uint32_t *__restrict__ bm, int64_t word_lo, int64_t word_hi, int32_t *q, BfsCounters *cnt) {
+__device__ __forceinline__ void bitmap_to_queue_dev(const uint32_t *bm, int64_t word_lo, int64_t word_hi, int32_t *q, int *tail) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -518,7 +557,7 @@ bitmap_to_queue(const uint32_t *__restrict__ bm, int64_t word_lo, int64_t word_h
     const int total = __shfl_sync(kFull, off, 31);
     if (total == 0) continue;
     int base = 0;
-    if (lane == 0) base = atomicAdd(&cnt->tail, total);
+    if (lane == 0) base = atomicAdd(tail, total);
     base = __shfl_sync(kFull, base, 0) + off - c;
     while (word) {
       const int bit = __ffs(word) - 1;
@@ -526,6 +565,10 @@ bitmap_to_queue(const uint32_t *__restrict__ bm, int64_t word_lo, int64_t word_h
       q[base++] = (int32_t)(widx * 32 + bit);
     }
   }
+}
+__global__ void __launch_bounds__(256, 4)
+bitmap_to_queue(const uint32_t *__restrict__ bm, int64_t word_lo, int64_t word_hi, int32_t *q, BfsCounters *cnt) {
+  bitmap_to_queue_dev(bm, word_lo, word_hi, q, &cnt->tail);
 }
 
 template <typename OffT>
@@ -550,6 +593,7 @@ __global__ void bfs_init(const OffT *__restrict__ out_rowptr, int32_t *depth, in
     const bool own = source >= row_lo && source < row_hi;
     cnt->scout = own ? (long long)(out_rowptr[source - row_lo + 1] - out_rowptr[source - row_lo]) : 0;   // degrees[source], omp_beamer.cc:130
     cnt->awake = 0; cnt->degsum = 0; cnt->tail = 0; cnt->pad = 0; cnt->bu_edges = 0; cnt->bu_scanned = 0; cnt->heavy_pack = 0;
+    cnt->b2q_tail = 0; cnt->ticket = 0;
   }
 }
 
@@ -635,13 +679,13 @@ static int bfs_alloc(gdn_graph *g) {
 // Rows at least this long are deferred to td_heavy.  `edges` = scout_count = the number of edges this
 // top-down step scans (known exactly from the previous step, omp_beamer.cc:155): aim at equal work per
 // warp of a full grid, never below one warp-width and never above what one warp should strip-mine.
-static uint32_t td_cut(int64_t edges, int sm) {
+__host__ __device__ __forceinline__ uint32_t td_cut(long long edges, int sm) {
   // a warp of td_expand owns 32 frontier rows: bound the ROW length by 1/32 of the per-warp share
-  const int64_t per_row = edges / ((int64_t)sm * 4 * 8 * 32);
-  return (uint32_t)std::max<int64_t>(32, std::min<int64_t>(kTdHeavy, per_row));
+  const long long per_row = edges / ((long long)sm * 4 * 8 * 32);
+  return (uint32_t)(per_row < 32 ? 32 : (per_row > kTdHeavy ? kTdHeavy : per_row));
 }
 
-// Build the hubs-first copy of the bottom-up columns on first use (8 bytes... 4 bytes per edge, ~50 ms at Kron-26).
+// Build the hubs-first copy of the bottom-up columns on first use (4 bytes per edge, ~50 ms at Kron-26).
 template <typename OffT>
 static int bfs_prepare(gdn_graph *g) {
   if (g->col_bu || !g->deg_class || g->one_shot || getenv("GDN_BFS_NO_REORDER")) return GDN_OK;
@@ -657,6 +701,149 @@ static int bfs_prepare(gdn_graph *g) {
   return GDN_OK;
 }
 
+// ------------------------------------------------------------------ the whole BFS as ONE cooperative kernel
+// The reference's CUDA variants -- and round 1 of this file -- return to the host after every level to read the
+// counters and choose the next step (src/bfs/hybrid_base.cu:104-144): seven or more round trips of ~30 us, more than the
+// kernels themselves at Kronecker scale 22.  Here the alpha/beta controller of src/bfs/omp_beamer.cc:135-160 lives on the
+// device: a persistent grid (4 CTAs of 256 threads per SM, co-resident) walks the levels, with a grid-wide barrier between
+// the phases of a step; the LAST CTA to finish a step (ticket counter) reads the step's counters, records the step and
+// decides direction and conversions for the next one.  One launch, one host synchronisation per BFS.
+struct PersistArgs {
+  int32_t *queue[2];
+  uint32_t *bm[2];
+  uint32_t *visited;
+  int32_t *depth, *parent;
+  int32_t *heavy_q;
+  uint32_t *heavy_off;
+  BfsCounters *cnt;
+  BfsCtrl *ctrl;
+  int64_t m, n_words;
+  int sm;
+};
+
+__device__ __forceinline__ void ctrl_record(BfsCtrl *c, int dir, long long frontier, long long disc, long long sc, long long edges, long long scanned) {
+  if (c->n_steps < GDN_MAX_BFS_STEPS) {
+    gdn_bfs_step &b = c->steps[c->n_steps];
+    b.dir = dir; b.pad = 0; b.frontier = frontier; b.discovered = disc; b.scout = sc; b.edges = edges; b.scanned = scanned;
+  }
+  c->n_steps++;
+}
+// `while (!queue.empty()) { if (scout_count > edges_to_check / alpha) ... else ...` (omp_beamer.cc:135-137,152-154)
+__device__ __forceinline__ void ctrl_decide(BfsCtrl *c, bool in_bitmap) {
+  if (c->n_front == 0) { c->mode = kModeDone; return; }
+  if (c->scout_count > c->edges_to_check / kAlpha) {
+    c->mode = kModeBU;
+    c->convert = in_bitmap ? kConvNone : kConvQ2B;
+    c->old_awake = c->n_front;                        // awake_count = queue.size(), :139
+  } else {
+    c->mode = kModeTD;
+    c->convert = in_bitmap ? kConvB2Q : kConvNone;
+    c->edges_to_check -= c->scout_count;              // :154
+  }
+  c->iter++;
+}
+// Executed by ONE thread once every CTA has finished the step.
+__device__ __forceinline__ void ctrl_after_step(BfsCtrl *c, BfsCounters *cnt, int64_t m) {
+  volatile BfsCounters *v = cnt;
+  if (c->mode == kModeTD) {
+    const long long scout = v->scout;
+    const int tail = v->tail;
+    ctrl_record(c, 0, c->n_front, tail, scout, v->bu_edges, 0);
+    c->reached += tail; c->reached_deg += scout;
+    c->scout_count = scout;                           // :155
+    c->n_front = tail;
+    c->cur ^= 1;                                      // queue.slide_window(), :156
+    c->level++;
+    ctrl_decide(c, false);
+  } else {
+    const long long awake = v->awake;
+    ctrl_record(c, 1, c->old_awake, awake, awake, v->bu_edges, v->bu_scanned);
+    c->reached += awake; c->reached_deg += v->degsum;
+    c->fb ^= 1;                                       // front.swap(curr), :145
+    c->level++;
+    if (awake >= c->old_awake || awake > m / kBeta) {  // :148-149
+      c->old_awake = awake;
+      c->convert = kConvNone;
+      c->iter++;
+    } else {
+      c->n_front = (int)awake;                        // BitmapToQueue, :150 (done at the head of the top-down step)
+      c->scout_count = 1;                             // :151
+      ctrl_decide(c, true);
+    }
+  }
+  if (c->n_steps > m + 8) { c->aborted = 1; c->mode = kModeDone; }
+  cnt->scout = 0; cnt->awake = 0; cnt->degsum = 0; cnt->tail = 0; cnt->bu_edges = 0; cnt->bu_scanned = 0; cnt->heavy_pack = 0;
+  cnt->b2q_tail = 0; cnt->ticket = 0;
+  __threadfence();
+}
+__device__ __forceinline__ unsigned long long bfs_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+template <typename OffT>
+__global__ void __launch_bounds__(256, 4)
+bfs_persist(const OffT *__restrict__ orp, const int32_t *__restrict__ ocol, const OffT *__restrict__ irp,
+            const int32_t *__restrict__ bu_col, PersistArgs p) {
+  // the phases never overlap inside a CTA: one buffer serves td_heavy's staging and the sweep's lists
+  __shared__ __align__(16) unsigned char s_buf[8 * 1024 * sizeof(uint16_t) + 8 * 32 * sizeof(uint32_t)];
+  static_assert(sizeof(s_buf) >= 8 * kTdStage * sizeof(int), "staging buffer of td_heavy");
+  cg::grid_group grid = cg::this_grid();
+  volatile BfsCtrl *vc = p.ctrl;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  // a step is over when every CTA has drawn a ticket; the last one runs the controller
+  auto step_done = [&]() {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(&p.cnt->ticket, 1u) == gridDim.x - 1) ctrl_after_step(p.ctrl, p.cnt, p.m);
+    }
+  };
+  for (;;) {
+    const int mode = vc->mode, convert = vc->convert, cur = vc->cur, fb = vc->fb, n_front = vc->n_front, level = vc->level;
+    if (mode == kModeDone) break;
+    int32_t *q_cur = cur ? p.queue[1] : p.queue[0], *q_nxt = cur ? p.queue[0] : p.queue[1];
+    uint32_t *bm_front = fb ? p.bm[1] : p.bm[0], *bm_next = fb ? p.bm[0] : p.bm[1];
+    if (mode == kModeTD) {
+      if (convert == kConvB2Q) {
+        bitmap_to_queue_dev(bm_front, 0, p.n_words, q_cur, &p.cnt->b2q_tail);
+        grid.sync();
+      }
+      const BfsState bs = {p.visited, p.depth, p.parent, q_nxt, p.cnt, nullptr, 0};
+      td_expand_dev<OffT>(orp, ocol, q_cur, n_front, bs, p.heavy_q, p.heavy_off, td_cut(vc->scout_count, p.sm), level + 1);
+      grid.sync();
+      td_heavy_dev<OffT>(orp, ocol, bs, p.heavy_q, p.heavy_off, level + 1, reinterpret_cast<int *>(s_buf));
+      step_done();
+      grid.sync();
+    } else {
+      if (convert == kConvQ2B) {
+        for (int64_t w = tid; w < p.n_words; w += nth) bm_front[w] = 0;
+        grid.sync();
+        queue_to_bitmap_dev(q_cur, n_front, bm_front);
+        grid.sync();
+      }
+      unsigned long long t0 = 0;
+      if (tid == 0) t0 = bfs_timer_ns();
+      bu_sweep_dev<OffT>(irp, bu_col, orp, bm_front, bm_next, p.visited, p.depth, p.parent, 0, p.n_words, 0, true, level + 1, p.cnt,
+                         reinterpret_cast<uint16_t *>(s_buf), reinterpret_cast<uint32_t *>(s_buf + 8 * 1024 * sizeof(uint16_t)));
+      step_done();
+      grid.sync();
+      if (tid == 0) p.ctrl->bu_ns += (long long)(bfs_timer_ns() - t0);
+    }
+  }
+}
+
+template <typename OffT>
+__global__ void bfs_ctrl_init(const OffT *__restrict__ out_rowptr, int source, int64_t nnz, BfsCtrl *c) {
+  c->edges_to_check = nnz;                                                     // g.E(), omp_beamer.cc:129
+  c->scout_count = (long long)(out_rowptr[source + 1] - out_rowptr[source]);   // degrees[source], :130
+  c->old_awake = 0; c->reached = 1; c->reached_deg = c->scout_count; c->bu_ns = 0;
+  c->n_front = 1; c->cur = 0; c->fb = 0; c->level = 0; c->iter = 0; c->n_steps = 0; c->aborted = 0; c->pad = 0;
+  c->mode = kModeTD; c->convert = kConvNone;
+  ctrl_decide(c, false);
+}
+
 template <typename OffT>
 static int bfs_t(gdn_graph *g, int32_t source, int32_t *d_depth, int32_t *d_parent, gdn_stats *st) {
   GDN_CHECK(bfs_alloc(g));
@@ -668,98 +855,54 @@ static int bfs_t(gdn_graph *g, int32_t source, int32_t *d_depth, int32_t *d_pare
   const OffT *irp = (const OffT *)ci.rowptr;
   const int32_t *bu_col = g->col_bu ? g->col_bu : ci.col;
   BfsCounters *cnt = (BfsCounters *)g->counters;
-  BfsCounters *h = (BfsCounters *)lib().pinned;
   const int64_t m = g->m;
   const int sm = lib().sm_count;
-  int64_t launches = 0;
+  if (!g->bfs_ctrl) {
+    GDN_CUDA(cudaMalloc((void **)&g->bfs_ctrl, sizeof(BfsCtrl)));
+    GDN_CUDA(cudaHostAlloc((void **)&g->bfs_ctrl_host, sizeof(BfsCtrl), cudaHostAllocDefault));
+  }
+  BfsCtrl *ctrl = (BfsCtrl *)g->bfs_ctrl, *h = (BfsCtrl *)g->bfs_ctrl_host;
+  static int ctas_per_sm = 0;
+  if (!ctas_per_sm) {
+    int a = 0, b = 0;
+    GDN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, bfs_persist<uint32_t>, 256, 0));
+    GDN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, bfs_persist<uint64_t>, 256, 0));
+    ctas_per_sm = std::max(1, std::min(4, std::min(a, b)));
+  }
 
+  // untimed, like the reference's own depth / bitmap initialisation (omp_beamer.cc:116-131 sit before t.Start())
   const int init_grid = (int)std::min<int64_t>((m + 255) / 256, (int64_t)sm * 8);
   bfs_init<OffT><<<init_grid, 256, 0, s>>>(orp, d_depth, d_parent, g->visited, m, g->n_words, source, g->queue[0], cnt,
                                            nullptr, 0, m, g->iso);
-  GDN_CUDA(cudaMemcpyAsync(h, cnt, sizeof(BfsCounters), cudaMemcpyDeviceToHost, s));
-  GDN_CUDA(cudaStreamSynchronize(s));
-  GDN_CUDA(cudaGetLastError());
+  bfs_ctrl_init<OffT><<<1, 1, 0, s>>>(orp, source, (int64_t)co.nnz, ctrl);
 
-  int64_t edges_to_check = (int64_t)co.nnz;          // g.E(), omp_beamer.cc:129
-  int64_t scout_count = h->scout;                    // degrees[source], :130
-  int64_t reached_deg = scout_count, reached = 1;
-  int64_t n_in = 1;
-  int cur = 0, level = 0, iter = 0, n_steps = 0;
-  uint32_t *front = g->front, *next = g->next;
-  auto record = [&](int dir, int64_t frontier, int64_t disc, int64_t sc, int64_t edges, int64_t scanned) {
-    if (st && n_steps < GDN_MAX_BFS_STEPS) {
-      gdn_bfs_step &b = st->steps[n_steps];
-      b.dir = dir; b.pad = 0; b.frontier = frontier; b.discovered = disc; b.scout = sc; b.edges = edges; b.scanned = scanned;
-    }
-    n_steps++;
-  };
-  const int sweep_grid = (int)std::max<int64_t>(1, std::min<int64_t>((g->n_words / 32 + 7) / 8, (int64_t)sm * 8));
-
-  kev_reset();
+  PersistArgs pa;
+  pa.queue[0] = g->queue[0]; pa.queue[1] = g->queue[1];
+  pa.bm[0] = g->front; pa.bm[1] = g->next;
+  pa.visited = g->visited; pa.depth = d_depth; pa.parent = d_parent;
+  pa.heavy_q = g->heavy_queue; pa.heavy_off = g->heavy_off;
+  pa.cnt = cnt; pa.ctrl = ctrl; pa.m = m; pa.n_words = g->n_words; pa.sm = sm;
+  const int32_t *ocol = co.col;
+  void *args[] = {(void *)&orp, (void *)&ocol, (void *)&irp, (void *)&bu_col, (void *)&pa};
   GDN_CUDA(cudaEventRecord(lib().ev0, s));
-  while (n_in > 0) {                                              // omp_beamer.cc:135
-    if (scout_count > edges_to_check / kAlpha) {                  // :136
-      GDN_CUDA(cudaMemsetAsync(front, 0, sizeof(uint32_t) * g->n_words, s));
-      queue_to_bitmap<<<(int)std::min<int64_t>((n_in + 255) / 256, sm * 8), 256, 0, s>>>(g->queue[cur], (int)n_in, front);
-      launches++;
-      int64_t awake = n_in, old_awake;                            // :139
-      do {
-        ++iter;
-        old_awake = awake;
-        GDN_CUDA(cudaMemsetAsync(cnt, 0, sizeof(BfsCounters), s));
-        kev_begin();
-        bu_sweep<OffT><<<sweep_grid, 256, 0, s>>>(irp, bu_col, orp, front, next, g->visited, d_depth, d_parent,
-                                                  0, g->n_words, 0, true, level + 1, cnt);
-        kev_end();
-        launches++;
-        GDN_CUDA(cudaMemcpyAsync(h, cnt, sizeof(BfsCounters), cudaMemcpyDeviceToHost, s));
-        GDN_CUDA(cudaStreamSynchronize(s));
-        awake = h->awake;
-        reached += awake; reached_deg += h->degsum;
-        level++;
-        std::swap(front, next);                                   // front.swap(curr), :145
-        record(1, old_awake, awake, awake, h->bu_edges, h->bu_scanned);
-      } while ((awake >= old_awake) || (awake > m / kBeta));      // :148-149
-      GDN_CUDA(cudaMemsetAsync(cnt, 0, sizeof(BfsCounters), s));
-      bitmap_to_queue<<<sweep_grid, 256, 0, s>>>(front, 0, g->n_words, g->queue[cur], cnt);
-      launches++;
-      GDN_CUDA(cudaMemcpyAsync(h, cnt, sizeof(BfsCounters), cudaMemcpyDeviceToHost, s));
-      GDN_CUDA(cudaStreamSynchronize(s));
-      n_in = h->tail;
-      scout_count = 1;                                            // :151
-    } else {
-      ++iter;
-      edges_to_check -= scout_count;                              // :154
-      GDN_CUDA(cudaMemsetAsync(cnt, 0, sizeof(BfsCounters), s));
-      BfsState bs = {g->visited, d_depth, d_parent, g->queue[cur ^ 1], cnt, nullptr, 0};
-      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_in + 255) / 256, (int64_t)sm * 8));
-      td_expand<OffT><<<grid, 256, 0, s>>>(orp, co.col, g->queue[cur], (int)n_in, bs, g->heavy_queue, g->heavy_off,
-                                           td_cut(scout_count, sm), level + 1);
-      td_heavy<OffT><<<sm * 4, 256, 0, s>>>(orp, co.col, bs, g->heavy_queue, g->heavy_off, level + 1);
-      launches += 2;
-      GDN_CUDA(cudaMemcpyAsync(h, cnt, sizeof(BfsCounters), cudaMemcpyDeviceToHost, s));
-      GDN_CUDA(cudaStreamSynchronize(s));
-      scout_count = h->scout;                                     // :155
-      record(0, n_in, h->tail, scout_count, h->bu_edges, 0);
-      reached += h->tail; reached_deg += scout_count;
-      n_in = h->tail;
-      cur ^= 1;
-      level++;
-    }
-  }
+  GDN_CUDA(cudaLaunchCooperativeKernel((const void *)bfs_persist<OffT>, dim3(sm * ctas_per_sm), dim3(256), args, 0, s));
   GDN_CUDA(cudaEventRecord(lib().ev1, s));
+  GDN_CUDA(cudaMemcpyAsync(h, ctrl, sizeof(BfsCtrl), cudaMemcpyDeviceToHost, s));
   GDN_CUDA(cudaStreamSynchronize(s));
   GDN_CUDA(cudaGetLastError());
+  if (h->aborted) { set_error("BFS controller did not terminate"); return GDN_ERR_CUDA; }
   if (st) {
     float ms = 0;
     GDN_CUDA(cudaEventElapsedTime(&ms, lib().ev0, lib().ev1));
     st->solve_ms = ms;
-    st->iterations = iter;
-    st->n_steps = n_steps;
-    st->kernel_launches = launches;
-    st->edges_reached = reached_deg;
-    st->vertices_reached = reached;
-    kev_collect(st);
+    st->iterations = h->iter;
+    st->n_steps = h->n_steps;
+    st->kernel_launches = 3;
+    st->edges_reached = h->reached_deg;
+    st->vertices_reached = h->reached;
+    st->kernel_ms = (double)h->bu_ns * 1e-6;       // bottom-up sweeps, timed inside the kernel (globaltimer)
+    st->kernel_calls = 0;
+    for (int i = 0; i < std::min(h->n_steps, GDN_MAX_BFS_STEPS); i++) { st->steps[i] = h->steps[i]; st->kernel_calls += h->steps[i].dir; }
   }
   return GDN_OK;
 }
@@ -767,6 +910,48 @@ static int bfs_t(gdn_graph *g, int32_t source, int32_t *d_depth, int32_t *d_pare
 int bfs_merge_or(gdn_graph *g, uint32_t *bm, uint32_t *xbuf);          // comm.cu
 int bfs_allgather_words(gdn_graph *g, uint32_t *bm);                   // comm.cu
 int allreduce_i64(long long *d_p, int n);                              // comm.cu
+
+// Partitioned mode: parents of the vertices this GPU owns that were discovered by a top-down step (their claim went
+// through the merged bitmap, which carries no source).  Depths are replicated, so any in-neighbour one level up is a valid
+// parent (the reference keeps parents only in comments, src/bfs/omp_beamer.cc:12,18,22,44,47; Graph500 accepts any tree
+// edge).  One warp per 32 owned vertices; a vertex that still needs a parent has its row scanned by the whole warp.
+template <typename OffT>
+__global__ void __launch_bounds__(256, 4)
+bfs_parents_from_depth(const OffT *__restrict__ in_rowptr, const int32_t *__restrict__ in_col, const int32_t *__restrict__ depth,
+                       int32_t *parent, int64_t row_lo, int64_t row_hi) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t v0 = row_lo + warp * 32; v0 < row_hi; v0 += nwarps * 32) {
+    const int64_t v = v0 + lane;
+    int d = -1;
+    if (v < row_hi) { d = depth[v]; if (d == GDN_INFINITY || d == 0 || parent[v] >= 0) d = -1; }
+    unsigned need = __ballot_sync(kFull, d > 0);
+    while (need) {
+      const int l = __ffs(need) - 1;
+      need &= need - 1;
+      const int64_t vv = v0 + l;
+      const int want = __shfl_sync(kFull, d, l) - 1;
+      const OffT b = in_rowptr[vv - row_lo], e = in_rowptr[vv - row_lo + 1];
+      int found = -1;
+      for (OffT i = b; i < e && found < 0; i += 32) {
+        const OffT k = i + lane;
+        int src = -1;
+        bool ok = false;
+        if (k < e) { src = in_col[k]; ok = depth[src] == want; }
+        const unsigned bal = __ballot_sync(kFull, ok);
+        if (bal) found = __shfl_sync(kFull, src, __ffs(bal) - 1);
+      }
+      if (lane == 0) parent[vv] = found;
+    }
+  }
+}
+__global__ void fill_i32(int32_t *p, int64_t n, int32_t v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void set_i32(int32_t *p, int32_t v) { *p = v; }
+
+int allgather_i32(int32_t *buf, int64_t per_rank);                     // comm.cu (in place)
 
 // 1-D row-partitioned BFS.  Every GPU holds its rows of the CSR and
 // FULL-length visited/frontier bitmaps and depth[]; all GPUs run the identical
@@ -779,7 +964,7 @@ int allreduce_i64(long long *d_p, int n);                              // comm.c
 //   absorb    : every GPU claims the merged new vertices (visited, depth) and the
 //               owners add up their out-degrees -> allreduce(scout_count)
 template <typename OffT>
-static int bfs_multi_t(gdn_graph *g, int32_t source, int32_t *d_depth, gdn_stats *st) {
+static int bfs_multi_t(gdn_graph *g, int32_t source, int32_t *d_depth, int32_t *d_parent, gdn_stats *st) {
   GDN_CHECK(bfs_alloc(g));
   GDN_CHECK(bfs_prepare<OffT>(g));
   cudaStream_t s = lib().stream;
@@ -801,6 +986,16 @@ static int bfs_multi_t(gdn_graph *g, int32_t source, int32_t *d_depth, gdn_stats
   }
   int64_t launches = 0;
   uint32_t *front = g->front, *next = g->next;
+  // parents: a global-indexed scratch of P equal slices (the allgather's shape); bottom-up steps write the owned rows
+  // directly, top-down discoveries are resolved from the depths at the end
+  const int64_t W = partition_width(m, P);
+  int32_t *pbuf = nullptr;
+  if (d_parent) {
+    if (!g->parent_buf) { GDN_CUDA(cudaMalloc((void **)&g->parent_buf, sizeof(int32_t) * W * P)); g->device_bytes += sizeof(int32_t) * W * P; }
+    pbuf = g->parent_buf;
+    fill_i32<<<sm * 8, 256, 0, s>>>(pbuf, W * P, -1);
+    if (source >= g->row_lo && source < g->row_hi) set_i32<<<1, 1, 0, s>>>(pbuf + source, source);
+  }
 
   const int init_grid = (int)std::min<int64_t>((m + 255) / 256, (int64_t)sm * 8);
   bfs_init<OffT><<<init_grid, 256, 0, s>>>(orp, d_depth, nullptr, g->visited, m, g->n_words, source, g->queue[0], cnt,
@@ -848,7 +1043,7 @@ static int bfs_multi_t(gdn_graph *g, int32_t source, int32_t *d_depth, gdn_stats
         old_awake = awake;
         GDN_CUDA(cudaMemsetAsync(cnt, 0, sizeof(BfsCounters), s));
         kev_begin();
-        bu_sweep<OffT><<<own_grid, 256, 0, s>>>(irp, g->col_bu ? g->col_bu : ci.col, orp, front, next, g->visited, d_depth, nullptr, own_lo,
+        bu_sweep<OffT><<<own_grid, 256, 0, s>>>(irp, g->col_bu ? g->col_bu : ci.col, orp, front, next, g->visited, d_depth, pbuf, own_lo,
                                                 own_hi, g->row_lo, false, level + 1, cnt);
         kev_end();
         launches++;
@@ -883,6 +1078,12 @@ static int bfs_multi_t(gdn_graph *g, int32_t source, int32_t *d_depth, gdn_stats
       level++;
     }
   }
+  if (d_parent) {
+    bfs_parents_from_depth<OffT><<<sm * 8, 256, 0, s>>>(irp, ci.col, d_depth, pbuf, g->row_lo, g->row_hi);
+    launches++;
+    GDN_CHECK(allgather_i32(pbuf, W));
+    GDN_CUDA(cudaMemcpyAsync(d_parent, pbuf, sizeof(int32_t) * m, cudaMemcpyDeviceToDevice, s));
+  }
   GDN_CUDA(cudaEventRecord(lib().ev1, s));
   GDN_CUDA(cudaStreamSynchronize(s));
   GDN_CUDA(cudaGetLastError());
@@ -910,8 +1111,7 @@ int bfs_run(gdn_graph *g, int32_t source, int32_t *d_depth, int32_t *d_parent, g
                 (long long)g->row_lo, (long long)g->row_hi, comm_rank(), comm_size());
       return GDN_ERR_ARG;
     }
-    if (d_parent) { set_error("partitioned BFS does not return parents yet"); return GDN_ERR_ARG; }
-    return g->out.off64 ? bfs_multi_t<uint64_t>(g, source, d_depth, st) : bfs_multi_t<uint32_t>(g, source, d_depth, st);
+    return g->out.off64 ? bfs_multi_t<uint64_t>(g, source, d_depth, d_parent, st) : bfs_multi_t<uint32_t>(g, source, d_depth, d_parent, st);
   }
   return g->out.off64 ? bfs_t<uint64_t>(g, source, d_depth, d_parent, st)
                       : bfs_t<uint32_t>(g, source, d_depth, d_parent, st);

@@ -154,6 +154,13 @@ int bfs_merge_or(gdn_graph *g, uint32_t *bm, uint32_t *xbuf) {
 
 int bfs_allgather_words(gdn_graph *g, uint32_t *bm) { return bitmap_exchange(g, bm, nullptr, 0); }
 
+int allgather_i32(int32_t *buf, int64_t per_rank) {
+  Nccl &n = nccl();
+  if (n.size == 1) return GDN_OK;
+  GDN_NCCL(n.AllGather(buf + (int64_t)n.rank * per_rank, buf, (size_t)per_rank, ncclInt32, n.comm, lib().stream));
+  return GDN_OK;
+}
+
 int allreduce_i64(long long *d_p, int cnt) {
   Nccl &n = nccl();
   if (n.size == 1) return GDN_OK;

@@ -203,7 +203,9 @@ struct gdn_graph {
   bool one_shot = false;              // graph lives for ONE solve (oneshot.cu): skip layouts that only pay off when amortised
   int32_t *col_bu = nullptr;          // bottom-up copy of the in-CSR columns, every row reordered hubs-first
   uint32_t *xbuf = nullptr;          // partitioned BFS: receive buffer of the OR-merge (P bitmap slices)
+  int32_t *parent_buf = nullptr;     // partitioned BFS: parents, P equal slices (global index)
   void *counters = nullptr;          // BfsCounters on device
+  void *bfs_ctrl = nullptr, *bfs_ctrl_host = nullptr;   // BfsCtrl: device-side controller state and its pinned host copy
   int64_t n_words = 0;               // bitmap words (32-bit), padded to a multiple of 32
   int64_t bm_alloc_words = 0;        // allocated words per bitmap (>= n_words; room for the allgather slices)
   // chunked upload of the pull CSR's column array (graph.cu upload_csr_begin): col_ev[k] fires when entries

@@ -402,7 +402,8 @@ int gdn_graph_destroy(gdn_graph *g) {
   cudaFree(g->err_trace); cudaFree(g->pr_done); cudaFree(g->abs_partial);
   cudaFree(g->visited); cudaFree(g->front); cudaFree(g->next); cudaFree(g->iso); cudaFree(g->queue[0]); cudaFree(g->queue[1]);
   cudaFree(g->heavy_queue); cudaFree(g->heavy_off); cudaFree(g->deg_class); cudaFree(g->col_bu);
-  cudaFree(g->counters); cudaFree(g->xbuf);
+  cudaFree(g->counters); cudaFree(g->xbuf); cudaFree(g->bfs_ctrl); cudaFree(g->parent_buf);
+  if (g->bfs_ctrl_host) cudaFreeHost(g->bfs_ctrl_host);
   {
     gdn::PullLayout &L = g->pull;
     cudaFree(L.perm); cudaFree(L.newid); cudaFree(L.sdeg); cudaFree(L.sout); cudaFree(L.rowid); cudaFree(L.slice_ptr);

@@ -12,6 +12,8 @@
 // usage:
 //   ref_driver csr  <filetype> <prefix> <symmetrize> <reverse> <out_prefix>
 //   ref_driver bfs  <filetype> <prefix> <symmetrize> <reverse> <source> <out.i32> [repeat]
+//   ref_driver bfs  <filetype> <prefix> <symmetrize> <reverse> <s0,s1,...> <out.i8>     (one BFS per source, one graph load;
+//                   depths of all sources concatenated as int8, -1 = unreached)
 //   ref_driver pr   <filetype> <prefix> <symmetrize> <out.f32> [repeat]
 //   ref_driver spmv <filetype> <prefix> <symmetrize> <reverse> <seed> <out.f32> [repeat]
 #include "bfs.h"     // src/bfs/bfs.h  -> common.h, csr_graph.h
@@ -19,6 +21,7 @@
 #include "spmv.h"    // src/spmv/spmv.h
 #include <random>
 #include <cstdio>
+#include <cstring>
 #include <string>
 
 template <typename T>
@@ -47,9 +50,27 @@ int main(int argc, char **argv) {
   }
   if (cmd == "bfs") {
     Graph g(argv[3], argv[2], atoi(argv[4]), atoi(argv[5]));
+    std::vector<DistT> dist(g.V(), MYINFINITY);
+    if (strchr(argv[6], ',')) {
+      std::vector<int> sources;
+      for (const char *p = argv[6]; *p;) { sources.push_back(atoi(p)); p = strchr(p, ','); if (!p) break; p++; }
+      FILE *f = fopen(argv[7], "wb");
+      if (!f) { perror(argv[7]); return 2; }
+      std::vector<signed char> d8(g.V());
+      for (int source : sources) {
+        std::fill(dist.begin(), dist.end(), MYINFINITY);   // src/bfs/main.cc:21
+        BFSSolver(g, source, &dist[0]);
+        for (size_t i = 0; i < dist.size(); i++) {
+          if (dist[i] != MYINFINITY && dist[i] > 126) { fprintf(stderr, "depth %d does not fit int8\n", dist[i]); return 3; }
+          d8[i] = dist[i] == MYINFINITY ? -1 : (signed char)dist[i];
+        }
+        if (fwrite(&d8[0], 1, d8.size(), f) != d8.size()) { perror("fwrite"); return 2; }
+      }
+      fclose(f);
+      return 0;
+    }
     int source = atoi(argv[6]);
     int repeat = argc > 8 ? atoi(argv[8]) : 1;
-    std::vector<DistT> dist(g.V(), MYINFINITY);
     for (int r = 0; r < repeat; r++) {
       std::fill(dist.begin(), dist.end(), MYINFINITY);   // src/bfs/main.cc:21
       BFSSolver(g, source, &dist[0]);

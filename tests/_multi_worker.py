@@ -30,8 +30,9 @@ def main():
     # third case: many small bands, so that the banded layout (csrc/band.cu) spreads over every rank's cold slice
     small = dict(GDN_PR_BANDS="96", GDN_PR_BAND_SIZE="512", GDN_PR_BAND_CMIN="2", GDN_PR_BAND_DMIN="8")
     seg = dict(GDN_PR_SEGMENT="1", GDN_PR_SEG_IDS="3000")           # segmented mode forced on a small uniform graph
-    for kind, scale, env in (("g", 16, {}), ("u", 15, {}), ("g", 17, small), ("u", 16, seg)):
-        for k in list(small) + list(seg):
+    nccl = dict(GDN_PR_NCCL="1")                                    # the NCCL collectives instead of the peer-mapped exchange
+    for kind, scale, env in (("g", 16, {}), ("u", 15, {}), ("g", 17, small), ("u", 16, seg), ("g", 16, nccl)):
+        for k in list(small) + list(seg) + list(nccl):
             os.environ.pop(k, None)
         os.environ.update(env)
         g = gb.Graph.generate(kind, scale, 16)
@@ -56,8 +57,9 @@ def main():
         depths = []
         for s in srcs:
             depth = torch.empty(m, dtype=torch.int32, device=dev)
-            stb = dg.bfs(s, depth)
-            depths.append((depth.cpu().numpy(), stb.iterations))
+            parent = torch.empty(m, dtype=torch.int32, device=dev)
+            stb = dg.bfs(s, depth, parent)
+            depths.append((depth.cpu().numpy(), stb.iterations, parent.cpu().numpy()))
         if rank == 0:
             from oracle import pyoracle as po
             rp, ci = g.out_rowptr(), g.out_colidx()
@@ -67,10 +69,10 @@ def main():
             print(f"[multi] {kind}{scale} world={world} PR iters {st.iterations} vs {oit} l1={l1:.3e} {'OK' if good else 'FAIL'} "
                   f"bands={pinfo['bands']}x{pinfo['band_ids']} band_entries={pinfo['band_entries']}", flush=True)
             ok &= good
-            for s, (d, it) in zip(srcs, depths):
+            for s, (d, it, par) in zip(srcs, depths):
                 od, oit, _ = po.bfs_do(m, rp, ci, rp, ci, s)
-                good = np.array_equal(d, od) and it == oit
-                print(f"[multi] {kind}{scale} BFS src {s}: iters {it} vs {oit} {'OK' if good else 'FAIL'}", flush=True)
+                good = np.array_equal(d, od) and it == oit and po.bfs_check_parents(m, rp, ci, s, od, par) == 0
+                print(f"[multi] {kind}{scale} BFS src {s}: iters {it} vs {oit}, parents {'OK' if good else 'FAIL'}", flush=True)
                 ok &= good
         dg.close()
     flag = torch.tensor([1 if ok else 0], device=dev)

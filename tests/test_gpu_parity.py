@@ -520,3 +520,80 @@ def test_pr_banded_accepts_any_start_vector(start):
     assert st2.pr_layout == 1 and st2.iterations == oit2
     assert float(np.abs(ds2.cpu().numpy().astype(np.float64) - o2.astype(np.float64)).sum()) <= PR_L1_TOL
     dg.close()
+
+
+# ------------------------------------------------------------------ BASELINE.json configurations, full size
+def test_config_c2_bfs_kron22_16_sources():
+    """configs[1]: direction-optimizing BFS on Kronecker scale 22 (m = 4,194,302, nnz = 128,311,436: the size KAT of SURVEY
+    8(c)), 16 GAP-style sources: depths bit-exact, the oracle's direction schedule level by level, valid parent trees."""
+    import torch
+    g = gb.Graph.generate("g", 22, 16)
+    m, rp, ci = g.m, g.out_rowptr(), g.out_colidx()
+    assert (m, g.nnz) == (4194302, 128311436)
+    dg = gb.DeviceGraph(g)
+    depth = torch.empty(m, dtype=torch.int32, device="cuda")
+    parent = torch.empty(m, dtype=torch.int32, device="cuda")
+    for i, s in enumerate([int(x) for x in g.pick_sources(16)]):
+        st = dg.bfs(s, depth, parent)
+        odist, oit, osteps = po.bfs_do(m, rp, ci, rp, ci, s)
+        assert np.array_equal(depth.cpu().numpy(), odist), s
+        assert st.iterations == oit
+        assert [x["dir"] for x in st.bfs_steps()] == [x["dir"] for x in osteps]
+        assert [x["discovered"] for x in st.bfs_steps()] == [x["discovered"] for x in osteps]
+        if i < 4:
+            assert po.bfs_check_parents(m, rp, ci, s, odist, parent.cpu().numpy()) == 0
+    dg.close()
+    # the one-shot entry point on the same graph (no hubs-first copy)
+    s = int(g.pick_sources(1)[0])
+    dist = np.full(m, gb.MYINFINITY, dtype=np.int32)
+    gb.BFSSolver(g, s, dist, verbose=False)
+    assert np.array_equal(dist, po.bfs_do(m, rp, ci, rp, ci, s)[0])
+
+
+def test_config_c3_spmv_urand24():
+    """configs[2]: fp32 CSR SpMV on uniform-random scale 24 against the oracle (sequential fp32 row sums), 1e-5 per row;
+    resident and one-shot entry points; a second product accumulates into y."""
+    import torch
+    g = gb.Graph.generate("u", 24, 16)
+    m, nnz, rp, ci = g.m, g.nnz, g.out_rowptr(), g.out_colidx()
+    both = gb.fill_uniform(13, nnz + m)
+    Ax, x = both[:nnz].copy(), both[nnz:].copy()
+    oy = po.spmv(m, rp, ci, Ax, x, np.zeros(m, np.float32))
+    dg = gb.DeviceGraph(g)
+    dAx, dx = torch.from_numpy(Ax).cuda(), torch.from_numpy(x).cuda()
+    y = torch.zeros(m, device="cuda")
+    dg.spmv(dAx, dx, y)
+    assert _rel(y.cpu().numpy(), oy) <= SPMV_REL_TOL
+    dg.spmv(dAx, dx, y)                                     # y += A x once more
+    assert _rel(y.cpu().numpy(), po.spmv(m, rp, ci, Ax, x, oy)) <= SPMV_REL_TOL
+    dg.close()
+    del dAx, dx, y
+    yh = np.zeros(m, dtype=np.float32)
+    gb.SpmvSolver(g, Ax, x, yh, verbose=False)
+    assert _rel(yh, oy) <= SPMV_REL_TOL
+
+
+def test_bfs_long_diameter_and_tiny_graphs():
+    """The device-side controller across hundreds of levels (a path never leaves top-down; a grid alternates) and on
+    graphs so small that `edges_to_check / alpha` is 0 (bottom-up re-entered straight after leaving it)."""
+    shapes = {
+        "path3000": [(i, i + 1) for i in range(2999)],
+        "grid": [(r * 60 + c, r * 60 + c + 1) for r in range(60) for c in range(59)] + [(r * 60 + c, (r + 1) * 60 + c) for r in range(59) for c in range(60)],
+        "triangle": [(0, 1), (1, 2), (0, 2)],
+        "pair": [(0, 1)],
+        "tiny_star": [(0, i) for i in range(1, 6)],
+        "k6": [(i, j) for i in range(6) for j in range(i + 1, 6)],
+    }
+    for name, edges in shapes.items():
+        m = max(max(a, b) for a, b in edges) + 1 + (3 if name == "pair" else 0)     # trailing isolated vertices too
+        g = RawGraph(_sym_csr(edges, m))
+        rp, ci = g.out_rowptr(), g.out_colidx()
+        for s in sorted({0, m // 2, m - 1}):
+            dist = np.full(m, gb.MYINFINITY, dtype=np.int32)
+            parent = np.full(m, -7, dtype=np.int32)
+            st = gb.BFSSolver(g, s, dist, parent, verbose=False)
+            odist, oit, osteps = po.bfs_do(m, rp, ci, rp, ci, s)
+            assert np.array_equal(dist, odist), (name, s)
+            assert st.iterations == oit, (name, s, st.iterations, oit)
+            assert [x["dir"] for x in st.bfs_steps()] == [x["dir"] for x in osteps], (name, s)
+            assert po.bfs_check_parents(m, rp, ci, s, dist, parent) == 0

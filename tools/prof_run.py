@@ -21,7 +21,7 @@ def main():
     ap.add_argument("--kind", default="g")
     ap.add_argument("--scale", type=int, default=22)
     ap.add_argument("--reps", type=int, default=2)
-    ap.add_argument("--sweep", default="", help="';'-separated env settings, e.g. 'GDN_PR_POLICY=0;GDN_PR_POLICY=1,GDN_PR_WARM_MB=32'")
+    ap.add_argument("--sweep", default="", help="';'-separated env settings, e.g. 'GDN_PR_WARM_MB=32;GDN_PR_WARM_MB=64,GDN_PR_BANDS=96'")
     args = ap.parse_args()
     import numpy as np
     import torch
