@@ -32,7 +32,7 @@ class GdnError(RuntimeError):
 
 
 class BfsStep(C.Structure):
-    _fields_ = [("dir", C.c_int32), ("pad", C.c_int32), ("frontier", C.c_int64),
+    _fields_ = [("dir", C.c_int32), ("ns", C.c_int32), ("frontier", C.c_int64),
                 ("discovered", C.c_int64), ("scout", C.c_int64), ("edges", C.c_int64), ("scanned", C.c_int64)]
 
 
@@ -50,7 +50,7 @@ class Stats(C.Structure):
 
     def bfs_steps(self):
         n = min(self.n_steps, GDN_MAX_BFS_STEPS)
-        return [dict(dir=s.dir, frontier=s.frontier, discovered=s.discovered, scout=s.scout, edges=s.edges, scanned=s.scanned)
+        return [dict(dir=s.dir, ns=s.ns, frontier=s.frontier, discovered=s.discovered, scout=s.scout, edges=s.edges, scanned=s.scanned)
                 for s in self.steps[:n]]
 
 

@@ -99,12 +99,13 @@ band_count(const int4 *__restrict__ sell, const uint32_t *__restrict__ slice_ptr
 // (row, band) pairs with fewer than cmin ids stay in the main array; rem_w[s] = widest remainder of slice s.
 __global__ void __launch_bounds__(256)
 band_select(uint32_t *__restrict__ cnt, int B, int64_t n_rows, uint32_t cmin, const int32_t *__restrict__ sdeg,
-            uint32_t *__restrict__ rem_w) {
+            uint32_t *__restrict__ rem_w, int64_t n_exact_rows) {
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_rows; j += (int64_t)gridDim.x * blockDim.x) {
     uint32_t tot = 0;
+    const uint32_t need = j < n_exact_rows ? 0xffffffffu : cmin;       // rows of exact slices keep every id in the main array
     for (int b = 0; b < B; b++) {
       const uint32_t v = cnt[(size_t)b * n_rows + j];
-      if (v < cmin) { if (v) cnt[(size_t)b * n_rows + j] = 0; } else tot += v;
+      if (v < need) { if (v) cnt[(size_t)b * n_rows + j] = 0; } else tot += v;
     }
     uint32_t rem = (uint32_t)sdeg[j] - tot;
 #pragma unroll
@@ -344,7 +345,7 @@ pr_band_finalize_fix(SellArgs a, long long *__restrict__ acc_fix, double inv_sca
 
 // ------------------------------------------------------------------ host: tables
 // Work tables of a SELL array from its slice pointers (same meaning as in pull_prepare; widths need not be monotone).
-static void make_work_tables(const std::vector<uint32_t> &sptr, int32_t n_slices, std::vector<int32_t> &chunk,
+static void make_work_tables(const std::vector<uint32_t> &sptr, int32_t n_slices, int32_t n_exact, std::vector<int32_t> &chunk,
                              std::vector<int32_t> &hslice, std::vector<int32_t> &hfirst, std::vector<int2> &hseg) {
   const uint64_t tot = sptr[n_slices];
   const int32_t n_chunks = (int32_t)(tot / kGroupCh + 1);
@@ -359,7 +360,7 @@ static void make_work_tables(const std::vector<uint32_t> &sptr, int32_t n_slices
   }
   chunk[n_chunks] = n_slices;
   hslice.clear(); hfirst.clear(); hseg.clear();
-  for (int32_t t = 0; t < n_slices; t++) {
+  for (int32_t t = n_exact; t < n_slices; t++) {          // (exact slices are items of their own, never cut)
     const uint32_t sz = sptr[t + 1] - sptr[t];
     if (sz <= (uint32_t)kGroupCh) continue;
     hslice.push_back(t);
@@ -393,7 +394,7 @@ struct BandHost {
 };
 
 static void band_host_tables(int B, int64_t n_rows, int32_t nb, uint32_t W, bool seg, int n_cta, const std::vector<uint32_t> &cnt,
-                             const std::vector<uint32_t> &remw, const std::vector<uint32_t> &sp, int32_t n_slices, BandHost &H) {
+                             const std::vector<uint32_t> &remw, const std::vector<uint32_t> &sp, int32_t n_slices, int32_t n_exact, BandHost &H) {
   // host: every band's rows sorted by their count in it; slices, items, ranks
   struct PerBand {
     std::vector<uint32_t> order;           // rows by (count desc, row asc)
@@ -540,7 +541,7 @@ static void band_host_tables(int B, int64_t n_rows, int32_t nb, uint32_t W, bool
   sp2[n_slices] = (uint32_t)tot2;
   std::vector<int32_t> chunk, hslice, hfirst;
   std::vector<int2> hseg;
-  make_work_tables(sp2, n_slices, chunk, hslice, hfirst, hseg);
+  make_work_tables(sp2, n_slices, n_exact, chunk, hslice, hfirst, hseg);
   H.rank = std::move(rank); H.item_ptr = std::move(item_ptr); H.bslice_ptr = std::move(bslice_ptr); H.bslice_item = std::move(bslice_item);
   H.sp2 = std::move(sp2);
   H.bslice_first = std::move(bslice_first); H.item_band = std::move(item_band); H.irow = std::move(irow);
@@ -552,7 +553,7 @@ static void band_host_tables(int B, int64_t n_rows, int32_t nb, uint32_t W, bool
 
 // Invariants of the host tables (what the kernels rely on); returns 0 or the negative number of the first one broken.
 static int band_host_check(int B, int64_t n_rows, int32_t nb, uint32_t W, bool seg, int n_cta, const std::vector<uint32_t> &cnt,
-                           const std::vector<uint32_t> &remw, const std::vector<uint32_t> &sp, int32_t n_slices, const BandHost &H) {
+                           const std::vector<uint32_t> &remw, const std::vector<uint32_t> &sp, int32_t n_slices, int32_t n_exact, const BandHost &H) {
   const int32_t n_items = H.n_items;
   if ((int64_t)H.item_ptr.size() != (int64_t)n_items + 1 || H.item_ptr[0] != 0 || H.item_ptr[n_items] != H.units) return -1;
   // 1. ranks of a band are a bijection between its rows and 0 .. n_b - 1; slices are wide enough for every row in them
@@ -620,7 +621,7 @@ static int band_host_check(int B, int64_t n_rows, int32_t nb, uint32_t W, bool s
   size_t hs = 0;
   for (int32_t t = 0; t < n_slices; t++) {
     const uint32_t sz = H.sp2[t + 1] - H.sp2[t];
-    if (sz > (uint32_t)kGroupCh) {
+    if (t >= n_exact && sz > (uint32_t)kGroupCh) {
       if (hs >= H.hslice.size() || H.hslice[hs] != t) return -28;
       if (H.hfirst[hs + 1] - H.hfirst[hs] != (int32_t)((sz + kGroupCh - 1) / kGroupCh)) return -29;
       hs++;
@@ -698,7 +699,7 @@ static int band_build_body(gdn_graph *g) {
   GDN_CUDA(cudaFuncSetAttribute(band_fill<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
   const int grid = (int)std::min<int64_t>((nb + 3) / 4, (int64_t)sm * 16);
   band_count<<<grid, 128, smem1, st>>>(L.sell, L.slice_ptr, nb, mp, d_cnt, n_rows);
-  band_select<<<(int)std::min<int64_t>((n_rows + 255) / 256, (int64_t)sm * 8), 256, 0, st>>>(d_cnt, B, n_rows, (uint32_t)cmin, L.sdeg, d_remw);
+  band_select<<<(int)std::min<int64_t>((n_rows + 255) / 256, (int64_t)sm * 8), 256, 0, st>>>(d_cnt, B, n_rows, (uint32_t)cmin, L.sdeg, d_remw, (int64_t)L.n_exact * 32);
   std::vector<uint32_t> cnt, remw;
   try { cnt.resize((size_t)B * n_rows); remw.resize((size_t)nb); }
   catch (const std::bad_alloc &) { set_error("band layout: out of host memory"); return GDN_ERR_NOMEM; }
@@ -711,11 +712,11 @@ static int band_build_body(gdn_graph *g) {
   // host: every band's rows sorted by their count in it; slices, items, ranks, jobs, main array tables
   const int n_cta = sm;
   BandHost H;
-  try { band_host_tables(B, n_rows, nb, W, seg, n_cta, cnt, remw, sp, L.n_slices, H); }
+  try { band_host_tables(B, n_rows, nb, W, seg, n_cta, cnt, remw, sp, L.n_slices, L.n_exact, H); }
   catch (const std::bad_alloc &) { set_error("band layout: out of host memory"); return GDN_ERR_NOMEM; }
   if (!H.ok) return GDN_OK;
   if (env_int("GDN_BAND_CHECK", 0)) {              // the same invariants the CPU test checks, on the real counts
-    const int bad = band_host_check(B, n_rows, nb, W, seg, n_cta, cnt, remw, sp, L.n_slices, H);
+    const int bad = band_host_check(B, n_rows, nb, W, seg, n_cta, cnt, remw, sp, L.n_slices, L.n_exact, H);
     if (bad) { set_error("band layout: host table invariant %d broken", bad); return GDN_ERR_GRAPH; }
   }
   trace("band_build: host tables");
@@ -830,13 +831,13 @@ extern "C" int gdn_band_host_probe(int32_t B, int64_t n_rows, int32_t ids_per_un
   const int32_t nb = (int32_t)(n_rows / 32);
   std::vector<uint32_t> c(cnt, cnt + (size_t)B * n_rows), rw(rem_w, rem_w + nb), sp(slice_ptr, slice_ptr + n_slices + 1);
   gdn::BandHost H;
-  gdn::band_host_tables(B, n_rows, nb, (uint32_t)ids_per_unit, segmented != 0, n_cta, c, rw, sp, n_slices, H);
+  gdn::band_host_tables(B, n_rows, nb, (uint32_t)ids_per_unit, segmented != 0, n_cta, c, rw, sp, n_slices, 0, H);
   if (!H.ok) return 1;
   if (stats) {
     stats[0] = H.n_items; stats[1] = (int64_t)H.units; stats[2] = (int64_t)H.pairs; stats[3] = (int64_t)H.moved;
     stats[4] = (int64_t)H.job.size(); stats[5] = (int64_t)H.tot2;
   }
-  return gdn::band_host_check(B, n_rows, nb, (uint32_t)ids_per_unit, segmented != 0, n_cta, c, rw, sp, n_slices, H);
+  return gdn::band_host_check(B, n_rows, nb, (uint32_t)ids_per_unit, segmented != 0, n_cta, c, rw, sp, n_slices, 0, H);
 }
 
 namespace gdn {

@@ -54,6 +54,7 @@ struct BfsCtrl {
   long long edges_to_check, scout_count, old_awake;
   long long reached, reached_deg;
   long long bu_ns;        // time spent in bottom-up sweeps (globaltimer), for the roofline's kernel share
+  long long t_step;       // globaltimer at the end of the previous step
   int n_front;            // |frontier| about to be expanded
   int mode, convert;
   int cur;                // queue holding the frontier
@@ -721,12 +722,19 @@ struct PersistArgs {
   int sm;
 };
 
+__device__ __forceinline__ unsigned long long bfs_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void ctrl_record(BfsCtrl *c, int dir, long long frontier, long long disc, long long sc, long long edges, long long scanned) {
+  const long long now = (long long)bfs_timer_ns();
   if (c->n_steps < GDN_MAX_BFS_STEPS) {
     gdn_bfs_step &b = c->steps[c->n_steps];
-    b.dir = dir; b.pad = 0; b.frontier = frontier; b.discovered = disc; b.scout = sc; b.edges = edges; b.scanned = scanned;
+    b.dir = dir; b.ns = (int32_t)(now - c->t_step); b.frontier = frontier; b.discovered = disc; b.scout = sc; b.edges = edges; b.scanned = scanned;
   }
   c->n_steps++;
+  c->t_step = now;
 }
 // `while (!queue.empty()) { if (scout_count > edges_to_check / alpha) ... else ...` (omp_beamer.cc:135-137,152-154)
 __device__ __forceinline__ void ctrl_decide(BfsCtrl *c, bool in_bitmap) {
@@ -776,12 +784,6 @@ __device__ __forceinline__ void ctrl_after_step(BfsCtrl *c, BfsCounters *cnt, in
   cnt->b2q_tail = 0; cnt->ticket = 0;
   __threadfence();
 }
-__device__ __forceinline__ unsigned long long bfs_timer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-
 template <typename OffT>
 __global__ void __launch_bounds__(256, 4)
 bfs_persist(const OffT *__restrict__ orp, const int32_t *__restrict__ ocol, const OffT *__restrict__ irp,
@@ -791,6 +793,7 @@ bfs_persist(const OffT *__restrict__ orp, const int32_t *__restrict__ ocol, cons
   static_assert(sizeof(s_buf) >= 8 * kTdStage * sizeof(int), "staging buffer of td_heavy");
   cg::grid_group grid = cg::this_grid();
   volatile BfsCtrl *vc = p.ctrl;
+  if (blockIdx.x == 0 && threadIdx.x == 0) p.ctrl->t_step = (long long)bfs_timer_ns();     // (the first step's clock starts here)
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
   // a step is over when every CTA has drawn a ticket; the last one runs the controller
   auto step_done = [&]() {
@@ -835,13 +838,15 @@ bfs_persist(const OffT *__restrict__ orp, const int32_t *__restrict__ ocol, cons
 }
 
 template <typename OffT>
-__global__ void bfs_ctrl_init(const OffT *__restrict__ out_rowptr, int source, int64_t nnz, BfsCtrl *c) {
+__global__ void bfs_ctrl_init(const OffT *__restrict__ out_rowptr, int source, int64_t nnz, BfsCtrl *c, BfsCounters *cnt) {
+  cnt->scout = 0;                                                              // (bfs_init left degrees[source] there for the host-driven path)
   c->edges_to_check = nnz;                                                     // g.E(), omp_beamer.cc:129
   c->scout_count = (long long)(out_rowptr[source + 1] - out_rowptr[source]);   // degrees[source], :130
   c->old_awake = 0; c->reached = 1; c->reached_deg = c->scout_count; c->bu_ns = 0;
   c->n_front = 1; c->cur = 0; c->fb = 0; c->level = 0; c->iter = 0; c->n_steps = 0; c->aborted = 0; c->pad = 0;
   c->mode = kModeTD; c->convert = kConvNone;
   ctrl_decide(c, false);
+  c->t_step = 0;
 }
 
 template <typename OffT>
@@ -874,7 +879,7 @@ static int bfs_t(gdn_graph *g, int32_t source, int32_t *d_depth, int32_t *d_pare
   const int init_grid = (int)std::min<int64_t>((m + 255) / 256, (int64_t)sm * 8);
   bfs_init<OffT><<<init_grid, 256, 0, s>>>(orp, d_depth, d_parent, g->visited, m, g->n_words, source, g->queue[0], cnt,
                                            nullptr, 0, m, g->iso);
-  bfs_ctrl_init<OffT><<<1, 1, 0, s>>>(orp, source, (int64_t)co.nnz, ctrl);
+  bfs_ctrl_init<OffT><<<1, 1, 0, s>>>(orp, source, (int64_t)co.nnz, ctrl, cnt);
 
   PersistArgs pa;
   pa.queue[0] = g->queue[0]; pa.queue[1] = g->queue[1];
@@ -1017,7 +1022,7 @@ static int bfs_multi_t(gdn_graph *g, int32_t source, int32_t *d_depth, int32_t *
   auto record = [&](int dir, int64_t frontier, int64_t disc, int64_t sc, int64_t edges, int64_t scanned) {
     if (st && n_steps < GDN_MAX_BFS_STEPS) {
       gdn_bfs_step &b = st->steps[n_steps];
-      b.dir = dir; b.pad = 0; b.frontier = frontier; b.discovered = disc; b.scout = sc; b.edges = edges; b.scanned = scanned;
+      b.dir = dir; b.ns = 0; b.frontier = frontier; b.discovered = disc; b.scout = sc; b.edges = edges; b.scanned = scanned;
     }
     n_steps++;
   };

@@ -146,6 +146,7 @@ struct PullLayout {
   bool prepared = false;       // host part done (orders, ids, slice pointers, work items)
   bool exact = false;          // exact-order mode: no wide-slice segments, no bands (every row summed in column order by one lane)
   uint32_t group_ch = 1024;    // int4 groups per work item (pull.cuh kGroupCh; 0xffffffff in exact-order mode)
+  int32_t n_exact = 0;         // leading slices whose rows keep the reference's summation order (never cut, never banded)
   bool symmetric_order = true; // row order == column order (row new-ids are two contiguous runs)
   int P = 1, R = 0;            // communicator size / rank the ids were laid out for
   int64_t W = 0, H = 0, Hp = 0, Wc = 0, Mp = 0;   // slice width, hot ids (total / per rank), cold width, id space
@@ -159,6 +160,7 @@ struct PullLayout {
   int32_t *rowid = nullptr;    // [rows]  new global id of sorted row j (only when !symmetric_order)
   uint32_t *slice_ptr = nullptr;   // [n_slices+1] in int4 groups
   int4 *sell = nullptr;            // [n_groups]   built lazily on the first PageRank call
+  float4 *exact_vals = nullptr;    // [slice_ptr[n_exact]] gathered values of the exact slices, rewritten every iteration
   int32_t n_chunks = 0;
   int32_t *chunk_slice = nullptr;  // [n_chunks+1]
   int32_t n_heavy_slices = 0, n_heavy_segs = 0, n_fill_wide = 0;
@@ -185,6 +187,7 @@ struct gdn_graph {
   double *err_trace = nullptr;       // double[GDN_MAX_PR_ITER + 8] on device (the tail slot takes sum |scores_0|)
   double *abs_partial = nullptr;     // per-warp partials of sum |scores_0| (pr_sell_load)
   int32_t *pr_done = nullptr;        // device flag: converged
+  int32_t *pr_work = nullptr;        // device counter: work batches drawn by the warps of the running iteration kernel
   int n_err_partial = 0;
   gdn::PullLayout pull;
   float *scores_sorted = nullptr;    // PR scores in sorted row order during a solve

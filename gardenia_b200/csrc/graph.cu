@@ -399,7 +399,7 @@ int gdn_graph_destroy(gdn_graph *g) {
   if (g->symmetric) { free_csr(g->out); g->in = DevCsr(); }
   else { free_csr(g->out); free_csr(g->in); }
   cudaFree(g->contrib[0]); cudaFree(g->contrib[1]); cudaFree(g->out_degree); cudaFree(g->err_partial);
-  cudaFree(g->err_trace); cudaFree(g->pr_done); cudaFree(g->abs_partial);
+  cudaFree(g->err_trace); cudaFree(g->pr_done); cudaFree(g->pr_work); cudaFree(g->abs_partial);
   cudaFree(g->visited); cudaFree(g->front); cudaFree(g->next); cudaFree(g->iso); cudaFree(g->queue[0]); cudaFree(g->queue[1]);
   cudaFree(g->heavy_queue); cudaFree(g->heavy_off); cudaFree(g->deg_class); cudaFree(g->col_bu);
   cudaFree(g->counters); cudaFree(g->xbuf); cudaFree(g->bfs_ctrl); cudaFree(g->parent_buf);
@@ -407,7 +407,7 @@ int gdn_graph_destroy(gdn_graph *g) {
   {
     gdn::PullLayout &L = g->pull;
     cudaFree(L.perm); cudaFree(L.newid); cudaFree(L.sdeg); cudaFree(L.sout); cudaFree(L.rowid); cudaFree(L.slice_ptr);
-    cudaFree(L.sell); cudaFree(L.chunk_slice); cudaFree(L.heavy_slice); cudaFree(L.heavy_first); cudaFree(L.heavy_seg);
+    cudaFree(L.sell); cudaFree(L.exact_vals); cudaFree(L.chunk_slice); cudaFree(L.heavy_slice); cudaFree(L.heavy_first); cudaFree(L.heavy_seg);
     cudaFree(L.partial); cudaFree(g->scores_sorted);
     gdn::band_free(L.band);
   }

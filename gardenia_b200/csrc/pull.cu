@@ -30,6 +30,7 @@
 // so the hot table is one contiguous prefix and each rank still owns two
 // contiguous slices of contrib (two in-place NCCL allgathers per iteration).
 #include "pull.cuh"
+#include "ordered_sum.cuh"
 #include <omp.h>
 #include <chrono>
 #include <cmath>
@@ -236,9 +237,20 @@ int pull_prepare(gdn_graph *g, const HostOffT *row_off, const HostOffT *key_off)
     }
     chunk[L.n_chunks] = L.n_slices;
   }
+  // Exact slices: the widest rows are never cut into segments and never banded -- every lane of ONE warp adds ITS row
+  // sequentially in column order like src/pr/omp_base.cc:28-30.  On a long row the fp32 rounding of a re-ordered sum differs
+  // from the reference's by ~ sqrt(length) ulps; at Kronecker scale 26 (rows of 10^6 entries that carry percents of the
+  // score mass) that alone is 1.15e-6 of L1 distance -- over the 1e-6 parity bar (profiles/r2_pr_exact_threshold.txt:
+  // 0.65e-6 with the 11 slices wider than 65536 columns exact).  A dependent chain of a million adds is 2 ms whatever feeds
+  // it, so the gathers are taken out of it: pr_exact_gather (whole grid) writes the slices' VALUES in column order, and
+  // the chain warp of pr_sell_pipe streams them through a TMA-fed shared-memory ring while the other warps do the rest.
+  const char *e_xc = getenv("GDN_PR_EXACT_COLS");
+  const int64_t exact_cols = e_xc ? atoll(e_xc) : (L.exact ? kExactColsStrict : kExactCols);
+  L.n_exact = 0;
+  while (L.n_exact < L.n_slices && width[L.n_exact] > exact_cols && (sptr[L.n_exact + 1] - sptr[L.n_exact]) > (uint32_t)kGroupCh) L.n_exact++;
   std::vector<int32_t> hslice, hfirst;
   std::vector<int2> hseg;
-  for (int32_t s = 0; s < L.n_slices; s++) {
+  for (int32_t s = L.n_exact; s < L.n_slices; s++) {
     const uint32_t sz = sptr[s + 1] - sptr[s];
     if (sz <= L.group_ch) break;                         // widths are non-increasing
     hslice.push_back(s);
@@ -489,7 +501,7 @@ int pull_build_sell(gdn_graph *g) {
 // their one-touch sectors do not push the warm part out of L2.  Written as three PREDICATED loads (no
 // branches): the compiler's branchy version spent a fifth of its issue slots on reconvergence and left
 // the 16 loads of a trip interleaved with them (ncu r1: stall_mio 18 %, short scoreboard 30 %).
-__device__ __forceinline__ float pull_one(const SellArgs &a, uint32_t s_hot_addr, int c, uint64_t pol_first, uint64_t pol_last) {
+__device__ __forceinline__ float pull_one(const SellArgs &a, int32_t hot_n, uint32_t s_hot_addr, int c, uint64_t pol_first, uint64_t pol_last) {
   float v = 0.f;
   const float *p = a.contrib_in + c;
   const int32_t t = tier_id(a, c);
@@ -503,7 +515,7 @@ __device__ __forceinline__ float pull_one(const SellArgs &a, uint32_t s_hot_addr
       "@pw ld.global.nc.L2::cache_hint.f32 %0, [%5], %6;\n\t"
       "@pc ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%5], %7;\n\t}"
       : "+f"(v)
-      : "r"(c), "r"(a.hot_n), "r"(a.warm), "r"(s_hot_addr + 4u * (uint32_t)c), "l"(p), "l"(pol_last), "l"(pol_first), "r"(t));
+      : "r"(c), "r"(hot_n), "r"(a.warm), "r"(s_hot_addr + 4u * (uint32_t)c), "l"(p), "l"(pol_last), "l"(pol_first), "r"(t));
   return v;
 }
 
@@ -525,20 +537,32 @@ struct TripDesc {
   int32_t ref;
 };
 
+// Work distribution is dynamic: a warp draws batches of kBatch items from one device counter, so a warp that first walks
+// the long sequential chain of an exact slice simply draws fewer batches and nobody waits for it at the end of the launch.
+constexpr int kBatch = 8;
 template <int G>
 struct TripIter {
   const SellArgs &a;
-  int32_t item, nwarps;           // work items of one GPU fit 31 bits (checked by pr_run_sell)
+  int32_t item, item_end;         // batch in progress; work items of one GPU fit 31 bits (checked by pr_run_sell)
   int32_t s, s_end, sa;
   uint32_t g, g_end, lo, hi;      // lo/hi: slice_ptr[sa + lane], slice_ptr[sa + lane + 1] of the current chunk
   int32_t kind, ref;
   int lane;
-  __device__ __forceinline__ TripIter(const SellArgs &a_, int32_t warp, int32_t nwarps_, int lane_)
-      : a(a_), item(warp - nwarps_), nwarps(nwarps_), s(0), s_end(0), sa(0),
-        g(0), g_end(0), lo(0), hi(0), kind(0), ref(0), lane(lane_) {}
+  __device__ __forceinline__ TripIter(const SellArgs &a_, int lane_)
+      : a(a_), item(0), item_end(0), s(0), s_end(0), sa(0), g(0), g_end(0), lo(0), hi(0), kind(0), ref(0), lane(lane_) {}
   __device__ __forceinline__ void load_bounds() {
     lo = a.slice_ptr[min(sa + lane, s_end)];
     hi = a.slice_ptr[min(sa + lane + 1, s_end)];
+  }
+  __device__ __forceinline__ bool grab() {
+    const int32_t n_items = a.n_heavy_segs + a.n_chunks;
+    int32_t b = 0;
+    if (lane == 0) b = atomicAdd(a.work_counter, 1);
+    b = __shfl_sync(kFull, b, 0);
+    if (b > 0x7fffffff / kBatch) return false;
+    item = b * kBatch;
+    item_end = min(item + kBatch, n_items);
+    return item < n_items;
   }
   __device__ __forceinline__ TripDesc next() {
     for (;;) {
@@ -557,20 +581,20 @@ struct TripIter {
         const uint32_t g0 = __shfl_sync(kFull, lo, s - sa), g1 = __shfl_sync(kFull, hi, s - sa);
         ref = s;
         s++;
-        if (g1 - g0 > a.group_ch) continue;                  // wide slice: handled as segments
+        if (ref < a.n_exact || g1 - g0 > a.group_ch) continue;      // exact slice: the chain warps' work; wide slice: handled as segments
         g = g0; g_end = g1; kind = 1;
         continue;
       }
-      item += nwarps;
-      if (item >= a.n_chunks + a.n_heavy_segs || item < 0) { item = 0x7fffffff - nwarps; TripDesc d; d.g = 0; d.n = 0; d.fin = 0; d.ref = 0; return d; }
-      if (item < a.n_heavy_segs) {
-        const int2 hs = a.heavy_seg[item];
+      if (item >= item_end && (item_end < 0 || !grab())) { item_end = -1; TripDesc d; d.g = 0; d.n = 0; d.fin = 0; d.ref = 0; return d; }
+      const int32_t it = item++;
+      if (it < a.n_heavy_segs) {
+        const int2 hs = a.heavy_seg[it];
         const uint32_t s0 = a.slice_ptr[hs.x], s1 = a.slice_ptr[hs.x + 1];
         g = s0 + (uint32_t)hs.y * a.group_ch;
         g_end = (s1 - g > a.group_ch) ? g + a.group_ch : s1;
-        kind = 2; ref = item; s = s_end = 0;
+        kind = 2; ref = it; s = s_end = 0;
       } else {
-        const int32_t k = item - a.n_heavy_segs;
+        const int32_t k = it - a.n_heavy_segs;
         sa = a.chunk_slice[k]; s = sa; s_end = a.chunk_slice[k + 1];
         load_bounds();
         g = g_end = 0;
@@ -579,22 +603,197 @@ struct TripIter {
   }
 };
 
+// ------------------------------------------------------------------ exact slices: gather pass + TMA-fed sequential chain
+// Values of the exact slices in the layout of their index groups: vals[g] = contrib[sell[g]] (padding -> +0.0f, which
+// leaves an fp32 sum unchanged).  Whole grid, one int4 group per thread and step.
+__global__ void __launch_bounds__(256, 4)
+pr_exact_gather(SellArgs a, float4 *__restrict__ vals, uint32_t n_groups) {
+  if (*a.done) return;
+  const uint64_t pol = l2_policy_evict_first(), pol_last = l2_policy_evict_last();
+  for (uint32_t g = blockIdx.x * 256 + threadIdx.x; g < n_groups; g += gridDim.x * 256) {
+    const int4 c = ld_stream_v4(a.sell + g, pol);
+    const int id[4] = {c.x, c.y, c.z, c.w};
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      v[u] = 0.f;
+      if (id[u] >= 0) {
+        const float *p = a.contrib_in + id[u];
+        if (tier_id(a, id[u]) < a.warm) v[u] = ld_gather_f32(p, pol_last);
+        else asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v[u]) : "l"(p), "l"(pol));
+      }
+    }
+    vals[g] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (TMA, 1-D; SASS UBLKCP); dst/src 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_l2(const void *src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
+// The chain eats 128 bytes every ~4.5 cycles (the dependent fp32 add).  Its value stream comes through a ring of TMA bulk
+// copies fed by a PRODUCER warp (warp 1 of the CTA: full / empty mbarriers per buffer, L2 prefetches further ahead), so
+// that the chain warp itself only waits, loads from shared memory and adds.  Measured at Kronecker scale 26 (1.0 M
+// columns in the top slice): 17.8 cycles per column with the 31 other warps of the CTA gathering beside it (their sectors
+// queue ahead of the bulk copies on the SM's one request port to L2), 8.4 with the chain warp issuing its own copies and
+// the CTA otherwise idle -- hence a dedicated producer and a CTA that does nothing else until its chain is done.
+constexpr int kRingBufs = 3;              // chunks of the value stream in shared memory ...
+constexpr int kRingGroups = 64;           // ... of 64 index groups = 256 columns x 32 rows x 4 B = 32 KB each
+constexpr int kRingAhead = 8;             // chunks requested into L2 ahead of the ring
+constexpr size_t kChainSmem = (size_t)kChainHot * sizeof(float) + 256 + (size_t)kRingBufs * kRingGroups * 32 * sizeof(float4);
+// (both chain layouts fit the 192 KB of the full hot table: a launch that asks for more shared memory loses L1 on EVERY SM,
+// and the L1 hits of the ordinary gathers are worth 1.7 ms per iteration at Kronecker scale 26 -- measured)
+static_assert(2 * kRingBufs * sizeof(uint64_t) <= 256 && kChainSmem <= (size_t)kHotMax * sizeof(float), "chain CTA: table + barriers + ring within the full table's 192 KB");
+constexpr uint32_t kChunkUnits = kRingGroups * 32;          // float4 units per chunk
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Producer warp: the chunks of exact slices first, first + stride, ... in order, each into the next ring buffer once the
+// chain warp has released it.
+__device__ __forceinline__ void exact_chain_producer(const SellArgs &a, float4 *ring, uint64_t *full, uint64_t *empty, int lane, int first, int stride) {
+  uint32_t k = 0;                                             // running chunk index: buffer k % kRingBufs, phase k / kRingBufs
+  for (int e = first; e < a.n_exact; e += stride) {
+    const uint32_t g0 = a.slice_ptr[e], g1 = a.slice_ptr[e + 1];
+    const uint32_t ngl = (g1 - g0) >> 5;                      // groups per lane
+    const uint32_t n_chunks = (ngl + kRingGroups - 1) / kRingGroups;
+    const float4 *src = a.exact_vals + g0;
+    if (lane == 0)
+      for (uint32_t c = 0; c < (uint32_t)kRingAhead && c < n_chunks; c++)
+        tma_prefetch_l2(src + (size_t)c * kChunkUnits, min((uint32_t)kRingGroups, ngl - c * kRingGroups) * 32 * (uint32_t)sizeof(float4));
+    for (uint32_t c = 0; c < n_chunks; c++, k++) {
+      const uint32_t slot = k % kRingBufs;
+      mbar_wait(&empty[slot], ((k / kRingBufs) & 1u) ^ 1u);   // (passes at once the first time round)
+      if (lane == 0) {
+        const uint32_t bytes = min((uint32_t)kRingGroups, ngl - c * kRingGroups) * 32 * (uint32_t)sizeof(float4);
+        // no proxy fence: the buffer was only READ through the generic proxy and those loads had delivered before the release
+        mbar_expect_tx(&full[slot], bytes);
+        tma_load_1d(ring + (size_t)slot * kChunkUnits, src + (size_t)c * kChunkUnits, bytes, &full[slot]);
+        const uint32_t pc = c + kRingAhead;
+        if (pc < n_chunks) tma_prefetch_l2(src + (size_t)pc * kChunkUnits, min((uint32_t)kRingGroups, ngl - pc * kRingGroups) * 32 * (uint32_t)sizeof(float4));
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// Chain warp (lane = row): adds the rows of its slices sequentially in column order, src/pr/omp_base.cc:28-30.
+__device__ __forceinline__ void exact_chain(const SellArgs &a, const float4 *ring, uint64_t *full, uint64_t *empty, int lane, int first, int stride, double &err) {
+  uint32_t k = 0;
+  for (int e = first; e < a.n_exact; e += stride) {
+    const uint32_t g0 = a.slice_ptr[e], g1 = a.slice_ptr[e + 1];
+    const uint32_t ngl = (g1 - g0) >> 5;
+    const uint32_t n_chunks = (ngl + kRingGroups - 1) / kRingGroups;
+    float acc = 0.f;
+    for (uint32_t c = 0; c < n_chunks; c++, k++) {
+      const uint32_t slot = k % kRingBufs;
+      mbar_wait(&full[slot], (k / kRingBufs) & 1u);
+      const uint32_t n = min((uint32_t)kRingGroups, ngl - c * kRingGroups);
+      const float4 *t = ring + (size_t)slot * kChunkUnits + lane;
+      if (n == (uint32_t)kRingGroups) {
+        // four groups (16 columns) are read one step ahead of the 16 dependent adds that consume them
+        float4 a0 = t[0], a1 = t[32], a2 = t[64], a3 = t[96];
+#pragma unroll 4
+        for (int q = 4; q <= kRingGroups; q += 4) {
+          float4 b0 = a0, b1 = a1, b2 = a2, b3 = a3;
+          if (q < kRingGroups) { b0 = t[q * 32]; b1 = t[(q + 1) * 32]; b2 = t[(q + 2) * 32]; b3 = t[(q + 3) * 32]; }
+          acc = __fadd_rn(acc, a0.x); acc = __fadd_rn(acc, a0.y); acc = __fadd_rn(acc, a0.z); acc = __fadd_rn(acc, a0.w);
+          acc = __fadd_rn(acc, a1.x); acc = __fadd_rn(acc, a1.y); acc = __fadd_rn(acc, a1.z); acc = __fadd_rn(acc, a1.w);
+          acc = __fadd_rn(acc, a2.x); acc = __fadd_rn(acc, a2.y); acc = __fadd_rn(acc, a2.z); acc = __fadd_rn(acc, a2.w);
+          acc = __fadd_rn(acc, a3.x); acc = __fadd_rn(acc, a3.y); acc = __fadd_rn(acc, a3.z); acc = __fadd_rn(acc, a3.w);
+          a0 = b0; a1 = b1; a2 = b2; a3 = b3;
+        }
+      } else {
+        for (uint32_t q = 0; q < n; q++) {
+          const float4 v = t[q * 32];
+          acc = __fadd_rn(acc, v.x); acc = __fadd_rn(acc, v.y); acc = __fadd_rn(acc, v.z); acc = __fadd_rn(acc, v.w);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[slot]);
+    }
+    const int64_t j = (int64_t)e * 32 + lane;
+    if (j < a.n_nz_rows) pr_epilogue(a, j, acc, err);
+  }
+}
+
 // G index groups (4 G gathers) per lane and trip, D trips of gathers in flight per warp, THREADS / 32 warps per SM.
 template <int G, int D, int THREADS>
 __device__ __forceinline__ void pr_sell_pipe_body(const SellArgs &a) {
   extern __shared__ float s_hot[];
   if (*a.done) return;
-  for (int i = threadIdx.x; i < a.hot_n; i += THREADS) s_hot[i] = a.contrib_in[i];
+  // a CTA that hosts a chain warp trades most of its hot table for the chain's ring of value chunks
+  // CTAs that first add rows of exact slices: one slice per CTA in exact-order mode (a sequential chain), kOrdSplit CTAs
+  // per slice otherwise (ordered-sum emulation, kOrdRows rows each)
+  const bool chain_cta = (int)blockIdx.x < (a.strict_chain ? a.n_exact : a.n_exact * kOrdSplit);
+  const int32_t hot_n = chain_cta ? min(a.hot_n, kChainHot) : a.hot_n;
+  for (int i = threadIdx.x; i < hot_n; i += THREADS) s_hot[i] = a.contrib_in[i];
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int32_t warp = (int32_t)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
-  const int32_t nwarps = (int32_t)gridDim.x * (THREADS / 32);
   const uint64_t pol = l2_policy_evict_first(), pol_last = l2_policy_evict_last();
   const uint32_t s_hot_addr = (uint32_t)__cvta_generic_to_shared(s_hot);
   const int32_t *degs = a.sout ? a.sout : a.sdeg;
   double err = 0.0;
   float acc = 0.f;
-  TripIter<G> it(a, warp, nwarps, lane);
+  if (chain_cta && !a.strict_chain) {
+    // default mode: warp w < kOrdRows adds one row of the CTA's exact slices by ordered-sum emulation, its value ring behind
+    // the table.  The other warps wait: beside their gathers a 512-column block of the emulation took 3450 cycles instead
+    // of 1170 (issue slots and the SM's request port), which made the 1.0 M-column rows of Kronecker scale 26 the critical
+    // path of the launch; idle, they cost 3 % of the grid for a millisecond and the work queue hands their share on.
+    if (threadIdx.x < kOrdRows * 32) {
+      const int wib = threadIdx.x >> 5;
+      float4 *ring = reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(s_hot) + (size_t)kChainHot * sizeof(float)) + (size_t)wib * kOrdDepth * 32 * 4;
+      const int r = ((int)blockIdx.x % kOrdSplit) * kOrdRows + wib;          // row inside the slice
+      const int stride = max((int)gridDim.x / kOrdSplit, 1);
+      for (int e = (int)blockIdx.x / kOrdSplit; e < a.n_exact; e += stride) {
+        const uint32_t g0 = a.slice_ptr[e], g1 = a.slice_ptr[e + 1];
+        const int64_t j = (int64_t)e * 32 + r;
+        if (j < a.n_nz_rows) {
+          const float sum = ordered_row_sum(a.exact_vals + g0 + r, (g1 - g0) >> 5, ring, lane);
+          if (lane == 0) pr_epilogue(a, j, sum, err);
+        }
+      }
+    }
+    __syncthreads();
+  } else if (chain_cta) {
+    // barriers, then the ring, behind the (shortened) hot table; warp 0 = chain, warp 1 = producer.  The other warps of
+    // the CTA wait here too: their gathers would queue ahead of the chain's copies, and the chain is the critical path of
+    // the launch -- the dynamic work queue hands their share to the other SMs meanwhile.
+    unsigned char *base = reinterpret_cast<unsigned char *>(s_hot) + (size_t)kChainHot * sizeof(float);
+    uint64_t *full = reinterpret_cast<uint64_t *>(base), *empty = full + kRingBufs;
+    float4 *ring = reinterpret_cast<float4 *>(base + 256);
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < kRingBufs; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) exact_chain(a, ring, full, empty, lane, (int)blockIdx.x, (int)gridDim.x, err);
+    else if (threadIdx.x < 64) exact_chain_producer(a, ring, full, empty, lane, (int)blockIdx.x, (int)gridDim.x);
+    __syncthreads();
+  }
+  TripIter<G> it(a, lane);
   int4 I[2][G];              // index groups: requested one step before their gathers are issued
   float V[D][4 * G];         // gathered values of the D trips in flight
   float S[D];                // old score / degree of the row a trip finishes (requested with its gathers)
@@ -613,10 +812,10 @@ __device__ __forceinline__ void pr_sell_pipe_body(const SellArgs &a) {
   auto gather = [&](float (&W)[4 * G], const int4 (&X)[G], const TripDesc &d, float &Sc, int32_t &Dc) {
 #pragma unroll
     for (int u = 0; u < G; u++) {
-      W[4 * u + 0] = pull_one(a, s_hot_addr, X[u].x, pol, pol_last);
-      W[4 * u + 1] = pull_one(a, s_hot_addr, X[u].y, pol, pol_last);
-      W[4 * u + 2] = pull_one(a, s_hot_addr, X[u].z, pol, pol_last);
-      W[4 * u + 3] = pull_one(a, s_hot_addr, X[u].w, pol, pol_last);
+      W[4 * u + 0] = pull_one(a, hot_n, s_hot_addr, X[u].x, pol, pol_last);
+      W[4 * u + 1] = pull_one(a, hot_n, s_hot_addr, X[u].y, pol, pol_last);
+      W[4 * u + 2] = pull_one(a, hot_n, s_hot_addr, X[u].z, pol, pol_last);
+      W[4 * u + 3] = pull_one(a, hot_n, s_hot_addr, X[u].w, pol, pol_last);
     }
     if (d.fin == 1) {
       const int64_t j = (int64_t)d.ref * 32 + lane;
@@ -888,6 +1087,7 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
     GDN_CUDA(cudaMalloc((void **)&g->scores_sorted, sizeof(float) * std::max<int64_t>(L.rows, 1)));
     GDN_CUDA(cudaMalloc((void **)&g->err_trace, sizeof(double) * (GDN_MAX_PR_ITER + 8)));
     GDN_CUDA(cudaMalloc((void **)&g->pr_done, sizeof(int32_t)));
+    GDN_CUDA(cudaMalloc((void **)&g->pr_work, sizeof(int32_t)));
     GDN_CUDA(cudaMalloc((void **)&g->abs_partial, sizeof(double) * igrid * 8));
     GDN_CUDA(cudaMemsetAsync(g->contrib[0], 0, sizeof(float) * (L.Mp + 64), s));
     GDN_CUDA(cudaMemsetAsync(g->contrib[1], 0, sizeof(float) * (L.Mp + 64), s));
@@ -907,7 +1107,11 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
     g->n_err_partial = n_partial;
   }
   if (max_iter > GDN_MAX_PR_ITER - 1) max_iter = GDN_MAX_PR_ITER - 1;
-  const size_t smem = sizeof(float) * (size_t)L.H;
+  const size_t smem = std::max(sizeof(float) * (size_t)L.H, L.n_exact > 0 ? std::max(kChainSmem, kOrdSmem) : (size_t)0);
+  if (L.n_exact > 0 && !L.exact_vals) {
+    GDN_CUDA(cudaMalloc((void **)&L.exact_vals, sizeof(float4) * (size_t)L.h_slice_ptr[L.n_exact] + 256));
+    g->device_bytes += sizeof(float4) * (size_t)L.h_slice_ptr[L.n_exact];
+  }
   // L2 residency tiers of the gathered vector (see pull_one): 48 MB measured best at Kron-26 (32: +4 %, 64: +5 %, 96: +17 %)
   const char *e_warm = getenv("GDN_PR_WARM_MB");
   const int64_t warm_ids = (int64_t)(e_warm ? atoi(e_warm) : 48) * (1 << 20) / 4;
@@ -923,7 +1127,8 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
   a.n_nz_rows = L.n_nz_rows; a.rows = L.rows; a.H = (int32_t)L.H; a.hot_n = (int32_t)L.H; a.Hp = L.Hp; a.Wc = L.Wc; a.rank = L.R;
   a.base = (1.0f - damp) / (float)(int32_t)g->m;            // src/pr/omp_base.cc:16
   a.damp = damp; a.err_partial = g->err_partial; a.done = g->pr_done;
-  a.group_ch = L.group_ch;
+  a.strict_chain = L.exact ? 1 : 0;
+  a.group_ch = L.group_ch; a.n_exact = L.n_exact; a.work_counter = g->pr_work; a.exact_vals = L.exact_vals;
   a.P = L.P; a.inv_wc = L.Wc > 0 ? 1.0f / (float)L.Wc : 0.f;
   // the warm budget is shared by the ranks' slices (tier_id): every rank's hottest cold ids stay L2-resident
   a.warm = (int32_t)std::min<int64_t>(L.P > 1 ? L.H + std::max<int64_t>(warm_ids - L.H, 0) / L.P : warm_ids, 0x7fffffff);
@@ -987,6 +1192,11 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
     if (banded) {
       GDN_CHECK(band_launch(g, a, fix_scale, s));
       launches += band_launches(g);
+    }
+    GDN_CUDA(cudaMemsetAsync(g->pr_work, 0, sizeof(int32_t), s));
+    if (L.n_exact > 0) {
+      pr_exact_gather<<<sm * 8, 256, 0, s>>>(a, L.exact_vals, L.h_slice_ptr[L.n_exact]);
+      launches++;
     }
     kern<<<sm, kSellThreads, smem, s>>>(a);
     if (!banded) kev_end();

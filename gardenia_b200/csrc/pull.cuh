@@ -7,6 +7,8 @@ namespace gdn {
 constexpr int kHotMax = 49152;          // fp32 entries in the shared-memory table (192 KB)
 constexpr int kGroupCh = 1024;          // int4 groups per work item (= 4096 column ids)
 constexpr int kSellThreads = 1024;      // one CTA per SM
+constexpr int kExactCols = 65536;        // slices wider than this keep the reference's summation order (pull.cu pull_prepare)
+constexpr int kExactColsStrict = 8192;   // ... in exact-order mode, where narrower slices are whole items of one warp
 constexpr int kMaxPeers = 7;            // other GPUs of one box whose vectors a row epilogue writes
 
 struct SellArgs {
@@ -37,6 +39,10 @@ struct SellArgs {
   int32_t P;                   // ranks of the row partition the id space was laid out for
   float inv_wc;                // 1 / Wc
   uint32_t group_ch;           // int4 groups per work item; slices wider than this are cut into segments (0xffffffff: never, exact order)
+  int32_t n_exact;             // the first n_exact slices are exact slices: one item each, never cut, never banded
+  int32_t *work_counter;       // batches of work items drawn so far by the warps of this launch
+  int32_t strict_chain;        // exact-order mode: exact slices by a true sequential chain (bit-exact) instead of the ordered-sum emulation
+  const float4 *exact_vals;    // gathered values of the exact slices (pr_exact_gather), laid out like their index groups
   // banded layout (band.cu): sorted rows below n_band_rows (a multiple of 32) only deposit the sum over the columns left
   // in the main array; pr_band_finalize adds their band partials and runs the row epilogue
   int64_t n_band_rows;

@@ -54,7 +54,7 @@ typedef enum {
 /* One step of the direction-optimizing controller (src/bfs/omp_beamer.cc:135-160). */
 typedef struct {
   int32_t dir;          /* 0 top-down, 1 bottom-up */
-  int32_t pad;
+  int32_t ns;           /* duration of the step on the device, nanoseconds (single-GPU path; 0 in partitioned mode) */
   int64_t frontier;     /* |frontier| expanded by this step */
   int64_t discovered;   /* vertices that received a depth */
   int64_t scout;        /* TD: scout_count, BU: awake_count */

@@ -179,8 +179,14 @@ def test_edge_shapes(shape):
         # test, PRVerifier residual, src/pr/verifier.cc:40-54, holds).  The exact-order mode sums
         # every row in column order in one lane and reproduces the reference bit for bit,
         # including its 101 iterations.
-        assert oit == 101 and st.iterations < 101
-        assert po.pr_residual(m, rp, ci, scores) < 1e-4
+        assert oit == 101
+        if shape == "star":
+            # its one hub row (70 000 entries) is an exact slice (csrc/pull.cu: rows longer than 65 536 keep the
+            # reference's order in the default mode too): same 101 iterations, same bits (and the same residual)
+            assert st.iterations == oit and np.array_equal(scores, oscores)
+        else:
+            assert st.iterations < 101
+            assert po.pr_residual(m, rp, ci, scores) < 1e-4
         _lib.check(_lib.lib.gdn_set_pr_exact_order(1))
         try:
             ex = np.full(m, np.float32(1.0) / np.float32(m), dtype=np.float32)
@@ -595,5 +601,7 @@ def test_bfs_long_diameter_and_tiny_graphs():
             odist, oit, osteps = po.bfs_do(m, rp, ci, rp, ci, s)
             assert np.array_equal(dist, odist), (name, s)
             assert st.iterations == oit, (name, s, st.iterations, oit)
-            assert [x["dir"] for x in st.bfs_steps()] == [x["dir"] for x in osteps], (name, s)
+            assert st.n_steps == len(osteps)
+            nrec = min(st.n_steps, _lib.GDN_MAX_BFS_STEPS)              # (the step log keeps the first 256 steps)
+            assert [x["dir"] for x in st.bfs_steps()] == [x["dir"] for x in osteps[:nrec]], (name, s)
             assert po.bfs_check_parents(m, rp, ci, s, dist, parent) == 0
