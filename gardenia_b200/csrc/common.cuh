@@ -160,7 +160,11 @@ struct PullLayout {
   int32_t *rowid = nullptr;    // [rows]  new global id of sorted row j (only when !symmetric_order)
   uint32_t *slice_ptr = nullptr;   // [n_slices+1] in int4 groups
   int4 *sell = nullptr;            // [n_groups]   built lazily on the first PageRank call
-  float4 *exact_vals = nullptr;    // [slice_ptr[n_exact]] gathered values of the exact slices, rewritten every iteration
+  float4 *exact_vals = nullptr;    // gathered values of the exact slices, rewritten every iteration (layout: see pull.cu exact_setup)
+  int32_t x_blocks = 0, x_tiles = 0;   // ordered-sum blocks of the exact rows (ordered_sum.cuh), tiles of 32 rows x 1 block, tables
+  uint32_t *x_blk_base = nullptr, *x_tile_base = nullptr /* same allocation */, *x_mx = nullptr, *x_Q = nullptr;
+  double *x_S = nullptr;
+  uint8_t *x_plan = nullptr;
   int32_t n_chunks = 0;
   int32_t *chunk_slice = nullptr;  // [n_chunks+1]
   int32_t n_heavy_slices = 0, n_heavy_segs = 0, n_fill_wide = 0;

@@ -407,7 +407,8 @@ int gdn_graph_destroy(gdn_graph *g) {
   {
     gdn::PullLayout &L = g->pull;
     cudaFree(L.perm); cudaFree(L.newid); cudaFree(L.sdeg); cudaFree(L.sout); cudaFree(L.rowid); cudaFree(L.slice_ptr);
-    cudaFree(L.sell); cudaFree(L.exact_vals); cudaFree(L.chunk_slice); cudaFree(L.heavy_slice); cudaFree(L.heavy_first); cudaFree(L.heavy_seg);
+    cudaFree(L.sell); cudaFree(L.exact_vals); cudaFree(L.x_blk_base); cudaFree(L.x_mx); cudaFree(L.x_Q); cudaFree(L.x_S); cudaFree(L.x_plan);
+    cudaFree(L.chunk_slice); cudaFree(L.heavy_slice); cudaFree(L.heavy_first); cudaFree(L.heavy_seg);
     cudaFree(L.partial); cudaFree(g->scores_sorted);
     gdn::band_free(L.band);
   }

@@ -241,9 +241,9 @@ int pull_prepare(gdn_graph *g, const HostOffT *row_off, const HostOffT *key_off)
   // sequentially in column order like src/pr/omp_base.cc:28-30.  On a long row the fp32 rounding of a re-ordered sum differs
   // from the reference's by ~ sqrt(length) ulps; at Kronecker scale 26 (rows of 10^6 entries that carry percents of the
   // score mass) that alone is 1.15e-6 of L1 distance -- over the 1e-6 parity bar (profiles/r2_pr_exact_threshold.txt:
-  // 0.65e-6 with the 11 slices wider than 65536 columns exact).  A dependent chain of a million adds is 2 ms whatever feeds
-  // it, so the gathers are taken out of it: pr_exact_gather (whole grid) writes the slices' VALUES in column order, and
-  // the chain warp of pr_sell_pipe streams them through a TMA-fed shared-memory ring while the other warps do the rest.
+  // 0.65e-6 with the 11 slices wider than 65536 columns exact).  A dependent chain of a million adds is 3.4 ms whatever
+  // feeds it, so these rows are summed by the block-parallel emulation of ordered_sum.cuh (same bits, no chain); the
+  // exact-order mode keeps a true chain (values gathered by the whole grid, streamed through a TMA-fed ring).
   const char *e_xc = getenv("GDN_PR_EXACT_COLS");
   const int64_t exact_cols = e_xc ? atoll(e_xc) : (L.exact ? kExactColsStrict : kExactCols);
   L.n_exact = 0;
@@ -603,11 +603,12 @@ struct TripIter {
   }
 };
 
-// ------------------------------------------------------------------ exact slices: gather pass + TMA-fed sequential chain
+// ------------------------------------------------------------------ exact slices, exact-order mode: gather pass + TMA-fed sequential chain
+// (the default mode sums them by the block-parallel emulation of ordered_sum.cuh)
 // Values of the exact slices in the layout of their index groups: vals[g] = contrib[sell[g]] (padding -> +0.0f, which
 // leaves an fp32 sum unchanged).  Whole grid, one int4 group per thread and step.
 __global__ void __launch_bounds__(256, 4)
-pr_exact_gather(SellArgs a, float4 *__restrict__ vals, uint32_t n_groups) {
+pr_exact_gather_sell(SellArgs a, float4 *__restrict__ vals, uint32_t n_groups) {
   if (*a.done) return;
   const uint64_t pol = l2_policy_evict_first(), pol_last = l2_policy_evict_last();
   for (uint32_t g = blockIdx.x * 256 + threadIdx.x; g < n_groups; g += gridDim.x * 256) {
@@ -657,6 +658,7 @@ __device__ __forceinline__ void tma_prefetch_l2(const void *src, uint32_t bytes)
 // columns in the top slice): 17.8 cycles per column with the 31 other warps of the CTA gathering beside it (their sectors
 // queue ahead of the bulk copies on the SM's one request port to L2), 8.4 with the chain warp issuing its own copies and
 // the CTA otherwise idle -- hence a dedicated producer and a CTA that does nothing else until its chain is done.
+constexpr int kChainHot = 16384;          // hot-table entries of a CTA that hosts a chain warp (64 KB)
 constexpr int kRingBufs = 3;              // chunks of the value stream in shared memory ...
 constexpr int kRingGroups = 64;           // ... of 64 index groups = 256 columns x 32 rows x 4 B = 32 KB each
 constexpr int kRingAhead = 8;             // chunks requested into L2 ahead of the ring
@@ -744,9 +746,8 @@ __device__ __forceinline__ void pr_sell_pipe_body(const SellArgs &a) {
   extern __shared__ float s_hot[];
   if (*a.done) return;
   // a CTA that hosts a chain warp trades most of its hot table for the chain's ring of value chunks
-  // CTAs that first add rows of exact slices: one slice per CTA in exact-order mode (a sequential chain), kOrdSplit CTAs
-  // per slice otherwise (ordered-sum emulation, kOrdRows rows each)
-  const bool chain_cta = (int)blockIdx.x < (a.strict_chain ? a.n_exact : a.n_exact * kOrdSplit);
+  // exact-order mode: CTA c first walks exact slices c, c + grid, ... as a true sequential chain (a.strict_chain)
+  const bool chain_cta = a.strict_chain && (int)blockIdx.x < a.n_exact;
   const int32_t hot_n = chain_cta ? min(a.hot_n, kChainHot) : a.hot_n;
   for (int i = threadIdx.x; i < hot_n; i += THREADS) s_hot[i] = a.contrib_in[i];
   __syncthreads();
@@ -757,27 +758,7 @@ __device__ __forceinline__ void pr_sell_pipe_body(const SellArgs &a) {
   const int32_t *degs = a.sout ? a.sout : a.sdeg;
   double err = 0.0;
   float acc = 0.f;
-  if (chain_cta && !a.strict_chain) {
-    // default mode: warp w < kOrdRows adds one row of the CTA's exact slices by ordered-sum emulation, its value ring behind
-    // the table.  The other warps wait: beside their gathers a 512-column block of the emulation took 3450 cycles instead
-    // of 1170 (issue slots and the SM's request port), which made the 1.0 M-column rows of Kronecker scale 26 the critical
-    // path of the launch; idle, they cost 3 % of the grid for a millisecond and the work queue hands their share on.
-    if (threadIdx.x < kOrdRows * 32) {
-      const int wib = threadIdx.x >> 5;
-      float4 *ring = reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(s_hot) + (size_t)kChainHot * sizeof(float)) + (size_t)wib * kOrdDepth * 32 * 4;
-      const int r = ((int)blockIdx.x % kOrdSplit) * kOrdRows + wib;          // row inside the slice
-      const int stride = max((int)gridDim.x / kOrdSplit, 1);
-      for (int e = (int)blockIdx.x / kOrdSplit; e < a.n_exact; e += stride) {
-        const uint32_t g0 = a.slice_ptr[e], g1 = a.slice_ptr[e + 1];
-        const int64_t j = (int64_t)e * 32 + r;
-        if (j < a.n_nz_rows) {
-          const float sum = ordered_row_sum(a.exact_vals + g0 + r, (g1 - g0) >> 5, ring, lane);
-          if (lane == 0) pr_epilogue(a, j, sum, err);
-        }
-      }
-    }
-    __syncthreads();
-  } else if (chain_cta) {
+  if (chain_cta) {
     // barriers, then the ring, behind the (shortened) hot table; warp 0 = chain, warp 1 = producer.  The other warps of
     // the CTA wait here too: their gathers would queue ahead of the chain's copies, and the chain is the critical path of
     // the launch -- the dynamic work queue hands their share to the other SMs meanwhile.
@@ -1063,6 +1044,50 @@ static double fix_scale_for(double tsum) {
   return ldexp(1.0, bits);
 }
 
+// Buffers of the exact slices.  Exact-order mode: the slices' values in the layout of their index groups.  Default mode: the
+// row-major value blocks and per-block tables of ordered_sum.cuh.
+static int exact_setup(gdn_graph *g) {
+  PullLayout &L = g->pull;
+  if (L.exact) {
+    GDN_CUDA(cudaMalloc((void **)&L.exact_vals, sizeof(float4) * (size_t)L.h_slice_ptr[L.n_exact] + 256));
+    g->device_bytes += sizeof(float4) * (size_t)L.h_slice_ptr[L.n_exact];
+    return GDN_OK;
+  }
+  std::vector<uint32_t> base((size_t)L.n_exact + 1), tbase((size_t)L.n_exact + 1);
+  uint64_t tot = 0, tiles = 0;
+  for (int32_t e = 0; e < L.n_exact; e++) {
+    base[e] = (uint32_t)tot;
+    tbase[e] = (uint32_t)tiles;
+    const uint32_t ngl = (L.h_slice_ptr[e + 1] - L.h_slice_ptr[e]) >> 5;
+    const uint32_t nb = (ngl + kOrdBlockGroups - 1) / kOrdBlockGroups;
+    tot += 32ull * nb;
+    tiles += nb;
+    if (tot > 0x7fffffffull) { L.n_exact = e; break; }                 // (cannot happen below 2^31 * 512 columns; keeps the 32-bit block index honest)
+  }
+  base[L.n_exact] = (uint32_t)tot;
+  tbase[L.n_exact] = (uint32_t)tiles;
+  L.x_blocks = (int32_t)tot;
+  L.x_tiles = (int32_t)tiles;
+  GDN_CUDA(cudaMalloc((void **)&L.x_blk_base, sizeof(uint32_t) * 2 * base.size()));
+  L.x_tile_base = L.x_blk_base + base.size();
+  GDN_CUDA(cudaMemcpyAsync(L.x_blk_base, base.data(), sizeof(uint32_t) * base.size(), cudaMemcpyHostToDevice, lib().stream));
+  GDN_CUDA(cudaMemcpyAsync(L.x_tile_base, tbase.data(), sizeof(uint32_t) * tbase.size(), cudaMemcpyHostToDevice, lib().stream));
+  GDN_CUDA(cudaStreamSynchronize(lib().stream));
+  GDN_CUDA(cudaMalloc((void **)&L.exact_vals, sizeof(float4) * (size_t)tot * kOrdBlockGroups + 256));
+  GDN_CUDA(cudaMalloc((void **)&L.x_S, sizeof(double) * (size_t)tot));
+  GDN_CUDA(cudaMalloc((void **)&L.x_mx, sizeof(uint32_t) * (size_t)tot));
+  GDN_CUDA(cudaMalloc((void **)&L.x_Q, sizeof(uint32_t) * (size_t)tot));
+  GDN_CUDA(cudaMalloc((void **)&L.x_plan, (size_t)tot + 16));
+  g->device_bytes += (sizeof(float4) * kOrdBlockGroups + 17) * (size_t)tot;
+  return GDN_OK;
+}
+static ExactArgs exact_args(const PullLayout &L) {
+  ExactArgs x;
+  x.n_exact = L.n_exact; x.n_blocks_total = L.x_blocks; x.blk_base = L.x_blk_base; x.vals = L.exact_vals;
+  x.S = L.x_S; x.mx = L.x_mx; x.plan = L.x_plan; x.Q = L.x_Q;
+  return x;
+}
+
 int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_iter, gdn_stats *st) {
   PullLayout &L = g->pull;
   GDN_CHECK(pull_build_sell(g));
@@ -1080,7 +1105,8 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
   const int fgrid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)max_heavy_slices, (int64_t)sm * 8));   // one CTA per wide slice
   const int igrid = sm * 8;                        // pr_sell_load's grid: its warps own the error partials of the settled rows
   const int bgrid = L.band.built ? band_finalize_grid(g) : 0;
-  const int n_partial = sm * wpc + fgrid * 8 + igrid * 8 + bgrid * 8;
+  const int xgrid = (L.n_exact * 32 + 7) / 8;       // pr_exact_combine: one warp per exact row
+  const int n_partial = sm * wpc + fgrid * 8 + igrid * 8 + bgrid * 8 + xgrid * 8;
   if (!g->contrib[0]) {
     GDN_CUDA(cudaMalloc((void **)&g->contrib[0], sizeof(float) * (L.Mp + 64)));
     GDN_CUDA(cudaMalloc((void **)&g->contrib[1], sizeof(float) * (L.Mp + 64)));
@@ -1107,11 +1133,8 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
     g->n_err_partial = n_partial;
   }
   if (max_iter > GDN_MAX_PR_ITER - 1) max_iter = GDN_MAX_PR_ITER - 1;
-  const size_t smem = std::max(sizeof(float) * (size_t)L.H, L.n_exact > 0 ? std::max(kChainSmem, kOrdSmem) : (size_t)0);
-  if (L.n_exact > 0 && !L.exact_vals) {
-    GDN_CUDA(cudaMalloc((void **)&L.exact_vals, sizeof(float4) * (size_t)L.h_slice_ptr[L.n_exact] + 256));
-    g->device_bytes += sizeof(float4) * (size_t)L.h_slice_ptr[L.n_exact];
-  }
+  const size_t smem = std::max(sizeof(float) * (size_t)L.H, (L.exact && L.n_exact > 0) ? kChainSmem : (size_t)0);
+  if (L.n_exact > 0 && !L.exact_vals) GDN_CHECK(exact_setup(g));
   // L2 residency tiers of the gathered vector (see pull_one): 48 MB measured best at Kron-26 (32: +4 %, 64: +5 %, 96: +17 %)
   const char *e_warm = getenv("GDN_PR_WARM_MB");
   const int64_t warm_ids = (int64_t)(e_warm ? atoi(e_warm) : 48) * (1 << 20) / 4;
@@ -1182,6 +1205,16 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
   constexpr int kRing = 4;
   if (!lib().pr_ev[0])
     for (int i = 0; i < kRing; i++) GDN_CUDA(cudaEventCreateWithFlags(&lib().pr_ev[i], cudaEventDisableTiming));
+  // GDN_PR_KTIME=1: CUDA-event time of every launch of the third iteration, in place (not under a profiler), on stderr
+  static cudaEvent_t kt_ev[16];
+  static bool kt_init = false;
+  const bool ktime = getenv("GDN_PR_KTIME") != nullptr;
+  if (ktime && !kt_init) { for (auto &e : kt_ev) cudaEventCreate(&e); kt_init = true; }
+  int kt_n = 0;
+  const char *kt_name[16] = {};
+  auto probe = [&](int iter, const char *name) {
+    if (ktime && iter == 2 && kt_n < 16) { cudaEventRecord(kt_ev[kt_n], s); kt_name[kt_n++] = name; }
+  };
   auto enqueue = [&](int iter) -> int {
     const int cur = iter & 1;
     a.contrib_in = g->contrib[cur];
@@ -1189,16 +1222,27 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
     if (peer) pull_peer_args(g, cur ^ 1, a);
     a.err_slot0 = 0;
     kev_begin();
+    probe(iter, "start");
     if (banded) {
       GDN_CHECK(band_launch(g, a, fix_scale, s));
       launches += band_launches(g);
+      probe(iter, "band sums");
     }
     GDN_CUDA(cudaMemsetAsync(g->pr_work, 0, sizeof(int32_t), s));
-    if (L.n_exact > 0) {
-      pr_exact_gather<<<sm * 8, 256, 0, s>>>(a, L.exact_vals, L.h_slice_ptr[L.n_exact]);
+    if (L.n_exact > 0 && L.exact) {                    // exact-order mode: values for the chain warps of the main kernel
+      pr_exact_gather_sell<<<sm * 8, 256, 0, s>>>(a, L.exact_vals, L.h_slice_ptr[L.n_exact]);
       launches++;
+    } else if (L.n_exact > 0) {                       // default mode: block-parallel ordered sum, passes 1 - 3 (ordered_sum.cuh)
+      const ExactArgs xa = exact_args(L);
+      pr_exact_gather<<<sm * 8, 256, 0, s>>>(a, xa);
+      probe(iter, "exact gather");
+      pr_exact_plan<<<(L.n_exact * 32 + 7) / 8, 256, 0, s>>>(a, xa);
+      pr_exact_qsum<<<sm * 8, 256, 0, s>>>(a, xa);
+      launches += 3;
+      probe(iter, "exact plan + qsum");
     }
     kern<<<sm, kSellThreads, smem, s>>>(a);
+    probe(iter, "main sums");
     if (!banded) kev_end();
     launches++;
     if (n_heavy_slices > 0) {
@@ -1206,10 +1250,17 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
       pr_sell_finalize<<<fgrid, 256, 0, s>>>(a);
       launches++;
     }
+    if (L.n_exact > 0 && !L.exact) {                  // pass 4: the exact rows' sums, in order -> epilogue (or acc_main of a band row)
+      a.err_slot0 = sm * wpc + fgrid * 8 + igrid * 8 + bgrid * 8;
+      pr_exact_combine<<<xgrid, 256, 0, s>>>(a, exact_args(L));
+      launches++;
+      probe(iter, "exact combine");
+    }
     if (banded) {
       // the iteration of the banded layout is band sums + main sums + the two finalize launches: timed as one
       a.err_slot0 = sm * wpc + fgrid * 8 + igrid * 8;
       GDN_CHECK(band_finalize_launch(g, a, fix_scale, bgrid, s));
+      probe(iter, "finalize");
       kev_end();
       launches++;
     }
@@ -1256,6 +1307,11 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
   GDN_CUDA(cudaStreamSynchronize(s));
   GDN_CUDA(cudaGetLastError());
   if (peer) GDN_CHECK(pull_peer_check());
+  if (ktime && kt_n > 1) {
+    fprintf(stderr, "[gdn] iteration 3, per launch (ms):");
+    for (int i = 1; i < kt_n; i++) { float ms = 0; cudaEventElapsedTime(&ms, kt_ev[i - 1], kt_ev[i]); fprintf(stderr, "  %s %.3f", kt_name[i], ms); }
+    fprintf(stderr, "\n");
+  }
   if (st) {
     float ms = 0;
     GDN_CUDA(cudaEventElapsedTime(&ms, lib().ev0, lib().ev1));

@@ -1,1 +1,2 @@
-python tools/pr_exact_sweep.py 26 "GDN_PR_EXACT_COLS=65536;GDN_PR_EXACT_COLS=32768;GDN_PR_EXACT_COLS=1000000000" 2>&1 | grep -v "^\[bench\]" | cut -c1-260 | tail -9
+export GDN_PR_KTIME=1
+python tools/pr_exact_sweep.py 26 "GDN_PR_EXACT_COLS=65536;GDN_PR_EXACT_COLS=1000000000" 2>&1 | grep -v "^\[bench\]" | cut -c1-330 | tail -9
