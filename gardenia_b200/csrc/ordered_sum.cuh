@@ -131,6 +131,13 @@ pr_exact_gather(SellArgs a, ExactArgs x) {
   for (uint32_t k = warp; k < (uint32_t)x.n_blocks_total; k += nwarps) {
     int e, r; uint32_t b, nb;
     exact_locate(x, k, e, r, b, nb);
+    // blocks past the end of THIS row (the slice is as wide as its longest row) hold padding only: their values were
+    // zeroed once (exact_setup), their sum is zero
+    const uint32_t row_groups = ((uint32_t)a.sdeg[e * 32 + r] + 3) >> 2;
+    if (b * kOrdBlockGroups >= row_groups) {
+      if (lane == 0) { x.S[k] = 0.0; x.mx[k] = 0u; }
+      continue;
+    }
     const uint32_t g0 = a.slice_ptr[e], ngl = (a.slice_ptr[e + 1] - g0) >> 5;
     double s = 0.0;
     uint32_t mbits = 0;
@@ -210,6 +217,7 @@ pr_exact_qsum(SellArgs a, ExactArgs x) {
   for (uint32_t k = warp; k < (uint32_t)x.n_blocks_total; k += nwarps) {
     const uint32_t ex = x.plan[k];
     if (ex == 0) continue;                                                 // warp-uniform
+    if (x.mx[k] == 0u) { if (lane == 0) x.Q[k] = 0u; continue; }           // nothing but zeros (padding past the end of the row)
     const float scale = ord_scale(ex);
     const float4 *src = x.vals + (size_t)k * kOrdBlockGroups + lane * 4;
     uint32_t run = 0;

@@ -241,13 +241,21 @@ int pull_prepare(gdn_graph *g, const HostOffT *row_off, const HostOffT *key_off)
   // sequentially in column order like src/pr/omp_base.cc:28-30.  On a long row the fp32 rounding of a re-ordered sum differs
   // from the reference's by ~ sqrt(length) ulps; at Kronecker scale 26 (rows of 10^6 entries that carry percents of the
   // score mass) that alone is 1.15e-6 of L1 distance -- over the 1e-6 parity bar (profiles/r2_pr_exact_threshold.txt:
-  // 0.65e-6 with the 11 slices wider than 65536 columns exact).  A dependent chain of a million adds is 3.4 ms whatever
+  // 0.58e-6 with the one slice wider than 2^18 columns exact, 0.65e-6 with the 11 wider than 2^16, 0.17e-6 with 559).  A dependent chain of a million adds is 3.4 ms whatever
   // feeds it, so these rows are summed by the block-parallel emulation of ordered_sum.cuh (same bits, no chain); the
   // exact-order mode keeps a true chain (values gathered by the whole grid, streamed through a TMA-fed ring).
   const char *e_xc = getenv("GDN_PR_EXACT_COLS");
   const int64_t exact_cols = e_xc ? atoll(e_xc) : (L.exact ? kExactColsStrict : kExactCols);
+  // ... as long as they stay cheap: their ids are mostly cold (a hub row points everywhere), one HBM sector per gather,
+  // whereas the banded layout serves most of them from shared memory -- so the default mode spends at most 3 % of the
+  // non-zeros (or 48 M, whichever is more; slots of the slices, padding included) on exact slices, widest first
+  // (profiles/r2_pr_exact_threshold.txt).  GDN_PR_EXACT_BUDGET (slots) overrides.
+  const char *e_xb = getenv("GDN_PR_EXACT_BUDGET");
+  const uint64_t budget = L.exact ? ~0ull : (e_xb ? strtoull(e_xb, nullptr, 10) : std::max<uint64_t>((uint64_t)(row_off[hi] - row_off[lo]) * 3 / 100, 48ull << 20));
   L.n_exact = 0;
-  while (L.n_exact < L.n_slices && width[L.n_exact] > exact_cols && (sptr[L.n_exact + 1] - sptr[L.n_exact]) > (uint32_t)kGroupCh) L.n_exact++;
+  while (L.n_exact < L.n_slices && width[L.n_exact] > exact_cols && (sptr[L.n_exact + 1] - sptr[L.n_exact]) > (uint32_t)kGroupCh &&
+         (uint64_t)sptr[L.n_exact + 1] * 4 <= budget)
+    L.n_exact++;
   std::vector<int32_t> hslice, hfirst;
   std::vector<int2> hseg;
   for (int32_t s = L.n_exact; s < L.n_slices; s++) {
@@ -1074,6 +1082,7 @@ static int exact_setup(gdn_graph *g) {
   GDN_CUDA(cudaMemcpyAsync(L.x_tile_base, tbase.data(), sizeof(uint32_t) * tbase.size(), cudaMemcpyHostToDevice, lib().stream));
   GDN_CUDA(cudaStreamSynchronize(lib().stream));
   GDN_CUDA(cudaMalloc((void **)&L.exact_vals, sizeof(float4) * (size_t)tot * kOrdBlockGroups + 256));
+  GDN_CUDA(cudaMemsetAsync(L.exact_vals, 0, sizeof(float4) * (size_t)tot * kOrdBlockGroups + 256, lib().stream));   // (padding blocks stay zero)
   GDN_CUDA(cudaMalloc((void **)&L.x_S, sizeof(double) * (size_t)tot));
   GDN_CUDA(cudaMalloc((void **)&L.x_mx, sizeof(uint32_t) * (size_t)tot));
   GDN_CUDA(cudaMalloc((void **)&L.x_Q, sizeof(uint32_t) * (size_t)tot));

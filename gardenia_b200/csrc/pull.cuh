@@ -7,7 +7,7 @@ namespace gdn {
 constexpr int kHotMax = 49152;          // fp32 entries in the shared-memory table (192 KB)
 constexpr int kGroupCh = 1024;          // int4 groups per work item (= 4096 column ids)
 constexpr int kSellThreads = 1024;      // one CTA per SM
-constexpr int kExactCols = 65536;        // slices wider than this keep the reference's summation order (pull.cu pull_prepare)
+constexpr int kExactCols = 262144;       // slices wider than this keep the reference's summation order (pull.cu pull_prepare)
 constexpr int kExactColsStrict = 8192;   // ... in exact-order mode, where narrower slices are whole items of one warp
 constexpr int kMaxPeers = 7;            // other GPUs of one box whose vectors a row epilogue writes
 
