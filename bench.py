@@ -428,46 +428,40 @@ def bench_pr(ctx, args):
     e2e_s = 0.0
     e2e_calls, e2e_parts = [], []
     e2e_l1 = None
-    for k in range(e2e_steps + 1):
-        if world == 1:
-            hs = h_scores.numpy()
+    # N > 1: the SAME call, from ONE process: gdn_init_gpus(N) makes the library split every one-shot solve over the N GPUs
+    # (a worker thread per GPU, each uploading its rows over its own PCIe link).  Rank 0 makes the calls, the other ranks of
+    # the launch have released their GPUs' memory and wait.
+    if rank == 0:
+        if world > 1:
+            _lib.check(_lib.lib.gdn_init_gpus(world))
+        full = torch.empty(m, dtype=torch.float32).pin_memory() if world > 1 else h_scores
+        for k in range(e2e_steps + 1):
+            hs = full.numpy()
             hs.fill(init)
             t_call = time.perf_counter()
             st = gb.PRSolver(g, hs, verbose=False)           # upload + layout + solve + download inside the call
             dt = time.perf_counter() - t_call
             h2d, d2h = st.h2d_bytes, st.d2h_bytes
-        else:
-            h_scores.fill_(init)
-            ctx.barrier()
-            # one solve per upload: the banded layout would not amortise -- plain SELL layout, as the one-shot entry point chooses
-            os.environ["GDN_PR_BANDS"] = "0"
-            t_call = time.perf_counter()
-            dgi = gb.DeviceGraph(g, lo, hi, device=ctx.local_rank)
-            sc = h_scores.to(dev, non_blocking=True)
-            st = dgi.pagerank(sc)
-            h_scores.copy_(sc)
-            torch.cuda.synchronize()
-            dgi.close()
-            ctx.barrier()
-            dt = time.perf_counter() - t_call
-            os.environ.pop("GDN_PR_BANDS", None)
-            h2d, d2h = 8 * (rows + 1) + 4 * info["nnz_local"] + 4 * rows, 4 * rows
-        if k == 0:
-            continue                                          # warm-up call
-        e_iters += st.iterations
-        e2e_s += dt
-        e2e_calls.append(round(dt * 1e3, 1))
-        e2e_parts.append([round(float(st.h2d_ms), 1), round(float(st.solve_ms), 1), round(float(st.d2h_ms), 1)])
-    if have_ref:
-        ref = np.fromfile(ref_path, dtype=np.float32, count=rows, offset=4 * lo)
-        e2e_l1 = ctx.allsum(float(np.abs(h_scores.numpy().astype(np.float64) - ref.astype(np.float64)).sum()))
-        parity["pr_l1_e2e"] = e2e_l1
-        parity["ok"] = bool(parity.get("ok") and e2e_l1 <= 1e-6)
-    e2e_s = ctx.allmax(e2e_s)
-    e2e = {"value": e_iters / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            if k == 0:
+                continue                                      # warm-up call
+            e_iters += st.iterations
+            e2e_s += dt
+            e2e_calls.append(round(dt * 1e3, 1))
+            e2e_parts.append([round(float(st.h2d_ms), 1), round(float(st.solve_ms), 1), round(float(st.d2h_ms), 1)])
+        if have_ref:
+            ref_full = np.fromfile(ref_path, dtype=np.float32)
+            e2e_l1 = float(np.abs(full.numpy().astype(np.float64) - ref_full.astype(np.float64)).sum())
+            parity["pr_l1_e2e"] = e2e_l1
+            parity["ok"] = bool(parity.get("ok") and e2e_l1 <= 1e-6)
+            del ref_full
+        if world > 1:
+            _lib.check(_lib.lib.gdn_init_gpus(1))
+    ctx.barrier()
+    e2e = {"value": e_iters / e2e_s if rank == 0 else None, "unit": "iterations/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
            "steps": e2e_steps, "ms_per_step": e2e_s * 1e3 / e2e_steps, "ms_per_call": e2e_calls, "h2d_solve_d2h_ms_per_call": e2e_parts,
-           "median_ms_per_call": sorted(e2e_calls)[len(e2e_calls) // 2],
-           "timed": "wall clock around each PRSolver call on pinned host arrays (1 warm-up call)"}
+           "median_ms_per_call": sorted(e2e_calls)[len(e2e_calls) // 2] if e2e_calls else None,
+           "timed": "wall clock around each PRSolver call on pinned host arrays (1 warm-up call)" +
+                    (f"; one process, gdn_init_gpus({world})" if world > 1 else "")} if rank == 0 else None
     for a in (g.out_rowptr(), g.out_colidx(), g.out_degrees()):
         _lib.lib.gdn_host_unpin(a.ctypes.data)
 

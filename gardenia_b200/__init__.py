@@ -6,5 +6,5 @@ The compute path is libgdn_b200.so (hand-written CUDA); this package is the
 thin host-side mirror of the reference's interface.  No CPU fallback exists.
 """
 from ._lib import GdnError, Stats, GDN_INFINITY  # noqa: F401
-from .graph import Graph, DeviceGraph, fill_uniform, partition_rows  # noqa: F401
+from .graph import Graph, DeviceGraph, fill_uniform, partition_rows, init_gpus  # noqa: F401
 from .solvers import BFSSolver, PRSolver, SpmvSolver, MYINFINITY, EPSILON, kDamp, MAX_ITER  # noqa: F401

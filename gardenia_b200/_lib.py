@@ -70,6 +70,8 @@ SIGNATURES = {
     "gdn_version": (C.c_int, []),
     "gdn_last_error": (C.c_char_p, []),
     "gdn_init": (C.c_int, [C.c_int]),
+    "gdn_init_gpus": (C.c_int, [C.c_int]),
+    "gdn_gpus": (C.c_int, []),
     "gdn_finalize": (C.c_int, []),
     "gdn_device_count": (C.c_int, []),
     "gdn_device_trim": (C.c_int, []),

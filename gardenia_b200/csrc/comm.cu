@@ -14,7 +14,12 @@
 #include <dlfcn.h>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
+#include <omp.h>
 
 namespace gdn {
 
@@ -78,8 +83,145 @@ static int load_nccl() {
     }                                                                                    \
   } while (0)
 
-int comm_size() { return nccl().size; }
-int comm_rank() { return nccl().rank; }
+// ------------------------------------------------------------------ the gang: one process, one worker thread per GPU
+// gdn_init_gpus(n) ("the replacement may spawn one host thread per GPU internally").  A worker owns a device
+// context (Lib), takes the rank of its GPU and runs the same partitioned code as a one-process-per-GPU rank; what the
+// ranks of separate processes exchange through NCCL / CUDA IPC (pointers of peer-mapped buffers, the renumbering, barriers)
+// the workers exchange through shared host memory.  The PageRank iteration itself has no collective in either mode.
+struct Gang {
+  int n = 0;
+  std::vector<std::thread> th;
+  std::vector<Lib *> libs;
+  std::mutex mu;
+  std::condition_variable cv_job, cv_done;
+  int (*fn)(int, void *) = nullptr;
+  void *arg = nullptr;
+  unsigned long long seq = 0;          // jobs posted
+  int pending = 0;
+  bool quit = false;
+  std::vector<int> rc;
+  std::string err;                     // message of the first worker that failed
+  // barrier of the workers
+  std::mutex bmu;
+  std::condition_variable bcv;
+  int bcount = 0;
+  unsigned long long bgen = 0;
+  // pointer exchange / shared host scratch
+  void *xchg[8] = {};
+  void *shared = nullptr;
+  size_t shared_bytes = 0;
+};
+static Gang &gang() { static Gang g; return g; }
+static thread_local int tl_gang_rank = -1;
+
+int gang_size() { return gang().n; }
+bool gang_worker() { return tl_gang_rank >= 0; }
+
+void gang_barrier() {
+  Gang &g = gang();
+  std::unique_lock<std::mutex> lk(g.bmu);
+  const unsigned long long gen = g.bgen;
+  if (++g.bcount == g.n) { g.bcount = 0; g.bgen++; g.bcv.notify_all(); }
+  else g.bcv.wait(lk, [&] { return g.bgen != gen; });
+}
+
+void *gang_shared(size_t bytes) {
+  Gang &g = gang();
+  gang_barrier();                                     // everybody is done with the previous contents
+  if (tl_gang_rank == 0 && g.shared_bytes < bytes) {
+    if (g.shared) cudaFreeHost(g.shared);
+    g.shared = nullptr; g.shared_bytes = 0;
+    if (cudaHostAlloc(&g.shared, bytes + bytes / 8, cudaHostAllocPortable) == cudaSuccess) g.shared_bytes = bytes + bytes / 8;
+    else cudaGetLastError();
+  }
+  gang_barrier();
+  return g.shared_bytes >= bytes ? g.shared : nullptr;
+}
+
+static void gang_worker_main(int rank) {
+  Gang &g = gang();
+  tl_gang_rank = rank;
+  lib_bind(g.libs[rank]);
+  omp_set_num_threads(std::max(1, omp_get_num_procs() / g.n));      // the host side of a rank (layout preprocessing) is OpenMP code
+  int rc = gdn_init(rank);
+  if (rc == GDN_OK) {
+    for (int p = 0; p < g.n && rc == GDN_OK; p++) {
+      if (p == rank) continue;
+      const cudaError_t e = cudaDeviceEnablePeerAccess(p, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { set_error("GPU %d cannot map GPU %d (%s)", rank, p, cudaGetErrorString(e)); rc = GDN_ERR_CUDA; }
+      cudaGetLastError();
+    }
+  }
+  unsigned long long seen = 0;
+  {
+    std::lock_guard<std::mutex> lk(g.mu);
+    g.rc[rank] = rc;
+    if (rc != GDN_OK && g.err.empty()) g.err = gdn_last_error();
+    if (--g.pending == 0) g.cv_done.notify_all();
+  }
+  for (;;) {
+    int (*fn)(int, void *);
+    void *arg;
+    {
+      std::unique_lock<std::mutex> lk(g.mu);
+      g.cv_job.wait(lk, [&] { return g.quit || g.seq != seen; });
+      if (g.quit) break;
+      seen = g.seq; fn = g.fn; arg = g.arg;
+    }
+    const int r = fn(rank, arg);
+    std::lock_guard<std::mutex> lk(g.mu);
+    g.rc[rank] = r;
+    if (r != GDN_OK && g.err.empty()) g.err = gdn_last_error();
+    if (--g.pending == 0) g.cv_done.notify_all();
+  }
+  gdn_finalize();
+  lib_bind(nullptr);
+}
+
+int gang_run(int (*fn)(int, void *), void *arg) {
+  Gang &g = gang();
+  if (g.n == 0) { set_error("gdn_init_gpus has not been called"); return GDN_ERR_ARG; }
+  std::unique_lock<std::mutex> lk(g.mu);
+  g.fn = fn; g.arg = arg; g.pending = g.n; g.err.clear();
+  g.seq++;
+  g.cv_job.notify_all();
+  g.cv_done.wait(lk, [&] { return g.pending == 0; });
+  for (int r = 0; r < g.n; r++)
+    if (g.rc[r] != GDN_OK) { set_error("GPU %d: %s", r, g.err.c_str()); return g.rc[r]; }
+  return GDN_OK;
+}
+
+static int gang_start(int n) {
+  Gang &g = gang();
+  if (g.n == n) return GDN_OK;
+  if (g.n) { set_error("gdn_init_gpus: already running on %d GPUs (gdn_finalize first)", g.n); return GDN_ERR_ARG; }
+  g.n = n; g.quit = false; g.seq = 0; g.pending = n; g.rc.assign(n, 0); g.err.clear();
+  g.libs.clear();
+  for (int r = 0; r < n; r++) g.libs.push_back(new Lib());
+  for (int r = 0; r < n; r++) g.th.emplace_back(gang_worker_main, r);
+  std::unique_lock<std::mutex> lk(g.mu);
+  g.cv_done.wait(lk, [&] { return g.pending == 0; });
+  for (int r = 0; r < n; r++)
+    if (g.rc[r] != GDN_OK) { const int rc = g.rc[r]; const std::string msg = g.err; lk.unlock(); set_error("GPU %d: %s", r, msg.c_str()); return rc; }
+  return GDN_OK;
+}
+
+void gang_stop() {
+  Gang &g = gang();
+  if (!g.n) return;
+  { std::lock_guard<std::mutex> lk(g.mu); g.quit = true; }
+  g.cv_job.notify_all();
+  for (auto &t : g.th) t.join();
+  g.th.clear();
+  for (Lib *l : g.libs) delete l;
+  g.libs.clear();
+  if (g.shared) cudaFreeHost(g.shared);
+  g.shared = nullptr; g.shared_bytes = 0;
+  g.n = 0;
+}
+
+int comm_size() { return gang_worker() ? gang().n : nccl().size; }
+int comm_rank() { return gang_worker() ? tl_gang_rank : nccl().rank; }
 
 // Equal-width ranges: width = ceil(m / nparts) rounded up to 1024 vertices, so that
 // every slice is a whole number of 32-word bitmap groups (and of 64-bit host words).
@@ -184,7 +326,7 @@ struct PeerBox {
   unsigned long long epoch = 0;
   int *timeout_flag = nullptr;                 // device: a barrier gave up waiting (a peer died)
 };
-static PeerBox &box() { static PeerBox b; return b; }
+static PeerBox &box() { static thread_local PeerBox b; return b; }      // (a gang worker has its own)
 constexpr size_t kMailBytes = 2u << 20;        // a whole 2 MB block: small cudaMalloc blocks are sub-allocated and not exportable alone
 
 struct PeerMailArgs {
@@ -194,6 +336,15 @@ struct PeerMailArgs {
 // Exchange one device pointer per rank: mine[rank] = local; the others are the peers' allocations mapped into this
 // process.  The 64-byte IPC handles travel through one ncclAllGather.
 static int ipc_exchange(void *local, void **mapped) {
+  if (gang_worker()) {
+    // one process: peer access is enabled (gang_worker_main), the pointers themselves are valid on every GPU
+    Gang &g = gang();
+    g.xchg[tl_gang_rank] = local;
+    gang_barrier();
+    for (int p = 0; p < g.n; p++) mapped[p] = g.xchg[p];
+    gang_barrier();
+    return GDN_OK;
+  }
   Nccl &n = nccl();
   cudaStream_t st = lib().stream;
   cudaIpcMemHandle_t mine;
@@ -214,6 +365,11 @@ static int ipc_exchange(void *local, void **mapped) {
 }
 
 static int comm_barrier_host() {          // every rank has reached this point (and its stream has drained)
+  if (gang_worker()) {
+    GDN_CUDA(cudaStreamSynchronize(lib().stream));
+    gang_barrier();
+    return GDN_OK;
+  }
   Nccl &n = nccl();
   if (n.size == 1 || !n.comm) return GDN_OK;
   int *d = nullptr;
@@ -227,9 +383,9 @@ static int comm_barrier_host() {          // every rank has reached this point (
 
 static int peer_box_setup() {
   PeerBox &b = box();
-  Nccl &n = nccl();
+  const int P = comm_size();
   if (b.ready || b.failed) return GDN_OK;
-  if (n.size > 8) { b.failed = true; return GDN_OK; }
+  if (P > 8) { b.failed = true; return GDN_OK; }
   b.failed = true;                           // until everything below has worked
   GDN_CUDA(cudaMalloc((void **)&b.mail, kMailBytes));
   GDN_CUDA(cudaMemsetAsync(b.mail, 0, kMailBytes, lib().stream));
@@ -238,7 +394,7 @@ static int peer_box_setup() {
   GDN_CUDA(cudaStreamSynchronize(lib().stream));
   void *mapped[8] = {};
   GDN_CHECK(ipc_exchange(b.mail, mapped));
-  for (int p = 0; p < n.size; p++) b.peer_mail[p] = (unsigned long long *)mapped[p];
+  for (int p = 0; p < P; p++) b.peer_mail[p] = (unsigned long long *)mapped[p];
   GDN_CHECK(comm_barrier_host());            // nobody signals into a mailbox that is not zeroed yet
   b.epoch = 0;
   b.failed = false;
@@ -248,10 +404,10 @@ static int peer_box_setup() {
 
 static void peer_box_teardown() {
   PeerBox &b = box();
-  Nccl &n = nccl();
+  const int P = comm_size(), R = comm_rank();
   if (b.mail) {
-    for (int p = 0; p < n.size; p++)
-      if (p != n.rank && b.peer_mail[p]) cudaIpcCloseMemHandle(b.peer_mail[p]);
+    for (int p = 0; p < P && !gang_worker(); p++)
+      if (p != R && b.peer_mail[p]) cudaIpcCloseMemHandle(b.peer_mail[p]);
     comm_barrier_host();                     // the peers have unmapped this mailbox before it is freed
     cudaFree(b.mail);
     cudaFree(b.timeout_flag);
@@ -261,15 +417,15 @@ static void peer_box_teardown() {
 
 // Map the two contrib vectors of every other GPU (once per graph; collective: all ranks solve the same graph together).
 int pull_peer_setup(gdn_graph *g) {
-  Nccl &n = nccl();
-  if (n.size == 1 || g->peer_ready || g->peer_failed) return GDN_OK;
+  const int P = comm_size();
+  if (P == 1 || g->peer_ready || g->peer_failed) return GDN_OK;
   GDN_CHECK(peer_box_setup());
   if (!box().ready) { g->peer_failed = true; return GDN_OK; }
   for (int k = 0; k < 2; k++) {
     void *mapped[8] = {};
     const int rc = ipc_exchange(g->contrib[k], mapped);
     if (rc != GDN_OK) { g->peer_failed = true; return rc; }
-    for (int p = 0; p < n.size; p++) g->peer_contrib[k][p] = (float *)mapped[p];
+    for (int p = 0; p < P; p++) g->peer_contrib[k][p] = (float *)mapped[p];
   }
   g->peer_ready = true;
   return GDN_OK;
@@ -278,20 +434,20 @@ bool pull_peer_ready(const gdn_graph *g) { return g->peer_ready; }
 
 // Unmap the peers' vectors; the owner frees its own only after every rank has done so.
 int pull_peer_release(gdn_graph *g) {
-  Nccl &n = nccl();
+  const int P = comm_size(), R = comm_rank();
   if (!g->peer_ready) return GDN_OK;
   for (int k = 0; k < 2; k++)
-    for (int p = 0; p < n.size; p++)
-      if (p != n.rank && g->peer_contrib[k][p]) { cudaIpcCloseMemHandle(g->peer_contrib[k][p]); g->peer_contrib[k][p] = nullptr; }
+    for (int p = 0; p < P; p++)
+      if (p != R && g->peer_contrib[k][p]) { if (!gang_worker()) cudaIpcCloseMemHandle(g->peer_contrib[k][p]); g->peer_contrib[k][p] = nullptr; }
   g->peer_ready = false;
   return comm_barrier_host();
 }
 
 void pull_peer_args(const gdn_graph *g, int buf_out, SellArgs &a) {
-  Nccl &n = nccl();
+  const int P = comm_size(), R = comm_rank();
   a.n_peers = 0;
-  for (int p = 0; p < n.size; p++) {
-    if (p == n.rank) continue;
+  for (int p = 0; p < P; p++) {
+    if (p == R) continue;
     a.peer_out[a.n_peers] = g->peer_contrib[buf_out][p];
     a.peer_other[a.n_peers] = g->peer_contrib[buf_out ^ 1][p];
     a.n_peers++;
@@ -356,12 +512,12 @@ peer_sync_kernel(const double *__restrict__ partial, int n_partial, PeerMailArgs
 int pull_peer_sync(gdn_graph *g, const double *partial, int n_partial, double *err_out, int iter, double eps, int32_t *done,
                    cudaStream_t s) {
   PeerBox &b = box();
-  Nccl &n = nccl();
+  const int P = comm_size(), R = comm_rank();
   (void)g;
   PeerMailArgs pm = {};
-  for (int p = 0; p < n.size; p++) pm.mail[p] = b.peer_mail[p];
+  for (int p = 0; p < P; p++) pm.mail[p] = b.peer_mail[p];
   b.epoch++;
-  peer_sync_kernel<<<1, 256, 0, s>>>(partial, n_partial, pm, n.rank, n.size, b.epoch, err_out, iter, eps, done, b.timeout_flag);
+  peer_sync_kernel<<<1, 256, 0, s>>>(partial, n_partial, pm, R, P, b.epoch, err_out, iter, eps, done, b.timeout_flag);
   return GDN_OK;
 }
 
@@ -417,6 +573,16 @@ int gdn_comm_destroy(void) {
   n.size = 1;
   return GDN_OK;
 }
+
+int gdn_init_gpus(int ngpus) {
+  const int have = gdn_device_count();
+  if (have == 0) { set_error("no CUDA device: libgdn_b200 has no CPU fallback"); return GDN_ERR_NO_DEVICE; }
+  if (ngpus < 1 || ngpus > have || ngpus > 8) { set_error("gdn_init_gpus: %d GPUs asked for, %d present (at most 8)", ngpus, have); return GDN_ERR_ARG; }
+  if (ngpus == 1) { gang_stop(); return gdn_init(0); }
+  GDN_CHECK(gdn_init(0));            // the calling thread keeps a context of its own (resident API, device buffers)
+  return gang_start(ngpus);
+}
+int gdn_gpus(void) { return gang_size() ? gang_size() : 1; }
 
 int gdn_comm_rank(void) { return nccl().rank; }
 int gdn_comm_size(void) { return nccl().size; }

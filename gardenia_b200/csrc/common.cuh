@@ -61,7 +61,15 @@ inline void kev_collect(gdn_stats *st, int n_valid = 1 << 30) {
   st->kernel_ms = tot;
   st->kernel_calls = l.n_kev;
 }
-Lib &lib();
+Lib &lib();                        // the calling thread's device context (a gang worker's own, else the process-wide one)
+void lib_bind(Lib *l);             // graph.cu: make `l` the calling thread's context (nullptr: back to the process-wide one)
+// Single-process multi-GPU mode (comm.cu): gdn_init_gpus(n) starts one worker thread per GPU; the one-shot entry points
+// hand each of them a row partition.  Inside a worker comm_size() / comm_rank() are the gang's.
+int gang_size();                   // 0 when the mode is off
+bool gang_worker();                // is the calling thread a gang worker?
+int gang_run(int (*fn)(int rank, void *arg), void *arg);       // run fn on every worker, wait; first non-zero status (message kept)
+void gang_barrier();               // workers only
+void *gang_shared(size_t bytes);   // workers only, collective: one page-locked host buffer of at least `bytes`, the same for all
 void *host_arena(int slot, size_t bytes);      // graph.cu; nullptr when page-locking fails (callers fall back to malloc)
 int ensure_init();
 // GDN_TRACE=1: wall-clock stage timings of the upload / preprocessing path on stderr

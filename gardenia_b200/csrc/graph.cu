@@ -22,7 +22,10 @@ void set_error(const char *fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
-Lib &lib() { static Lib l; return l; }
+static thread_local Lib *tl_lib = nullptr;
+static Lib &process_lib() { static Lib l; return l; }
+Lib &lib() { return tl_lib ? *tl_lib : process_lib(); }
+void lib_bind(Lib *l) { tl_lib = l; }
 
 void trace(const char *label) {
   static const bool on = getenv("GDN_TRACE") != nullptr;
@@ -73,6 +76,7 @@ int bfs_run(gdn_graph *g, int32_t source, int32_t *d_depth, int32_t *d_parent, g
 int pr_run(gdn_graph *g, float *d_scores, float damp, double eps, int max_iter, gdn_stats *st);
 int spmv_run(gdn_graph *g, const float *d_Ax, const float *d_x, float *d_y, gdn_stats *st);
 int pull_peer_release(gdn_graph *g);       // comm.cu
+void gang_stop();                          // comm.cu
 
 // in[i] - base -> out[i]
 template <typename InT, typename OutT>
@@ -303,6 +307,12 @@ static int graph_create_t(int64_t m, int64_t nnz, const HostOffT *out_rowptr, co
   return GDN_OK;
 }
 
+// gen-1 callers (int offsets) behind a row partition: the gang's workers (oneshot.cu)
+int graph_create_i32_part(int32_t m, int32_t nnz, const int32_t *out_rp, const int32_t *out_ci, const int32_t *in_rp, const int32_t *in_ci,
+                          int64_t row_lo, int64_t row_hi, gdn_graph **g) {
+  return graph_create_t<int32_t>(m, nnz, out_rp, out_ci, in_rp, in_ci, row_lo, row_hi, g);
+}
+
 }  // namespace gdn
 
 using namespace gdn;
@@ -352,6 +362,7 @@ int gdn_init(int device) {
 }
 
 int gdn_finalize(void) {
+  if (!gang_worker()) gang_stop();      // the workers of gdn_init_gpus finalize their own contexts
   Lib &l = lib();
   if (!l.inited) return GDN_OK;
   cudaStreamSynchronize(l.stream);
@@ -492,7 +503,7 @@ int gdn_memcpy_d2h(void *h, const void *d, size_t bytes) {
 }
 int gdn_host_pin(void *h_ptr, size_t bytes) {
   GDN_CHECK(ensure_init());
-  GDN_CUDA(cudaHostRegister(h_ptr, bytes, cudaHostRegisterDefault));
+  GDN_CUDA(cudaHostRegister(h_ptr, bytes, cudaHostRegisterPortable));      // (portable: every GPU of a gang copies from it)
   return GDN_OK;
 }
 int gdn_host_unpin(void *h_ptr) {

@@ -5,10 +5,16 @@
 // src/spmv/base.cu:28-76).  These are what BFSSolver / PRSolver / SpmvSolver
 // shims bind.
 #include "common.cuh"
+#include <algorithm>
 #include <chrono>
 #include <cstring>
 
 using namespace gdn;
+namespace gdn {
+int64_t partition_width(int64_t m, int nparts);
+int graph_create_i32_part(int32_t m, int32_t nnz, const int32_t *out_rp, const int32_t *out_ci, const int32_t *in_rp, const int32_t *in_ci,
+                          int64_t row_lo, int64_t row_hi, gdn_graph **g);
+}
 
 namespace {
 double now_ms() {
@@ -74,11 +80,76 @@ int bfs_oneshot(int64_t m, int64_t nnz, const OffT *orp, const int32_t *oci, con
   return GDN_OK;
 }
 
+// ---- PageRank on the gang (gdn_init_gpus): every worker uploads ITS rows of the caller's CSR over its own PCIe link,
+// solves its partition with the others (peer-mapped exchange, comm.cu) and writes its slice of the scores back.
+template <typename OffT>
+struct PrJob {
+  int64_t m, nnz;
+  const OffT *irp;
+  const int32_t *ici, *out_degree;
+  float *scores;
+  float damp;
+  double eps;
+  int max_iter;
+  gdn_stats st[8];
+};
+template <typename OffT>
+int create_part(int64_t m, int64_t nnz, const OffT *irp, const int32_t *ici, int64_t lo, int64_t hi, gdn_graph **g);
+template <>
+int create_part<uint64_t>(int64_t m, int64_t nnz, const uint64_t *irp, const int32_t *ici, int64_t lo, int64_t hi, gdn_graph **g) {
+  return gdn_graph_create(m, nnz, nullptr, nullptr, irp, ici, lo, hi, g);
+}
+template <>
+int create_part<int32_t>(int64_t m, int64_t nnz, const int32_t *irp, const int32_t *ici, int64_t lo, int64_t hi, gdn_graph **g) {
+  return graph_create_i32_part((int32_t)m, (int32_t)nnz, nullptr, nullptr, irp, ici, lo, hi, g);
+}
+template <typename OffT>
+int pr_oneshot_rank(int rank, void *arg) {
+  PrJob<OffT> &J = *(PrJob<OffT> *)arg;
+  PoolScope arena;
+  const int64_t W = partition_width(J.m, gang_size());
+  const int64_t lo = std::min<int64_t>((int64_t)rank * W, J.m), hi = std::min<int64_t>(lo + W, J.m), rows = hi - lo;
+  DevBuf sc, od;
+  GDN_CHECK(sc.alloc(sizeof(float) * std::max<int64_t>(rows, 1)));
+  GDN_CHECK(od.alloc(sizeof(int32_t) * (std::max<int64_t>(rows, 1) + 1)));
+  GDN_CHECK(h2d(sc.p, J.scores + lo, sizeof(float) * rows));
+  GDN_CHECK(h2d(od.p, J.out_degree + lo, sizeof(int32_t) * rows));
+  GraphGuard gg;
+  GDN_CHECK(create_part<OffT>(J.m, J.nnz, J.irp, J.ici, lo, hi, &gg.g));
+  gg.g->one_shot = true;
+  gg.g->out_degree = (int32_t *)od.p;      // the graph owns it from here
+  od.p = nullptr;
+  GDN_CHECK(gdn_pagerank_resident(gg.g, (float *)sc.p, J.damp, J.eps, J.max_iter, &J.st[rank]));
+  GDN_CHECK(d2h(J.scores + lo, sc.p, sizeof(float) * rows));
+  return GDN_OK;
+}
+
 template <typename OffT>
 int pr_oneshot(int64_t m, int64_t nnz, const OffT *irp, const int32_t *ici, const int32_t *out_degree,
                float *scores, float damp, double eps, int max_iter, gdn_stats *st) {
   if (!irp || !ici || !out_degree || !scores) { set_error("gdn_pagerank_pull: null argument"); return GDN_ERR_ARG; }
   GDN_CHECK(ensure_init());
+  if (gang_size() > 1 && !gang_worker() && m >= (int64_t)gang_size() * 65536) {
+    // (small graphs stay on one GPU: a partition must be worth a GPU, and every rank needs rows of its own)
+    PrJob<OffT> *J = new PrJob<OffT>();
+    J->m = m; J->nnz = nnz; J->irp = irp; J->ici = ici; J->out_degree = out_degree; J->scores = scores;
+    J->damp = damp; J->eps = eps; J->max_iter = max_iter;
+    const double t0 = now_ms();
+    const int rc = gang_run(pr_oneshot_rank<OffT>, J);
+    const double t1 = now_ms();
+    if (rc == GDN_OK && st) {
+      *st = J->st[0];
+      for (int r = 1; r < gang_size(); r++) {
+        st->solve_ms = std::max(st->solve_ms, J->st[r].solve_ms);
+        st->kernel_launches += J->st[r].kernel_launches;
+      }
+      st->h2d_ms = (t1 - t0) - st->solve_ms; st->d2h_ms = 0;      // upload + layout + download of all GPUs, overlapped
+      st->h2d_bytes = (int64_t)(sizeof(OffT) * (m + 1) + sizeof(int32_t) * nnz + 8 * m);
+      st->d2h_bytes = (int64_t)sizeof(float) * m;
+    }
+    delete J;
+    return rc;
+  }
   PoolScope arena;                 // declared before every buffer of the call: they are parked, not freed, on the way out
   const double t0 = now_ms();
   // the two small inputs go first (queued, not waited for); then the CSR, whose column array crosses PCIe in

@@ -151,14 +151,20 @@ int pull_prepare(gdn_graph *g, const HostOffT *row_off, const HostOffT *key_off)
   L.group_ch = L.exact ? 0xffffffffu : (uint32_t)kGroupCh;
 
   trace("pull_prepare: begin");
+  // A gang worker (one process, one thread per GPU) ranks only ITS vertices -- O(m / P) host work per GPU -- and the
+  // renumbering of the whole graph is assembled in host memory shared by the workers.  Separate processes (and directed
+  // graphs, whose column order is not the row order) rank every partition themselves.
+  const bool part_only = gang_worker() && L.symmetric_order && P > 1;
+  const int64_t d_lo = part_only ? lo : 0, d_hi = part_only ? hi : m;
   // degree array and row order live in the library's page-locked scratch (reused from call to call)
   RawBuf<int32_t> rdeg_own, kdeg;
-  int32_t *rdeg = (int32_t *)host_arena(0, sizeof(int32_t) * (size_t)m);
-  if (!rdeg) { rdeg_own.alloc(m); rdeg = rdeg_own.data(); }
-  if (!rdeg) { set_error("out of host memory"); return GDN_ERR_NOMEM; }
+  int32_t *rdeg_buf = (int32_t *)host_arena(0, sizeof(int32_t) * (size_t)std::max<int64_t>(d_hi - d_lo, 1));
+  if (!rdeg_buf) { rdeg_own.alloc(std::max<int64_t>(d_hi - d_lo, 1)); rdeg_buf = rdeg_own.data(); }
+  if (!rdeg_buf) { set_error("out of host memory"); return GDN_ERR_NOMEM; }
+  int32_t *rdeg = rdeg_buf - d_lo;                         // indexed by global vertex id in [d_lo, d_hi)
   int64_t bad = 0;          // the device-side validation of these offsets is still in flight: do not index with garbage
 #pragma omp parallel for reduction(+ : bad)
-  for (int64_t v = 0; v < m; v++) {
+  for (int64_t v = d_lo; v < d_hi; v++) {
     rdeg[v] = (int32_t)(row_off[v + 1] - row_off[v]);
     bad += row_off[v + 1] < row_off[v] || (uint64_t)(row_off[v + 1] - row_off[v]) > 0x7fffffffull;
   }
@@ -172,16 +178,34 @@ int pull_prepare(gdn_graph *g, const HostOffT *row_off, const HostOffT *key_off)
     }
     kd = kdeg.data();
   }
-  if (bad) { L.prepared = false; return GDN_OK; }      // upload_csr_end reports the malformed CSR
+  if (part_only) {
+    // (a malformed partition must not leave the other workers waiting at the barriers below: everybody goes on, the
+    // device-side validation reports the error)
+    if (bad) {
+#pragma omp parallel for
+      for (int64_t v = d_lo; v < d_hi; v++) rdeg[v] = 0;
+    }
+  } else if (bad) { L.prepared = false; return GDN_OK; }      // upload_csr_end reports the malformed CSR
   // on one GPU of a symmetric graph the row order IS the column order: one sort, and newid / sdeg are
   // derived from it on the device (no 268 MB host scatter, no upload)
   const bool one_sort = L.symmetric_order && P == 1;
   RawBuf<int32_t> perm_own, newid, tmp, sdeg, rowid;
+  int32_t *newid_host = nullptr;
   int32_t *perm = (int32_t *)host_arena(1, sizeof(int32_t) * (size_t)std::max<int64_t>(rows, 1));
   if (!perm) { perm_own.alloc(std::max<int64_t>(rows, 1)); perm = perm_own.data(); }
   if (!perm) { set_error("out of host memory"); return GDN_ERR_NOMEM; }
   if (one_sort) {
     sort_by_degree(kd, 0, m, perm);
+  } else if (part_only) {
+    int32_t *shared = (int32_t *)gang_shared(sizeof(int32_t) * (size_t)m);      // collective
+    if (!shared) { set_error("out of page-locked host memory"); return GDN_ERR_NOMEM; }
+    sdeg.alloc(std::max<int64_t>(rows, 1));
+    if (rows > 0) sort_by_degree(rdeg, lo, hi, perm, sdeg.data());
+#pragma omp parallel for
+    for (int64_t j = 0; j < rows; j++)
+      shared[lo + perm[j]] = (int32_t)(j < L.Hp ? (int64_t)R * L.Hp + j : L.H + (int64_t)R * L.Wc + (j - L.Hp));
+    gang_barrier();                                        // every worker's slice of the renumbering is in
+    newid_host = shared;
   } else {
     newid.alloc(m); tmp.alloc(W); sdeg.alloc(std::max<int64_t>(rows, 1));
     for (int q = 0; q < P; q++) {
@@ -199,6 +223,7 @@ int pull_prepare(gdn_graph *g, const HostOffT *row_off, const HostOffT *key_off)
 #pragma omp parallel for
       for (int64_t j = 0; j < rows; j++) rowid[j] = newid[lo + perm[j]];
     }
+    newid_host = newid.data();
   }
   trace("pull_prepare: orders");
   auto len_of = [&](int64_t j) -> int32_t { return rdeg[lo + perm[j]]; };     // length of sorted row j
@@ -286,7 +311,7 @@ int pull_prepare(gdn_graph *g, const HostOffT *row_off, const HostOffT *key_off)
     if (c.off64) sdeg_from_perm<uint64_t><<<grid, 256, 0, st>>>((const uint64_t *)c.rowptr, L.perm, L.sdeg, rows);
     else sdeg_from_perm<uint32_t><<<grid, 256, 0, st>>>((const uint32_t *)c.rowptr, L.perm, L.sdeg, rows);
   } else {
-    GDN_CHECK(upload(g, &L.newid, newid.data(), (size_t)m));
+    GDN_CHECK(upload(g, &L.newid, newid_host, (size_t)m));
     GDN_CHECK(upload(g, &L.sdeg, sdeg.data(), (size_t)rows));
     if (!L.symmetric_order) GDN_CHECK(upload(g, &L.rowid, rowid.data(), (size_t)rows));
   }
@@ -1215,8 +1240,8 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
   if (!lib().pr_ev[0])
     for (int i = 0; i < kRing; i++) GDN_CUDA(cudaEventCreateWithFlags(&lib().pr_ev[i], cudaEventDisableTiming));
   // GDN_PR_KTIME=1: CUDA-event time of every launch of the third iteration, in place (not under a profiler), on stderr
-  static cudaEvent_t kt_ev[16];
-  static bool kt_init = false;
+  static thread_local cudaEvent_t kt_ev[16];
+  static thread_local bool kt_init = false;
   const bool ktime = getenv("GDN_PR_KTIME") != nullptr;
   if (ktime && !kt_init) { for (auto &e : kt_ev) cudaEventCreate(&e); kt_init = true; }
   int kt_n = 0;

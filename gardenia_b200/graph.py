@@ -99,6 +99,12 @@ class Graph:
         return out
 
 
+def init_gpus(n):
+    """Split every one-shot solve (PRSolver) over the first n GPUs of the box: gdn_init_gpus, one worker thread per GPU
+    inside the library; n = 1 goes back to one GPU."""
+    check(lib.gdn_init_gpus(int(n)))
+
+
 def fill_uniform(seed, n):
     """fp32 U[0,1) from std::mt19937(seed): (draw >> 8) * 2**-24 (same stream as oracle/ref_driver.cc)."""
     out = np.empty(n, dtype=np.float32)

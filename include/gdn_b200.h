@@ -89,6 +89,12 @@ const char *gdn_last_error(void);
 /* Select the CUDA device (default 0) and create the library stream.  Fails with
  * GDN_ERR_NO_DEVICE when no sm_100 device is present. */
 int gdn_init(int device);
+/* Use the first `ngpus` GPUs of the box for the one-shot solvers (gdn_init(ngpus)): one worker thread per GPU
+ * inside the library, 1-D row partition, the PageRank vector exchanged by peer-mapped stores over NVLink.  After this call
+ * gdn_pagerank_pull / _i32 split every solve over the GPUs; everything else keeps running on device 0.  ngpus = 1 goes back
+ * to one GPU.  (The resident API partitions across PROCESSES instead: gdn_comm_init, one rank per GPU.) */
+int gdn_init_gpus(int ngpus);
+int gdn_gpus(void);           /* GPUs the one-shot solvers use (1 unless gdn_init_gpus) */
 int gdn_finalize(void);
 int gdn_device_count(void);   /* 0 when no driver / device */
 /* One-shot calls park their device blocks (>= 1 MB) in a bounded arena instead of freeing them, so that the next
