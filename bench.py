@@ -279,6 +279,8 @@ class Ctx:
             dist.broadcast(uid, 0)
             self._uid = np.ascontiguousarray(uid.cpu().numpy())       # keep alive across the C call
             _lib.check(_lib.lib.gdn_comm_init(self.rank, self.world, self._uid.ctypes.data))
+            # a barrier that leaves the GPUs alone (an NCCL barrier is a kernel spinning on every waiting rank's GPU)
+            self.cpu_group = dist.new_group(backend="gloo")
         self.ncpu = os.cpu_count() or 1
         self.peak, self.peak_src = hbm_peak()
 
@@ -286,6 +288,11 @@ class Ctx:
         if self.world > 1:
             self.dist.barrier()
         self.torch.cuda.synchronize()
+
+    def cpu_barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier(group=self.cpu_group)
 
     def allmax(self, x):
         if self.world == 1:
@@ -422,12 +429,13 @@ def bench_pr(ctx, args):
     for a in (g.out_rowptr(), g.out_colidx(), g.out_degrees()):
         _lib.lib.gdn_host_pin(a.ctypes.data, a.nbytes)       # page-lock the caller's CSR + degree array once (untimed)
     dg.close()
-    ctx.barrier()
+    ctx.cpu_barrier()
     e_iters = 0
     h2d = d2h = 0
     e2e_s = 0.0
     e2e_calls, e2e_parts = [], []
     e2e_l1 = None
+    e2e_last_trace = []
     # N > 1: the SAME call, from ONE process: gdn_init_gpus(N) makes the library split every one-shot solve over the N GPUs
     # (a worker thread per GPU, each uploading its rows over its own PCIe link).  Rank 0 makes the calls, the other ranks of
     # the launch have released their GPUs' memory and wait.
@@ -446,6 +454,7 @@ def bench_pr(ctx, args):
                 continue                                      # warm-up call
             e_iters += st.iterations
             e2e_s += dt
+            e2e_last_trace = [float(f"{x:.6g}") for x in st.pr_trace()[:12]]
             e2e_calls.append(round(dt * 1e3, 1))
             e2e_parts.append([round(float(st.h2d_ms), 1), round(float(st.solve_ms), 1), round(float(st.d2h_ms), 1)])
         if have_ref:
@@ -456,10 +465,11 @@ def bench_pr(ctx, args):
             del ref_full
         if world > 1:
             _lib.check(_lib.lib.gdn_init_gpus(1))
-    ctx.barrier()
+    ctx.cpu_barrier()            # (the other ranks wait on the CPU: their GPUs belong to rank 0's gang meanwhile)
     e2e = {"value": e_iters / e2e_s if rank == 0 else None, "unit": "iterations/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
            "steps": e2e_steps, "ms_per_step": e2e_s * 1e3 / e2e_steps, "ms_per_call": e2e_calls, "h2d_solve_d2h_ms_per_call": e2e_parts,
            "median_ms_per_call": sorted(e2e_calls)[len(e2e_calls) // 2] if e2e_calls else None,
+           "iterations_per_call": e_iters / max(len(e2e_calls), 1), "l1_delta_trace_last_call": e2e_last_trace,
            "timed": "wall clock around each PRSolver call on pinned host arrays (1 warm-up call)" +
                     (f"; one process, gdn_init_gpus({world})" if world > 1 else "")} if rank == 0 else None
     for a in (g.out_rowptr(), g.out_colidx(), g.out_degrees()):

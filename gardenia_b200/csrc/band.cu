@@ -341,6 +341,7 @@ pr_band_finalize_fix(SellArgs a, long long *__restrict__ acc_fix, double inv_sca
   }
   err = warp_sum(err);
   if (lane == 0) a.err_partial[a.err_slot0 + warp] = err;
+  contrib_flush(a);
 }
 
 // ------------------------------------------------------------------ host: tables

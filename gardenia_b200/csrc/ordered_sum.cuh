@@ -285,6 +285,7 @@ pr_exact_combine(SellArgs a, ExactArgs x) {
   }
   err = warp_sum(err);
   if (lane == 0) a.err_partial[a.err_slot0 + warp] = err;
+  contrib_flush(a);
 }
 
 }  // namespace gdn

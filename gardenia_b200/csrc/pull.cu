@@ -882,6 +882,7 @@ __device__ __forceinline__ void pr_sell_pipe_body(const SellArgs &a) {
   }
   err = warp_sum(err);
   if (lane == 0) a.err_partial[a.err_slot0 + warp] = err;
+  contrib_flush(a);
 }
 
 template <int G, int D, int THREADS>
@@ -928,6 +929,7 @@ pr_sell_finalize(SellArgs a) {
     err = warp_sum(err);
     if (lane == 0) a.err_partial[a.err_slot0 + blockIdx.x] = err;
   }
+  contrib_flush(a);
 }
 
 // rows without in-edges: score = base (src/pr/omp_base.cc:28-32 with an empty sum).  They reach that
@@ -956,6 +958,7 @@ pr_sell_isolated(SellArgs a, float *contrib_other) {
   }
   err = warp_sum(err);
   if (lane == 0) a.err_partial[a.err_slot0 + warp] = err;
+  contrib_flush(a);
 }
 
 // Scores into sorted order + the first contrib (src/pr/omp_base.cc:24-25).  Rows without in-edges are settled here,
@@ -995,6 +998,7 @@ pr_sell_load(const float *__restrict__ scores_user, const int32_t *__restrict__ 
   }
   tsum = warp_sum(tsum);
   if (lane == 0) abs_partial[warp] = tsum;
+  contrib_flush(a);
 }
 __global__ void pr_sell_store(float *__restrict__ scores_user, const int32_t *__restrict__ perm,
                               const float *__restrict__ scores_sorted, int64_t rows) {
@@ -1159,8 +1163,9 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
   }
   // row partition: map the other GPUs' vectors once per graph (GDN_PR_NCCL=1 keeps the NCCL collectives instead; they are
   // also what runs when the mapping is not possible)
-  if (multi && !getenv("GDN_PR_NCCL") && pull_peer_setup(g) != GDN_OK) cudaGetLastError();
+  if (multi && (gang_worker() || !getenv("GDN_PR_NCCL")) && pull_peer_setup(g) != GDN_OK) cudaGetLastError();
   const bool peer = multi && pull_peer_ready(g);
+  if (multi && !peer && gang_worker()) { set_error("the GPUs of the gang cannot map each other's memory"); return GDN_ERR_CUDA; }
   if (g->n_err_partial < n_partial) {
     if (g->err_partial) GDN_CUDA(cudaFree(g->err_partial));
     GDN_CUDA(cudaMalloc((void **)&g->err_partial, sizeof(double) * n_partial));

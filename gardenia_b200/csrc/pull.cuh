@@ -88,6 +88,13 @@ __device__ __forceinline__ void contrib_store_other(const SellArgs &a, float *co
     if (p < a.n_peers) a.peer_other[p][id] = cv;
 }
 
+// Last statement of every kernel that may have stored into the peers' vectors: each thread makes ITS remote stores
+// performed system-wide before the kernel can end, so that the flag the barrier kernel raises afterwards (comm.cu
+// peer_sync_kernel) can never overtake them on the way to another GPU.
+__device__ __forceinline__ void contrib_flush(const SellArgs &a) {
+  if (a.n_peers > 0) __threadfence_system();
+}
+
 // scores[dst] = base + damp * sum; error += |new - old|; next contrib   (src/pr/omp_base.cc:24-25,31-33)
 __device__ __forceinline__ void pr_epilogue_pre(const SellArgs &a, int64_t j, float acc, double &err, float old_score, int32_t deg) {
   // scores / sdeg are touched once per iteration: streaming (evict-first) accesses keep them from

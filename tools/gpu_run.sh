@@ -13,8 +13,8 @@ for st in "$@"; do
     multi) timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node=$arg --master-addr 127.0.0.1 --master-port 29517 tests/_multi_worker.py > $O/${TAG}_multi$arg.log 2>&1; echo "rc=$?"; grep -E "\[multi\]|Error|error" $O/${TAG}_multi$arg.log | tail -40 ;;
     smoke) timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $O/${TAG}_smoke.log 2>&1; echo "rc=$?"; tail -3 $O/${TAG}_smoke.log ;;
     bench) timeout 1500 python bench.py $arg > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; echo "rc=$?"; tail -4 $O/${TAG}_bench.err; head -c 1500 $O/${TAG}_bench.json; echo ;;
-    benchN) n=${arg%%:*}; rest=""; [[ "$arg" == *:* ]] && rest=${arg#*:}
-      timeout 1800 python -m torch.distributed.run --nnodes=1 --nproc-per-node=$n --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus $n $rest > $O/${TAG}_bench_n$n.json 2> $O/${TAG}_bench_n$n.err; echo "rc=$?"; grep -v "^W\|^\*\*\*" $O/${TAG}_bench_n$n.err | tail -6; head -c 1500 $O/${TAG}_bench_n$n.json; echo ;;
+    benchN) n=${arg%%:*}; rest=""; [[ "$arg" == *:* ]] && rest=${arg#*:}; sfx=$(echo "$rest" | tr -c "a-zA-Z0-9" "_" | cut -c1-24)
+      timeout 1800 python -m torch.distributed.run --nnodes=1 --nproc-per-node=$n --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus $n $rest > $O/${TAG}_bench_n${n}_$sfx.json 2> $O/${TAG}_bench_n${n}_$sfx.err; echo "rc=$?"; grep -v "^W\|^\*\*\*" $O/${TAG}_bench_n${n}_$sfx.err | tail -6; head -c 1500 $O/${TAG}_bench_n${n}_$sfx.json; echo ;;
     ncu_list) timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/${TAG}_launches.csv python tools/prof_run.py $arg > $O/${TAG}_ncu_list.log 2>&1; echo "rc=$?"; python tools/launch_list.py $O/${TAG}_launches.csv | tee $O/${TAG}_launches.txt | head -30 ;;
     ncu_full) k=${arg%%:*}; rest=${arg#*:}
       timeout 1500 ncu --set full --clock-control none --import-source on -k "regex:$k" -c 3 -o $O/${TAG}_full -f python tools/prof_run.py $rest > $O/${TAG}_ncu_full.log 2>&1; echo "rc=$?"; tail -3 $O/${TAG}_ncu_full.log ;;
