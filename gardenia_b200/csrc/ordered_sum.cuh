@@ -103,7 +103,7 @@ struct ExactArgs {
   float4 *vals;                    // [n_blocks_total * 128] row-major values, block after block
   double *S;                       // [n_blocks_total] real-valued sum of the block
   uint32_t *mx;                    // [n_blocks_total] largest addend (bits); >= 0x7f800000: a negative / non-finite addend
-  uint8_t *plan;                   // [n_blocks_total] guessed biased exponent of the accumulator at the block, 0 = no fast path
+  uint8_t *plan;                   // [n_blocks_total] guessed biased exponent of the accumulator at the block; 0 = no fast path, 1 = all-zero block
   uint32_t *Q;                     // [n_blocks_total] sum of rne(x / ulp) under the guess
 };
 
@@ -195,12 +195,13 @@ pr_exact_plan(SellArgs a, ExactArgs x) {
     const double P = base + incl - s;                                      // real prefix at the start of block b
     if (b < nb) {
       uint8_t plan = 0;
+      if (x.mx[k0 + b] == 0u) plan = 1;                                   // nothing but +0.0f (padding past the end of the row): adds nothing
       const float pf = (float)P, qf = (float)(P + s);
       const uint32_t pb = __float_as_uint(pf), qb = __float_as_uint(qf);
       const uint32_t ex = pb >> 23;
       if (b > 0 && x.mx[k0 + b] < 0x7f800000u && ord_acc_ok(pb) && (qb >> 23) == ex &&
           (pb & 0x7fffffu) > 0x4000u && (qb & 0x7fffffu) < 0x7fc000u &&       // 2^-9 away from both ends of the binade
-          __fmul_rn(__uint_as_float(x.mx[k0 + b]), ord_scale(ex)) < 16384.f)
+          __fmul_rn(__uint_as_float(x.mx[k0 + b]), ord_scale(ex)) < 16384.f && plan == 0)
         plan = (uint8_t)ex;
       x.plan[k0 + b] = plan;
     }
@@ -216,8 +217,7 @@ pr_exact_qsum(SellArgs a, ExactArgs x) {
   const uint32_t warp = (blockIdx.x * 256 + threadIdx.x) >> 5, nwarps = (gridDim.x * 256) >> 5;
   for (uint32_t k = warp; k < (uint32_t)x.n_blocks_total; k += nwarps) {
     const uint32_t ex = x.plan[k];
-    if (ex == 0) continue;                                                 // warp-uniform
-    if (x.mx[k] == 0u) { if (lane == 0) x.Q[k] = 0u; continue; }           // nothing but zeros (padding past the end of the row)
+    if (ex <= 1) continue;                                                 // warp-uniform: careful block / all-zero block
     const float scale = ord_scale(ex);
     const float4 *src = x.vals + (size_t)k * kOrdBlockGroups + lane * 4;
     uint32_t run = 0;
@@ -250,7 +250,8 @@ pr_exact_combine(SellArgs a, ExactArgs x) {
     // the plans and integer sums of 32 blocks at a time, one per lane, requested one run ahead
     uint32_t plan_n = lane < nb ? x.plan[k0 + lane] : 0u, q_n = lane < nb ? x.Q[k0 + lane] : 0u;
     for (uint32_t b0 = 0; b0 < nb; b0 += 32) {
-      const uint32_t plan_l = plan_n, q_l = plan_n ? q_n : 0u;
+      const uint32_t plan_l = plan_n, q_l = plan_n > 1u ? q_n : 0u;
+      const bool bl_past = b0 + lane >= nb;
       const uint32_t bn = b0 + 32 + lane;
       plan_n = bn < nb ? x.plan[k0 + bn] : 0u;
       q_n = bn < nb ? x.Q[k0 + bn] : 0u;
@@ -260,13 +261,15 @@ pr_exact_combine(SellArgs a, ExactArgs x) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) qs += __shfl_xor_sync(kFull, qs, o);
       const uint32_t M0 = (ab & 0x7fffffu) | 0x800000u;
-      if (n == 32 && __all_sync(kFull, plan_l == (ab >> 23)) && ord_acc_ok(ab) && qs < kOrdOne && M0 + qs < kOrdOne) {
+      if (__all_sync(kFull, plan_l == 1u || bl_past)) continue;             // a run of all-zero blocks
+      if (n == 32 && __all_sync(kFull, plan_l == (ab >> 23) || plan_l == 1u) && ord_acc_ok(ab) && qs < kOrdOne && M0 + qs < kOrdOne) {
         ab = (ab & 0xff800000u) | ((M0 + qs) & 0x7fffffu);
         continue;
       }
       for (int i = 0; i < n; i++) {
         const uint32_t p = __shfl_sync(kFull, plan_l, i), q = __shfl_sync(kFull, q_l, i);
         const uint32_t M = (ab & 0x7fffffu) | 0x800000u;
+        if (p == 1u) continue;
         if (p != 0 && p == (ab >> 23) && q < kOrdOne && M + q < kOrdOne) {
           ab = (ab & 0xff800000u) | ((M + q) & 0x7fffffu);
         } else {
