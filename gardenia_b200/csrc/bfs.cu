@@ -31,7 +31,7 @@ namespace gdn {
 constexpr int kTdHeavy = 8192;     // largest row a single warp strip-mines; the host lowers the cut for small frontiers
 constexpr int kTdPiece = 128;      // edges per work piece of a deferred ("heavy") row
 constexpr int kBuReorderMax = 16384;   // rows longer than this keep their order in the hubs-first copy
-constexpr int kBuSerial = 8;       // in-neighbours a lane probes alone before the warp helps
+constexpr int kBuSerial = 34;      // in-neighbours a lane probes alone (2 from the head array, then 4 per step) before the warp helps
 constexpr int kAlpha = 15, kBeta = 18;   // src/bfs/omp_beamer.cc:111
 
 struct BfsCounters {
@@ -393,20 +393,38 @@ __device__ __forceinline__ int bu_warp_scan(const int32_t *__restrict__ col, con
   return -1;
 }
 
+// head[v] = the first two entries of v's (hubs-first) bottom-up row in 8 bytes: x = first neighbour or -1; y = second
+// neighbour, -1 when there is none, or -(id) - 2 when the row goes on after it.  Most vertices of a skewed graph are
+// settled by these two probes, which cost a quarter of a sector each (consecutive vertices share it) instead of a sector
+// of the offsets array plus a sector of the column array.
 template <typename OffT>
-__device__ __forceinline__ void bu_sweep_dev(const OffT *__restrict__ rowptr, const int32_t *__restrict__ col, const OffT *__restrict__ out_rowptr,
+__global__ void bu_head_build(const OffT *__restrict__ rowptr, const int32_t *__restrict__ col, int2 *__restrict__ head, int64_t rows) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+    const OffT b = rowptr[r], e = rowptr[r + 1];
+    int2 h = make_int2(-1, -1);
+    if (e > b) h.x = col[b];
+    if (e > b + 1) { h.y = col[b + 1]; if (e > b + 2) h.y = -h.y - 2; }
+    head[r] = h;
+  }
+}
+
+// depth == nullptr: the caller writes the depths of this level itself (the partitioned path: bfs_absorb, on every GPU).
+// (Writing them at the end of the BFS from per-level `next` bitmaps was measured: the sweeps got 0.15 ms faster, the extra
+// pass cost 0.19 ms.)  head == nullptr: no head array (one-shot graphs).
+template <typename OffT>
+__device__ __forceinline__ void bu_sweep_dev(const OffT *__restrict__ rowptr, const int32_t *__restrict__ col, const int2 *__restrict__ head,
                                              const uint32_t *front, uint32_t *next, uint32_t *visited, int32_t *depth,
                                              int32_t *parent, int64_t word_lo, int64_t word_hi, int64_t row_lo, bool update_visited, int level,
-                                             BfsCounters *cnt, uint16_t *s_list /* [8][1024] */, uint32_t *s_next /* [8][32] */) {
+                                             BfsCounters *cnt, uint16_t *s_list /* [8][2048] */, uint32_t *s_next /* [8][32] */) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int64_t g_lo = word_lo >> 5, g_hi = word_hi >> 5;   // word ranges are multiples of 32
   rowptr -= row_lo;                                          // rows are addressed by global vertex id
-  out_rowptr -= row_lo;
-  uint16_t *list = s_list + wib * 1024;
+  if (head) head -= row_lo;
+  uint16_t *list = s_list + wib * 2048;                      // [0, 1024): unvisited vertices of the group; [1024, 2048): pass B's list
   uint32_t *nx = s_next + wib * 32;
-  long long awake = 0, degsum = 0, probed = 0, swept = 0;
+  long long awake = 0, probed = 0, swept = 0;
   for (int64_t g = g_lo + warp; g < g_hi; g += nwarps) {
     const int64_t widx = g * 32 + lane;
     const uint32_t vis = visited[widx];
@@ -430,36 +448,102 @@ __device__ __forceinline__ void bu_sweep_dev(const OffT *__restrict__ rowptr, co
     }
     __syncwarp();
     const int64_t vbase = g * 1024;
-    for (int i0 = 0; i0 < total; i0 += 64) {
-      const bool on_a = i0 + lane < total, on_b = i0 + 32 + lane < total;
-      const int la = on_a ? list[i0 + lane] : 0, lb = on_b ? list[i0 + 32 + lane] : 0;
+    // Pass A (graphs with a head array): the first two entries of every unvisited vertex's row, four vertices per lane in
+    // flight -- two short chains of loads (head -> frontier word) that settle most vertices of a skewed graph.  The
+    // vertices that still have unprobed entries are compacted into list2: pass B then runs with every lane busy.
+    uint16_t *list2 = list;
+    int total2 = total;
+    if (head) {
+      list2 = list + 1024;
+      total2 = 0;
+      for (int i0 = 0; i0 < total; i0 += 128) {
+        int l[4];
+        int2 h[4];
+        uint32_t w0[4], w1[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int idx = i0 + u * 32 + lane;
+          l[u] = idx < total ? list[idx] : -1;
+          h[u] = l[u] >= 0 ? head[vbase + l[u]] : make_int2(-1, -1);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) w0[u] = h[u].x >= 0 ? front[(uint32_t)h[u].x >> 5] : 0u;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int y = h[u].y < -1 ? -h[u].y - 2 : h[u].y;
+          const bool hit0 = h[u].x >= 0 && ((w0[u] >> (h[u].x & 31)) & 1u);
+          w1[u] = (!hit0 && y >= 0) ? front[(uint32_t)y >> 5] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int y = h[u].y < -1 ? -h[u].y - 2 : h[u].y;
+          const bool hit0 = h[u].x >= 0 && ((w0[u] >> (h[u].x & 31)) & 1u);
+          const bool hit1 = !hit0 && y >= 0 && ((w1[u] >> (y & 31)) & 1u);
+          const int par = hit0 ? h[u].x : hit1 ? y : -1;
+          probed += (int)(h[u].x >= 0) + (int)(!hit0 && y >= 0);
+          if (par >= 0) {
+            const int64_t v = vbase + l[u];
+            if (depth) depth[v] = level;
+            if (parent) parent[v] = par;
+            atomicOr(&nx[l[u] >> 5], 1u << (l[u] & 31));
+          }
+          const bool more = l[u] >= 0 && par < 0 && h[u].y < -1;
+          const unsigned fm = __ballot_sync(kFull, par >= 0), mm = __ballot_sync(kFull, more);
+          if (lane == 0) awake += __popc(fm);
+          if (more) list2[total2 + __popc(mm & ((1u << lane) - 1u))] = (uint16_t)l[u];
+          total2 += __popc(mm);
+        }
+      }
+      __syncwarp();
+    }
+    const int skip = head ? 2 : 0;                           // entries of a row that pass A has covered
+    // Pass B: the rest of the rows, two vertices per lane
+    for (int i0 = 0; i0 < total2; i0 += 64) {
+      const bool on_a = i0 + lane < total2, on_b = i0 + 32 + lane < total2;
+      const int la = on_a ? list2[i0 + lane] : 0, lb = on_b ? list2[i0 + 32 + lane] : 0;
       const int64_t va = vbase + la, vb = vbase + lb;
-      OffT ia = 0, ea = 0, ib = 0, eb = 0;
-      if (on_a) { ia = rowptr[va]; ea = rowptr[va + 1]; }
-      if (on_b) { ib = rowptr[vb]; eb = rowptr[vb + 1]; }
-      const OffT lima = (ea - ia > (OffT)kBuSerial) ? ia + kBuSerial : ea;
-      const OffT limb = (eb - ib > (OffT)kBuSerial) ? ib + kBuSerial : eb;
       int pa = -1, pb = -1;
+      const bool more_a = on_a, more_b = on_b;
+      OffT ia = 0, ea = 0, ib = 0, eb = 0;
+      if (more_a) { ia = rowptr[va] + (OffT)skip; ea = rowptr[va + 1]; }
+      if (more_b) { ib = rowptr[vb] + (OffT)skip; eb = rowptr[vb + 1]; }
+      // every lane walks ITS two rows, four entries per step (the four column loads, then the four frontier probes, are
+      // independent: two memory latencies per step instead of eight), up to kBuSerial entries; what is left of longer
+      // rows is scanned by the whole warp below
+      const OffT lima = (ea - ia > (OffT)(kBuSerial - skip)) ? ia + (kBuSerial - skip) : ea;
+      const OffT limb = (eb - ib > (OffT)(kBuSerial - skip)) ? ib + (kBuSerial - skip) : eb;
 #pragma unroll 1
-      for (int p = 0; p < kBuSerial; p++) {
+      for (;;) {
         const bool ga = pa < 0 && ia < lima, gb = pb < 0 && ib < limb;
         if (!__any_sync(kFull, ga || gb)) break;
-        const int sa = ga ? col[ia] : 0, sb = gb ? col[ib] : 0;
-        const uint32_t wa = ga ? front[(uint32_t)sa >> 5] : 0u, wb = gb ? front[(uint32_t)sb >> 5] : 0u;
-        if (ga && ((wa >> (sa & 31)) & 1u)) pa = sa;
-        if (gb && ((wb >> (sb & 31)) & 1u)) pb = sb;
-        probed += (int)ga + (int)gb;
-        ia++; ib++;
+        int sa[4], sb[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          sa[u] = (ga && ia + u < lima) ? col[ia + u] : -1;
+          sb[u] = (gb && ib + u < limb) ? col[ib + u] : -1;
+        }
+        uint32_t wa[4], wb[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          wa[u] = sa[u] >= 0 ? front[(uint32_t)sa[u] >> 5] : 0u;
+          wb[u] = sb[u] >= 0 ? front[(uint32_t)sb[u] >> 5] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {                          // first hit in row order; entries after it are not counted as probed
+          if (pa < 0 && sa[u] >= 0) { probed++; if ((wa[u] >> (sa[u] & 31)) & 1u) pa = sa[u]; }
+          if (pb < 0 && sb[u] >= 0) { probed++; if ((wb[u] >> (sb[u] & 31)) & 1u) pb = sb[u]; }
+        }
+        ia += 4; ib += 4;
       }
       // long rows that have not hit yet: the whole warp scans the remainder
-      unsigned rest = __ballot_sync(kFull, on_a && pa < 0 && lima < ea);
+      unsigned rest = __ballot_sync(kFull, more_a && pa < 0 && lima < ea);
       while (rest) {
         const int l = __ffs(rest) - 1;
         rest &= rest - 1;
         const int hit = bu_warp_scan<OffT>(col, front, __shfl_sync(kFull, lima, l), __shfl_sync(kFull, ea, l), lane, probed);
         if (lane == l) pa = hit;
       }
-      rest = __ballot_sync(kFull, on_b && pb < 0 && limb < eb);
+      rest = __ballot_sync(kFull, more_b && pb < 0 && limb < eb);
       while (rest) {
         const int l = __ffs(rest) - 1;
         rest &= rest - 1;
@@ -467,15 +551,13 @@ __device__ __forceinline__ void bu_sweep_dev(const OffT *__restrict__ rowptr, co
         if (lane == l) pb = hit;
       }
       if (pa >= 0) {
-        depth[va] = level;
+        if (depth) depth[va] = level;
         if (parent) parent[va] = pa;
-        degsum += (long long)(out_rowptr[va + 1] - out_rowptr[va]);
         atomicOr(&nx[la >> 5], 1u << (la & 31));
       }
       if (pb >= 0) {
-        depth[vb] = level;
+        if (depth) depth[vb] = level;
         if (parent) parent[vb] = pb;
-        degsum += (long long)(out_rowptr[vb + 1] - out_rowptr[vb]);
         atomicOr(&nx[lb >> 5], 1u << (lb & 31));
       }
       const unsigned fa = __ballot_sync(kFull, pa >= 0), fb = __ballot_sync(kFull, pb >= 0);
@@ -488,27 +570,23 @@ __device__ __forceinline__ void bu_sweep_dev(const OffT *__restrict__ rowptr, co
     __syncwarp();
   }
   awake = warp_sum(awake);
-  degsum = warp_sum(degsum);
   probed = warp_sum(probed);
   swept = warp_sum(swept);
   if (lane == 0 && swept) {
     atomicAdd((unsigned long long *)&cnt->bu_edges, (unsigned long long)probed);
     atomicAdd((unsigned long long *)&cnt->bu_scanned, (unsigned long long)swept);
   }
-  if (lane == 0 && awake) {
-    atomicAdd((unsigned long long *)&cnt->awake, (unsigned long long)awake);
-    atomicAdd((unsigned long long *)&cnt->degsum, (unsigned long long)degsum);
-  }
+  if (lane == 0 && awake) atomicAdd((unsigned long long *)&cnt->awake, (unsigned long long)awake);
 }
 template <typename OffT>
 __global__ void __launch_bounds__(256, 4)
-bu_sweep(const OffT *__restrict__ rowptr, const int32_t *__restrict__ col, const OffT *__restrict__ out_rowptr,
+bu_sweep(const OffT *__restrict__ rowptr, const int32_t *__restrict__ col, const int2 *__restrict__ head,
          const uint32_t *__restrict__ front, uint32_t *__restrict__ next, uint32_t *visited, int32_t *depth,
          int32_t *parent, int64_t word_lo, int64_t word_hi, int64_t row_lo, bool update_visited, int level,
          BfsCounters *cnt) {
-  __shared__ uint16_t s_list[8 * 1024];
+  __shared__ uint16_t s_list[8 * 2048];
   __shared__ uint32_t s_next[8 * 32];
-  bu_sweep_dev<OffT>(rowptr, col, out_rowptr, front, next, visited, depth, parent, word_lo, word_hi, row_lo, update_visited, level, cnt,
+  bu_sweep_dev<OffT>(rowptr, col, head, front, next, visited, depth, parent, word_lo, word_hi, row_lo, update_visited, level, cnt,
                      s_list, s_next);
 }
 
@@ -696,6 +774,9 @@ static int bfs_prepare(gdn_graph *g) {
   GDN_CUDA(cudaMalloc((void **)&g->col_bu, sizeof(int32_t) * ci.nnz + 256));
   g->device_bytes += sizeof(int32_t) * ci.nnz;
   hubs_first<OffT><<<lib().sm_count * 8, 256, 0, lib().stream>>>((const OffT *)ci.rowptr, ci.col, g->deg_class, g->col_bu, ci.rows);
+  GDN_CUDA(cudaMalloc((void **)&g->bu_head, sizeof(int2) * std::max<int64_t>(ci.rows, 1)));
+  g->device_bytes += sizeof(int2) * ci.rows;
+  bu_head_build<OffT><<<lib().sm_count * 8, 256, 0, lib().stream>>>((const OffT *)ci.rowptr, g->col_bu, g->bu_head, ci.rows);
   GDN_CUDA(cudaStreamSynchronize(lib().stream));
   GDN_CUDA(cudaGetLastError());
   g->prep_ms[3] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -712,6 +793,7 @@ static int bfs_prepare(gdn_graph *g) {
 struct PersistArgs {
   int32_t *queue[2];
   uint32_t *bm[2];
+  const int2 *head;               // nullable
   uint32_t *visited;
   int32_t *depth, *parent;
   int32_t *heavy_q;
@@ -766,7 +848,7 @@ __device__ __forceinline__ void ctrl_after_step(BfsCtrl *c, BfsCounters *cnt, in
   } else {
     const long long awake = v->awake;
     ctrl_record(c, 1, c->old_awake, awake, awake, v->bu_edges, v->bu_scanned);
-    c->reached += awake; c->reached_deg += v->degsum;
+    c->reached += awake;
     c->fb ^= 1;                                       // front.swap(curr), :145
     c->level++;
     if (awake >= c->old_awake || awake > m / kBeta) {  // :148-149
@@ -789,7 +871,7 @@ __global__ void __launch_bounds__(256, 4)
 bfs_persist(const OffT *__restrict__ orp, const int32_t *__restrict__ ocol, const OffT *__restrict__ irp,
             const int32_t *__restrict__ bu_col, PersistArgs p) {
   // the phases never overlap inside a CTA: one buffer serves td_heavy's staging and the sweep's lists
-  __shared__ __align__(16) unsigned char s_buf[8 * 1024 * sizeof(uint16_t) + 8 * 32 * sizeof(uint32_t)];
+  __shared__ __align__(16) unsigned char s_buf[8 * 2048 * sizeof(uint16_t) + 8 * 32 * sizeof(uint32_t)];
   static_assert(sizeof(s_buf) >= 8 * kTdStage * sizeof(int), "staging buffer of td_heavy");
   cg::grid_group grid = cg::this_grid();
   volatile BfsCtrl *vc = p.ctrl;
@@ -828,13 +910,27 @@ bfs_persist(const OffT *__restrict__ orp, const int32_t *__restrict__ ocol, cons
       }
       unsigned long long t0 = 0;
       if (tid == 0) t0 = bfs_timer_ns();
-      bu_sweep_dev<OffT>(irp, bu_col, orp, bm_front, bm_next, p.visited, p.depth, p.parent, 0, p.n_words, 0, true, level + 1, p.cnt,
-                         reinterpret_cast<uint16_t *>(s_buf), reinterpret_cast<uint32_t *>(s_buf + 8 * 1024 * sizeof(uint16_t)));
+      bu_sweep_dev<OffT>(irp, bu_col, p.head, bm_front, bm_next, p.visited, p.depth, p.parent, 0, p.n_words, 0, true, level + 1, p.cnt,
+                         reinterpret_cast<uint16_t *>(s_buf), reinterpret_cast<uint32_t *>(s_buf + 8 * 2048 * sizeof(uint16_t)));
       step_done();
       grid.sync();
       if (tid == 0) p.ctrl->bu_ns += (long long)(bfs_timer_ns() - t0);
     }
   }
+}
+
+// Sum of out-degree over the reached vertices (the numerator of TEPS): measurement bookkeeping, outside the timed region
+// like the reference's own verifier; out[0] += degrees, out[1] += vertices.
+template <typename OffT>
+__global__ void __launch_bounds__(256, 4)
+bfs_count_reached(const OffT *__restrict__ out_rowptr, const int32_t *__restrict__ depth, int64_t m, unsigned long long *out) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long deg = 0, cntv = 0;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < m; v += (int64_t)gridDim.x * blockDim.x)
+    if (depth[v] != GDN_INFINITY) { deg += (unsigned long long)(out_rowptr[v + 1] - out_rowptr[v]); cntv++; }
+  deg = (unsigned long long)warp_sum((long long)deg);
+  cntv = (unsigned long long)warp_sum((long long)cntv);
+  if (lane == 0 && cntv) { atomicAdd(out, deg); atomicAdd(out + 1, cntv); }
 }
 
 template <typename OffT>
@@ -867,6 +963,7 @@ static int bfs_t(gdn_graph *g, int32_t source, int32_t *d_depth, int32_t *d_pare
     GDN_CUDA(cudaHostAlloc((void **)&g->bfs_ctrl_host, sizeof(BfsCtrl), cudaHostAllocDefault));
   }
   BfsCtrl *ctrl = (BfsCtrl *)g->bfs_ctrl, *h = (BfsCtrl *)g->bfs_ctrl_host;
+  if (!g->bfs_reached) GDN_CUDA(cudaMalloc((void **)&g->bfs_reached, 2 * sizeof(unsigned long long)));
   static int ctas_per_sm = 0;
   if (!ctas_per_sm) {
     int a = 0, b = 0;
@@ -883,7 +980,7 @@ static int bfs_t(gdn_graph *g, int32_t source, int32_t *d_depth, int32_t *d_pare
 
   PersistArgs pa;
   pa.queue[0] = g->queue[0]; pa.queue[1] = g->queue[1];
-  pa.bm[0] = g->front; pa.bm[1] = g->next;
+  pa.bm[0] = g->front; pa.bm[1] = g->next; pa.head = g->bu_head;
   pa.visited = g->visited; pa.depth = d_depth; pa.parent = d_parent;
   pa.heavy_q = g->heavy_queue; pa.heavy_off = g->heavy_off;
   pa.cnt = cnt; pa.ctrl = ctrl; pa.m = m; pa.n_words = g->n_words; pa.sm = sm;
@@ -893,6 +990,12 @@ static int bfs_t(gdn_graph *g, int32_t source, int32_t *d_depth, int32_t *d_pare
   GDN_CUDA(cudaLaunchCooperativeKernel((const void *)bfs_persist<OffT>, dim3(sm * ctas_per_sm), dim3(256), args, 0, s));
   GDN_CUDA(cudaEventRecord(lib().ev1, s));
   GDN_CUDA(cudaMemcpyAsync(h, ctrl, sizeof(BfsCtrl), cudaMemcpyDeviceToHost, s));
+  unsigned long long h_reached[2] = {0, 0};
+  if (st) {                                        // TEPS numerator: after the clock has stopped
+    GDN_CUDA(cudaMemsetAsync(g->bfs_reached, 0, 2 * sizeof(unsigned long long), s));
+    bfs_count_reached<OffT><<<sm * 8, 256, 0, s>>>(orp, d_depth, m, g->bfs_reached);
+    GDN_CUDA(cudaMemcpyAsync(h_reached, g->bfs_reached, sizeof(h_reached), cudaMemcpyDeviceToHost, s));
+  }
   GDN_CUDA(cudaStreamSynchronize(s));
   GDN_CUDA(cudaGetLastError());
   if (h->aborted) { set_error("BFS controller did not terminate"); return GDN_ERR_CUDA; }
@@ -903,8 +1006,8 @@ static int bfs_t(gdn_graph *g, int32_t source, int32_t *d_depth, int32_t *d_pare
     st->iterations = h->iter;
     st->n_steps = h->n_steps;
     st->kernel_launches = 3;
-    st->edges_reached = h->reached_deg;
-    st->vertices_reached = h->reached;
+    st->edges_reached = (int64_t)h_reached[0];
+    st->vertices_reached = (int64_t)h_reached[1];
     st->kernel_ms = (double)h->bu_ns * 1e-6;       // bottom-up sweeps, timed inside the kernel (globaltimer)
     st->kernel_calls = 0;
     for (int i = 0; i < std::min(h->n_steps, GDN_MAX_BFS_STEPS); i++) { st->steps[i] = h->steps[i]; st->kernel_calls += h->steps[i].dir; }
@@ -1048,7 +1151,7 @@ static int bfs_multi_t(gdn_graph *g, int32_t source, int32_t *d_depth, int32_t *
         old_awake = awake;
         GDN_CUDA(cudaMemsetAsync(cnt, 0, sizeof(BfsCounters), s));
         kev_begin();
-        bu_sweep<OffT><<<own_grid, 256, 0, s>>>(irp, g->col_bu ? g->col_bu : ci.col, orp, front, next, g->visited, d_depth, pbuf, own_lo,
+        bu_sweep<OffT><<<own_grid, 256, 0, s>>>(irp, g->col_bu ? g->col_bu : ci.col, g->bu_head, front, next, g->visited, nullptr, pbuf, own_lo,
                                                 own_hi, g->row_lo, false, level + 1, cnt);
         kev_end();
         launches++;

@@ -217,6 +217,8 @@ struct gdn_graph {
   uint8_t *deg_class = nullptr;       // uint8[m]: log-scale out-degree class of every vertex, 0 = hub (host-built at create)
   bool one_shot = false;              // graph lives for ONE solve (oneshot.cu): skip layouts that only pay off when amortised
   int32_t *col_bu = nullptr;          // bottom-up copy of the in-CSR columns, every row reordered hubs-first
+  int2 *bu_head = nullptr;            // first two entries of every row of col_bu (bfs.cu bu_head_build)
+  unsigned long long *bfs_reached = nullptr;
   uint32_t *xbuf = nullptr;          // partitioned BFS: receive buffer of the OR-merge (P bitmap slices)
   int32_t *parent_buf = nullptr;     // partitioned BFS: parents, P equal slices (global index)
   void *counters = nullptr;          // BfsCounters on device
