@@ -203,6 +203,11 @@ struct gdn_graph {
   int n_err_partial = 0;
   gdn::PullLayout pull;
   float *scores_sorted = nullptr;    // PR scores in sorted row order during a solve
+  // SpMV on skewed graphs: hot-first column ids + x scattered into that order (gather.cu spmv_hot_columns)
+  bool spmv_tried = false;
+  int32_t *spmv_col = nullptr;
+  float *spmv_x = nullptr;
+  double spmv_prep_ms = 0;
   // row partition: the contrib vectors of the other GPUs mapped here (comm.cu pull_peer_setup); [k][own rank] = contrib[k]
   bool peer_ready = false, peer_failed = false;
   float *peer_contrib[2][8] = {};

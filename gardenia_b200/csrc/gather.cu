@@ -21,6 +21,7 @@
 //            per row by finalize_heavy in a fixed order.
 // No atomics, deterministic run to run.
 #include "common.cuh"
+#include <chrono>
 #include <cstdlib>
 
 namespace gdn {
@@ -504,16 +505,68 @@ static void fill_sched(const DevCsr &c, GatherArgs &a) {
   a.rows = c.rows; a.nnz = c.nnz;
 }
 
+// ---- hot-first columns for SpMV on skewed graphs whose vector does not fit L2 (Kronecker scale >= 25) --------------
+// With the generator's random ids every x[Aj] of such a graph is an HBM sector miss: 19.8 ms per SpMV at Kronecker scale
+// 26 where PageRank's iteration over the same edges takes 4.5.  The degree ranking that the PageRank layout already holds
+// (newid: hottest vertex first) is applied to the COLUMN ids only -- the rows, their order of addition and Ax stay as they
+// are, so every y[r] keeps its bits -- and x is scattered into that order at the start of each call (0.4 ms): three
+// quarters of the gathers then land in a dozen L2-resident megabytes.  Built once per resident graph (4 bytes per edge).
+__global__ void __launch_bounds__(256)
+spmv_renumber_cols(const int32_t *__restrict__ col, const int32_t *__restrict__ newid, int32_t *__restrict__ out, uint64_t nnz) {
+  for (uint64_t e = (uint64_t)blockIdx.x * 256 + threadIdx.x; e < nnz; e += (uint64_t)gridDim.x * 256) out[e] = newid[col[e]];
+}
+__global__ void __launch_bounds__(256)
+spmv_scatter_x(const float *__restrict__ x, const int32_t *__restrict__ newid, float *__restrict__ xp, int64_t m) {
+  for (int64_t v = (int64_t)blockIdx.x * 256 + threadIdx.x; v < m; v += (int64_t)gridDim.x * 256) xp[__ldcs(newid + v)] = __ldcs(x + v);
+}
+double pull_hot_share(const PullLayout &L);          // pull.cu
+
+static int spmv_hot_columns(gdn_graph *g) {
+  if (g->spmv_tried) return GDN_OK;
+  g->spmv_tried = true;
+  const PullLayout &L = g->pull;
+  const char *e = getenv("GDN_SPMV_HOT");           // 0: never, 1: whenever the ranking exists
+  const int force = e ? atoi(e) : -1;
+  if (force == 0 || g->one_shot || !L.prepared || L.P != 1 || !L.newid || !L.symmetric_order || L.rows != g->m) return GDN_OK;
+  if (force < 0 && (g->m * 4 <= ((int64_t)48 << 20) || pull_hot_share(L) < 0.4)) return GDN_OK;
+  const DevCsr &c = g->in;
+  const auto t0 = std::chrono::steady_clock::now();
+  int32_t *colr = nullptr;
+  float *xp = nullptr;
+  if (cudaMalloc((void **)&colr, sizeof(int32_t) * c.nnz + 256) != cudaSuccess || cudaMalloc((void **)&xp, sizeof(float) * (g->m + 64)) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(colr);
+    return GDN_OK;                                   // an optimisation: without the memory the plain column ids do
+  }
+  GDN_CUDA(cudaMemsetAsync((char *)colr + sizeof(int32_t) * c.nnz, 0, 256, lib().stream));
+  spmv_renumber_cols<<<lib().sm_count * 16, 256, 0, lib().stream>>>(c.col, L.newid, colr, c.nnz);
+  GDN_CUDA(cudaStreamSynchronize(lib().stream));
+  GDN_CUDA(cudaGetLastError());
+  g->spmv_col = colr; g->spmv_x = xp;
+  g->device_bytes += sizeof(int32_t) * c.nnz + sizeof(float) * g->m;
+  g->spmv_prep_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return GDN_OK;
+}
+
 template <typename OffT>
 static int spmv_t(gdn_graph *g, const float *d_Ax, const float *d_x, float *d_y, gdn_stats *st) {
   const DevCsr &c = g->in;
+  GDN_CHECK(spmv_hot_columns(g));
   GatherArgs a = {};
   fill_sched(c, a);
   a.Ax = d_Ax; a.vec = d_x; a.y = d_y;
   cudaStream_t s = lib().stream;
   const OffT *rp = (const OffT *)c.rowptr;
+  const int32_t *col = c.col;
   kev_reset();
   GDN_CUDA(cudaEventRecord(lib().ev0, s));
+  int launches = 0;
+  if (g->spmv_col) {
+    spmv_scatter_x<<<lib().sm_count * 8, 256, 0, s>>>(d_x, g->pull.newid, g->spmv_x, g->m);
+    a.vec = g->spmv_x;
+    col = g->spmv_col;
+    launches++;
+  }
   // 24 warps per SM at 76-80 registers measured best on urand-24 (profiles/r1_spmv_pipe_sweep.txt): 32 warps force 64
   // registers and spill (4.2 ms), 16 warps are short of gathers in flight (2.8 ms).  Negative results kept in profiles/:
   // a TMA-staged index/value stream (cp.async.bulk per 1 K-entry item: 2.6x slower), column passes over an L2-sized
@@ -522,9 +575,9 @@ static int spmv_t(gdn_graph *g, const float *d_Ax, const float *d_x, float *d_y,
   const size_t smem = sizeof(float) * (size_t)kCap * (kPipeThreads / 32);
   GDN_CUDA(cudaFuncSetAttribute(spmv_pipe<OffT, kPipeThreads, kPipeCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kev_begin();
-  spmv_pipe<OffT, kPipeThreads, kPipeCtas><<<lib().sm_count * kPipeCtas, kPipeThreads, smem, s>>>(rp, c.col, a);
+  spmv_pipe<OffT, kPipeThreads, kPipeCtas><<<lib().sm_count * kPipeCtas, kPipeThreads, smem, s>>>(rp, col, a);
   kev_end();
-  int launches = 1;
+  launches++;
   if (c.n_heavy_rows > 0) {
     finalize_heavy<OffT, kModeSpmv><<<heavy_grid(c), kThreads, 0, s>>>(rp, a);
     launches++;

@@ -410,6 +410,7 @@ int gdn_graph_destroy(gdn_graph *g) {
   if (g->symmetric) { free_csr(g->out); g->in = DevCsr(); }
   else { free_csr(g->out); free_csr(g->in); }
   cudaFree(g->contrib[0]); cudaFree(g->contrib[1]); cudaFree(g->out_degree); cudaFree(g->err_partial);
+  cudaFree(g->spmv_col); cudaFree(g->spmv_x);
   cudaFree(g->err_trace); cudaFree(g->pr_done); cudaFree(g->pr_work); cudaFree(g->abs_partial);
   cudaFree(g->visited); cudaFree(g->front); cudaFree(g->next); cudaFree(g->iso); cudaFree(g->queue[0]); cudaFree(g->queue[1]);
   cudaFree(g->heavy_queue); cudaFree(g->heavy_off); cudaFree(g->deg_class); cudaFree(g->col_bu); cudaFree(g->bu_head); cudaFree(g->bfs_reached);

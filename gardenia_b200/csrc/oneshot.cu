@@ -194,6 +194,7 @@ int spmv_oneshot(int64_t m, int64_t nnz, const OffT *Ap, const int32_t *Aj, cons
   const double t0 = now_ms();
   GraphGuard gg;
   GDN_CHECK(create<OffT>(m, nnz, nullptr, nullptr, Ap, Aj, &gg.g));
+  gg.g->one_shot = true;
   DevBuf dAx, dx, dy;
   GDN_CHECK(dAx.alloc(sizeof(float) * nnz + 256));
   GDN_CHECK(dx.alloc(sizeof(float) * m));

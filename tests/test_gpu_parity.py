@@ -636,3 +636,33 @@ def test_pr_ordered_sum_slices(monkeypatch, kind, scale, cols):
             assert diff.mean() <= 0.005, float(diff.mean())
             ulp = np.abs(got.view(np.int32).astype(np.int64) - oscores.view(np.int32).astype(np.int64))
             assert ulp.max() <= 8, int(ulp.max())
+
+
+def test_spmv_hot_first_columns_keep_every_bit(monkeypatch):
+    """SpMV on skewed graphs whose vector does not fit L2 gathers through hot-first column ids (csrc/gather.cu
+    spmv_hot_columns; chosen by itself from Kronecker scale 25 on, forced here): rows, order of addition and values are
+    untouched, so y is bit-identical to the plain path -- and within 1e-5 per row of the oracle."""
+    import torch
+    g = gb.Graph.generate("g", 18, 16)
+    m, nnz = g.m, g.nnz
+    Ax = torch.from_numpy(gb.fill_uniform(13, nnz)).cuda()
+    x = torch.from_numpy(gb.fill_uniform(14, m)).cuda()
+    y0 = torch.from_numpy(gb.fill_uniform(15, m)).cuda()
+    monkeypatch.setenv("GDN_SPMV_HOT", "0")
+    dg = gb.DeviceGraph(g)
+    ya = y0.clone()
+    dg.spmv(Ax, x, ya)
+    dg.close()
+    monkeypatch.setenv("GDN_SPMV_HOT", "1")
+    dg = gb.DeviceGraph(g)
+    yb = y0.clone()
+    st = dg.spmv(Ax, x, yb)
+    assert st.kernel_launches >= 2                      # the scatter of x ran: the hot-first path is in use
+    yc = y0.clone()
+    dg.spmv(Ax, 2 * x, yc)                              # a second call with another x
+    dg.close()
+    assert torch.equal(ya, yb)
+    oy = po.spmv(m, g.out_rowptr(), g.out_colidx(), Ax.cpu().numpy(), x.cpu().numpy(), y0.cpu().numpy())
+    assert _rel(yb.cpu().numpy(), oy) <= SPMV_REL_TOL
+    oy2 = po.spmv(m, g.out_rowptr(), g.out_colidx(), Ax.cpu().numpy(), (2 * x).cpu().numpy(), y0.cpu().numpy())
+    assert _rel(yc.cpu().numpy(), oy2) <= SPMV_REL_TOL
