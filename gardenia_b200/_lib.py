@@ -110,6 +110,8 @@ SIGNATURES = {
     "gdn_comm_size": (C.c_int, []),
     "gdn_read_graph": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(_vp)]),
     "gdn_generate": (C.c_int, [C.c_char, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "gdn_generate_gpu": (C.c_int, [C.c_char, C.c_int, C.c_int, C.POINTER(_vp), _vp]),
+    "gdn_build_csr_gpu": (C.c_int, [_i64, _vp, C.POINTER(_vp), _vp]),
     "gdn_host_graph_free": (C.c_int, [_vp]),
     "gdn_host_graph_m": (_i64, [_vp]),
     "gdn_host_graph_nnz": (_i64, [_vp]),

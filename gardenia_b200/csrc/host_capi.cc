@@ -11,7 +11,12 @@
 #include "../host/generator.hpp"
 #include "../host/graph_io.hpp"
 
-namespace gdn { void set_error(const char *fmt, ...); }
+namespace gdn {
+void set_error(const char *fmt, ...);
+// build.cu: the CSR builder on the GPU (same result as build_symmetric_csr)
+int gpu_build_symmetric_csr(const void *el_host, int64_t n_edges, int64_t *m_out, uint64_t **rowptr_out, int32_t **col_out,
+                            uint64_t *nnz_out, int32_t *maxdeg_out, double ms[4]);
+}
 
 struct gdn_host_graph {
   gdn::Graph g;                 // gen-2 loader / generator
@@ -65,6 +70,39 @@ int gdn_generate(char kind, int scale, int degree, gdn_host_graph **out) {
   gdn::generate_graph(hg->g, kind == 'u', scale, degree);
   *out = hg;
   return GDN_OK;
+}
+
+// Edge list -> symmetric, sorted, duplicate-free, self-loop-free CSR, built on the GPU (csrc/build.cu).
+int gdn_build_csr_gpu(int64_t n_edges, const int32_t *pairs, gdn_host_graph **out, double *ms /* nullable [4] */) {
+  if (!out || n_edges < 0 || (n_edges > 0 && !pairs)) { gdn::set_error("gdn_build_csr_gpu: bad argument"); return GDN_ERR_ARG; }
+  int64_t m = 0;
+  uint64_t *rowptr = nullptr, nnz = 0;
+  int32_t *col = nullptr, maxdeg = 0;
+  const int rc = gdn::gpu_build_symmetric_csr(pairs, n_edges, &m, &rowptr, &col, &nnz, &maxdeg, ms);
+  if (rc != GDN_OK) return rc;
+  gdn_host_graph *hg = new gdn_host_graph();
+  hg->g.adopt_symmetric((VertexId)m, nnz, rowptr, col, (VertexId)maxdeg);
+  *out = hg;
+  return GDN_OK;
+}
+
+// gdn_generate with the builder on the GPU: the edge streams are drawn on the host (they are defined by libstdc++'s
+// mt19937 / distributions, include/generator.h:64-114), the CSR is built by csrc/build.cu.  ms (nullable, 5 entries):
+// edge generation, upload + keys, sort, unique + offsets, download.
+int gdn_generate_gpu(char kind, int scale, int degree, gdn_host_graph **out, double *ms) {
+  if (!out || (kind != 'g' && kind != 'u') || scale < 1 || scale > 30 || degree < 1) {
+    gdn::set_error("gdn_generate_gpu: bad argument");
+    return GDN_ERR_ARG;
+  }
+  const int64_t n_edges = (int64_t(1) << scale) * degree;
+  gdn::EdgePair32 *el = new gdn::EdgePair32[n_edges];
+  const double t0 = omp_get_wtime();
+  if (kind == 'u') gdn::make_uniform_el(scale, degree, el);
+  else gdn::make_rmat_el(scale, degree, el);
+  if (ms) ms[0] = (omp_get_wtime() - t0) * 1e3;
+  const int rc = gdn_build_csr_gpu(n_edges, reinterpret_cast<const int32_t *>(el), out, ms ? ms + 1 : nullptr);
+  delete[] el;
+  return rc;
 }
 
 int gdn_host_graph_free(gdn_host_graph *hg) { delete hg; return GDN_OK; }

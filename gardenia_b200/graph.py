@@ -45,6 +45,25 @@ class Graph:
         return cls(_handle=h)
 
     @classmethod
+    def generate_gpu(cls, kind, scale, degree=16):
+        """Same graph as generate(), its CSR built on the GPU (csrc/build.cu); .build_ms holds the stage times."""
+        h = C.c_void_p()
+        ms = (C.c_double * 5)()
+        check(lib.gdn_generate_gpu(kind.encode()[0:1], int(scale), int(degree), C.byref(h), C.cast(ms, C.c_void_p)))
+        g = cls(_handle=h)
+        g.build_ms = dict(zip(["edge_streams_host", "upload_keys", "sort", "unique_offsets", "download"], [float(x) for x in ms]))
+        return g
+
+    @classmethod
+    def from_edges(cls, pairs):
+        """Symmetrized, squished CSR of an (n, 2) int32 edge array, built on the GPU."""
+        import numpy as np
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        h = C.c_void_p()
+        check(lib.gdn_build_csr_gpu(len(pairs), pairs.ctypes.data, C.byref(h), None))
+        return cls(_handle=h)
+
+    @classmethod
     def from_file(cls, path, symmetrize=False):
         """gen-1 reader dispatching on the suffix (.mtx/.graph/.gr/.el), include/graph_io.h:357-377."""
         h = C.c_void_p()

@@ -219,6 +219,12 @@ int gdn_read_graph(const char *prefix, const char *filetype, int symmetrize, int
 /* kind 'g' = Kronecker (R-MAT), 'u' = uniform random; always symmetrized
  * (include/command_line.h:75-76). */
 int gdn_generate(char kind, int scale, int degree, gdn_host_graph **hg);
+/* The same graph as gdn_generate with the CSR built ON THE GPU (csrc/build.cu: 64-bit radix sort of both directions of
+ * every edge, adjacent-unique, offsets by binary search) in place of the reference's host builder (include/builder.h:
+ * 152-257).  ms (nullable): [0] edge streams on the host, [1] upload + keys, [2] sort, [3] unique + offsets, [4] download. */
+int gdn_generate_gpu(char kind, int scale, int degree, gdn_host_graph **hg, double *ms);
+/* Any edge list: n_edges (u, v) int32 pairs on the host -> symmetrized, squished CSR (include/builder.h:66-119,152-195). */
+int gdn_build_csr_gpu(int64_t n_edges, const int32_t *pairs, gdn_host_graph **hg, double *ms);
 int gdn_host_graph_free(gdn_host_graph *hg);
 int64_t gdn_host_graph_m(const gdn_host_graph *hg);
 int64_t gdn_host_graph_nnz(const gdn_host_graph *hg);

@@ -666,3 +666,44 @@ def test_spmv_hot_first_columns_keep_every_bit(monkeypatch):
     assert _rel(yb.cpu().numpy(), oy) <= SPMV_REL_TOL
     oy2 = po.spmv(m, g.out_rowptr(), g.out_colidx(), Ax.cpu().numpy(), (2 * x).cpu().numpy(), y0.cpu().numpy())
     assert _rel(yc.cpu().numpy(), oy2) <= SPMV_REL_TOL
+
+
+# ------------------------------------------------------------------ the CSR builder on the GPU (csrc/build.cu)
+@pytest.mark.parametrize("kind,scale,degree", [("g", 10, 16), ("u", 10, 16), ("g", 12, 8), ("g", 16, 16), ("u", 16, 16), ("g", 20, 16), ("u", 21, 16)])
+def test_gpu_csr_build_is_bit_identical(kind, scale, degree):
+    """Edge list -> CSR on the GPU (64-bit radix sort + unique + offsets, our own kernels) gives exactly the arrays of the
+    host builder -- which tests/test_host.py pins to the reference's Builder (ref_gen CSRs and the size KATs of SURVEY 8(c))."""
+    a = gb.Graph.generate(kind, scale, degree)
+    b = gb.Graph.generate_gpu(kind, scale, degree)
+    assert (a.m, a.nnz) == (b.m, b.nnz)
+    assert np.array_equal(a.out_rowptr(), b.out_rowptr())
+    assert np.array_equal(a.out_colidx(), b.out_colidx())
+    assert b.symmetric and b.has_reverse_graph()
+
+
+def test_gpu_csr_build_edge_cases():
+    """Duplicates in both directions, self loops, isolated vertices below the maximum id, a single edge, an empty list."""
+    rng = np.random.default_rng(11)
+    cases = {
+        "dups": np.array([[0, 1], [1, 0], [0, 1], [2, 2], [5, 3], [3, 5], [5, 5], [7, 0]], np.int32),
+        "single": np.array([[3, 9]], np.int32),
+        "loops_only": np.array([[4, 4], [2, 2]], np.int32),
+        "random": rng.integers(0, 5000, size=(200000, 2)).astype(np.int32),
+        "hub": np.stack([np.zeros(70000, np.int32), rng.integers(0, 100000, 70000).astype(np.int32)], 1),
+    }
+    for name, pairs in cases.items():
+        g = gb.Graph.from_edges(pairs)
+        m = int(pairs.max()) + 1
+        rows = {}
+        for u, v in pairs.tolist():
+            if u != v:
+                rows.setdefault(u, set()).add(v)
+                rows.setdefault(v, set()).add(u)
+        rp = np.zeros(m + 1, np.uint64)
+        for r, s in rows.items():
+            rp[r + 1] = len(s)
+        rp = np.cumsum(rp).astype(np.uint64)
+        ci = np.concatenate([np.array(sorted(rows.get(r, ())), np.int32) for r in range(m)]) if rows else np.zeros(0, np.int32)
+        assert g.m == m and g.nnz == len(ci), name
+        assert np.array_equal(g.out_rowptr(), rp), name
+        assert np.array_equal(g.out_colidx(), ci), name
