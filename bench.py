@@ -617,6 +617,8 @@ def bench_bfs(ctx, args, scale, steps, warmup, side=False):
     e2e = None
     if world == 1:
         dg.close()
+        for a in (g.out_rowptr(), g.out_colidx()):           # page-lock the caller's CSR once (untimed), like a loader would
+            ctx._lib.lib.gdn_host_pin(a.ctypes.data, a.nbytes)
         dist_h = np.empty(m, dtype=np.int32)
         calls = []
         edges = 0.0
@@ -631,7 +633,9 @@ def bench_bfs(ctx, args, scale, steps, warmup, side=False):
             edges += st.edges_reached / 2
         e2e = {"value": edges / sum(calls) / 1e9, "unit": "GTEPS", "h2d_bytes_per_step": int(st.h2d_bytes), "d2h_bytes_per_step": int(st.d2h_bytes),
                "steps": len(calls), "ms_per_call": [round(c * 1e3, 1) for c in calls],
-               "timed": "wall clock around each BFSSolver call on host arrays (upload + solve + download; 1 warm-up call)"}
+               "timed": "wall clock around each BFSSolver call on pinned host arrays (upload + solve + download; 1 warm-up call)"}
+        for a in (g.out_rowptr(), g.out_colidx()):
+            ctx._lib.lib.gdn_host_unpin(a.ctypes.data)
     else:
         dg.close()
         e2e = {"value": None, "unit": "GTEPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
@@ -711,7 +715,9 @@ def bench_spmv(ctx, args, scale, steps, warmup, side=False):
         parity.update(spmv_maxrel=rel, ok=bool(rel <= 1e-5), rows_bit_identical=float((mine == ref).mean()))
     dgu.close()
     del Ax, x, y
-    # e2e: SpmvSolver on host arrays
+    # e2e: SpmvSolver on host arrays (page-locked once, untimed, like a loader would)
+    for a in (gu.out_rowptr(), gu.out_colidx(), Ax_h):
+        ctx._lib.lib.gdn_host_pin(a.ctypes.data, a.nbytes)
     y_h = np.zeros(m, dtype=np.float32)
     calls = []
     for k in range(3):
@@ -723,7 +729,9 @@ def bench_spmv(ctx, args, scale, steps, warmup, side=False):
             calls.append(dt)
     e2e = {"value": 2.0 * nnz / (sum(calls) / len(calls)) / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": int(st.h2d_bytes),
            "d2h_bytes_per_step": int(st.d2h_bytes), "steps": len(calls), "ms_per_call": [round(c * 1e3, 1) for c in calls],
-           "timed": "wall clock around each SpmvSolver call on host arrays (upload + solve + download; 1 warm-up call)"}
+           "timed": "wall clock around each SpmvSolver call on pinned host arrays (upload + solve + download; 1 warm-up call)"}
+    for a in (gu.out_rowptr(), gu.out_colidx(), Ax_h):
+        ctx._lib.lib.gdn_host_unpin(a.ctypes.data)
     line = {
         "metric": METRICS["spmv"][0], "value": 2.0 * nnz / (ms / 1e3) / 1e9, "unit": "GFLOP/s", "n_gpus": 1, "steps": steps, "warmup": max(warmup, 3),
         "ms_per_step": tot / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

@@ -123,6 +123,7 @@ SIGNATURES = {
     "gdn_host_graph_in_colidx": (_vp, [_vp]),
     "gdn_host_graph_weights": (_vp, [_vp]),
     "gdn_host_graph_write_bin": (C.c_int, [_vp, C.c_char_p]),
+    "gdn_host_graph_write_sg": (C.c_int, [_vp, C.c_char_p, C.c_int]),
     "gdn_set_host_threads": (C.c_int, [C.c_int]),
     "gdn_fill_uniform": (C.c_int, [C.c_uint32, _i64, _vp]),
     "gdn_pick_sources": (C.c_int, [_vp, C.c_int, _vp]),

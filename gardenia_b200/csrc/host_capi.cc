@@ -36,6 +36,10 @@ int gdn_read_graph(const char *prefix, const char *filetype, int symmetrize, int
   if (!prefix || !filetype || !out) { gdn::set_error("gdn_read_graph: null argument"); return GDN_ERR_ARG; }
   gdn_host_graph *hg = new gdn_host_graph();
   std::string ft = filetype;
+  {
+    const std::string path = prefix;                       // "auto" on a .sg path: the serialized-graph reader
+    if (ft == "auto" && path.size() > 3 && path.compare(path.size() - 3, 3, ".sg") == 0) ft = "sg";
+  }
   if (ft == "auto") {
     gdn::ReadOpts o;
     o.symmetrize = symmetrize != 0;
@@ -121,6 +125,15 @@ const int32_t *gdn_host_graph_in_colidx(const gdn_host_graph *hg) {
   return (hg->gen1 || !hg->g.has_reverse_graph()) ? nullptr : hg->g.in_colidx();
 }
 const int32_t *gdn_host_graph_weights(const gdn_host_graph *hg) { return hg->gen1 ? hg->c1.weight : nullptr; }
+
+int gdn_host_graph_write_sg(const gdn_host_graph *hg, const char *path, int offset_bytes) {
+  if (!hg || !path || hg->gen1) { gdn::set_error("gdn_host_graph_write_sg: bad argument"); return GDN_ERR_ARG; }
+  if (hg->g.write_sg(path, offset_bytes) != 0) {
+    gdn::set_error("cannot write %s (offset width %d; a directed graph needs its reverse CSR)", path, offset_bytes);
+    return GDN_ERR_IO;
+  }
+  return GDN_OK;
+}
 
 int gdn_host_graph_write_bin(const gdn_host_graph *hg, const char *prefix) {
   if (!hg || !prefix || hg->gen1) { gdn::set_error("gdn_host_graph_write_bin: bad argument"); return GDN_ERR_ARG; }

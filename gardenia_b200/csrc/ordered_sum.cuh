@@ -16,9 +16,11 @@
 //                         ~25 that carry into the next binade, a wrong guess, a negative or non-finite addend) is redone
 //                         by ordered_block below, which emulates the adds of that block exactly -- so a wrong guess
 //                         costs time, never a bit.
-// The result equals the sequential sum bit for bit except where an addend falls EXACTLY half-way between two multiples of
-// ulp with M odd (round-half-even looks at M: probability ~2^-19 per add, one ulp of the accumulator each) -- against
-// sqrt(n) ulps for a re-ordered sum.  The critical path of a 10^6-entry row is ~2000 integer adds plus ~30 careful blocks.
+// One case is NOT order-free: an addend EXACTLY half-way between two multiples of ulp is rounded by the hardware to the
+// even ACCUMULATOR, not to the even addend (probability 2^-d per add, d = exponent gap between accumulator and addend:
+// a few adds per long row, nearly every add of its first block).  A block that holds such a tie is summed by true
+// sequential adds (pass 3 un-plans it, ordered_block takes its fallback), so the result IS the sequential sum, bit for
+// bit.  The critical path of a 10^6-entry row is ~2000 integer adds plus ~40 careful blocks, ~10 of them sequential.
 #pragma once
 #include "pull.cuh"
 
@@ -33,6 +35,8 @@ constexpr uint32_t kOrdOne = 0x1000000u;  // 2^24: the mantissa integer M of the
 __device__ __forceinline__ bool ord_acc_ok(uint32_t ab) { return ab >= 0x0C000000u && ab < 0x7f000000u; }
 // 1 / ulp(acc) = 2^(23 - (e - 127)) for biased exponent e
 __device__ __forceinline__ float ord_scale(uint32_t e) { return __uint_as_float((277u - e) << 23); }
+// t = x / ulp lies exactly half-way between two integers (t < 2^23: above that a float has no fraction bits)
+__device__ __forceinline__ bool ord_tie(float t) { return t < 8388608.f && t - floorf(t) == 0.5f; }
 
 // One block, exactly: the accumulator (bits ab) after adding the 512 columns of a block in order; lane l holds columns
 // 16 l .. 16 l + 15 in x[].  stage = 512 floats of shared memory owned by the warp (used only by the sequential fallback).
@@ -44,7 +48,14 @@ __device__ __forceinline__ uint32_t ordered_block(uint32_t ab, const float (&x)[
   const bool good = __all_sync(kFull, mbits < 0x7f800000u);
   int pos = 0;                                                             // columns of the block already in the accumulator
   while (pos < 512) {
-    if (!good || !ord_acc_ok(ab)) {
+    bool tie = false;                                                      // a half-way addend under the current ulp?
+    if (good && ord_acc_ok(ab)) {
+      const float sc = ord_scale(ab >> 23);
+#pragma unroll
+      for (int i = 0; i < 16; i++) tie |= lane * 16 + i >= pos && ord_tie(__fmul_rn(x[i], sc));
+      tie = __any_sync(kFull, tie);
+    }
+    if (!good || !ord_acc_ok(ab) || tie) {
       // one true add at a time (every lane computes the same accumulator)
 #pragma unroll
       for (int i = 0; i < 16; i++) stage[lane * 16 + i] = x[i];
@@ -209,7 +220,8 @@ pr_exact_plan(SellArgs a, ExactArgs x) {
   }
 }
 
-// Pass 3.  One warp per planned block: Q_b = sum of rne(x / ulp) for the planned binade.
+// Pass 3.  One warp per planned block: Q_b = sum of rne(x / ulp) for the planned binade; a block with a half-way addend
+// loses its plan (pass 4 then adds it sequentially).
 __global__ void __launch_bounds__(256, 4)
 pr_exact_qsum(SellArgs a, ExactArgs x) {
   if (*a.done) return;
@@ -221,15 +233,21 @@ pr_exact_qsum(SellArgs a, ExactArgs x) {
     const float scale = ord_scale(ex);
     const float4 *src = x.vals + (size_t)k * kOrdBlockGroups + lane * 4;
     uint32_t run = 0;
+    bool tie = false;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       const float4 v = __ldcs(src + i);
-      run += __float2uint_rn(__fmul_rn(v.x, scale)) + __float2uint_rn(__fmul_rn(v.y, scale)) +
-             __float2uint_rn(__fmul_rn(v.z, scale)) + __float2uint_rn(__fmul_rn(v.w, scale));
+      const float t[4] = {__fmul_rn(v.x, scale), __fmul_rn(v.y, scale), __fmul_rn(v.z, scale), __fmul_rn(v.w, scale)};
+#pragma unroll
+      for (int u = 0; u < 4; u++) { run += __float2uint_rn(t[u]); tie |= ord_tie(t[u]); }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) run += __shfl_xor_sync(kFull, run, o);
-    if (lane == 0) x.Q[k] = run;
+    tie = __any_sync(kFull, tie);
+    if (lane == 0) {
+      x.Q[k] = run;
+      if (tie) x.plan[k] = 0;
+    }
   }
 }
 

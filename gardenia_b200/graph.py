@@ -111,6 +111,10 @@ class Graph:
     def write_bin(self, prefix):
         check(lib.gdn_host_graph_write_bin(self._h, str(prefix).encode()))
 
+    def write_sg(self, path, offset_bytes=4):
+        """The serialized graph the GAP-style drivers read (include/reader.h:259-316)."""
+        check(lib.gdn_host_graph_write_sg(self._h, str(path).encode(), int(offset_bytes)))
+
     def pick_sources(self, n=16):
         """GAP-style BFS sources: mt19937(27491095), degree-0 rejected."""
         out = np.zeros(n, dtype=np.int32)

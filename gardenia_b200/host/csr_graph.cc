@@ -225,10 +225,124 @@ int Graph::load_bin(const std::string &prefix, bool symmetrize, bool need_revers
   return kLoadOk;
 }
 
+// Serialized graph of the GAP-style reader (include/reader.h:259-316):
+//   bool directed | SGOffset num_edges | SGOffset num_vertices | SGOffset offsets[nv + 1] | int32 neighs[ne]
+//   and, for a directed graph, the inverse CSR: offsets[nv + 1] | neighs[ne].
+// SGOffset is `int` in the reference (include/graph.h:77-79) and int64_t in upstream GAP files: the width is recognised
+// from the file size, which either layout determines exactly.  The file holds a finished CSR: it is adopted as it is
+// (symmetrize has nothing to do, as in include/builder.h:264); only its consistency is checked.
+template <typename Off>
+static int read_sg_body(FILE *f, long long fsize, bool directed, bool want_inverse, VertexId &nv_out, uint64_t &ne_out,
+                        uint64_t *&rowptr, VertexId *&col, uint64_t *&t_rowptr, VertexId *&t_col) {
+  Off hdr[2];
+  if (fseek(f, 1, SEEK_SET) != 0 || fread(hdr, sizeof(Off), 2, f) != 2) return kLoadBadHeader;
+  const long long ne = (long long)hdr[0], nv = (long long)hdr[1];
+  if (ne < 0 || nv < 0 || nv > 0x7fffffffll) return kLoadBadHeader;
+  const long long part = (nv + 1) * (long long)sizeof(Off) + ne * (long long)sizeof(VertexId);
+  if (fsize != 1 + 2 * (long long)sizeof(Off) + (directed ? 2 : 1) * part) return kLoadBadHeader;
+  auto read_csr = [&](uint64_t *&rp, VertexId *&ci) -> int {
+    rp = new uint64_t[nv + 1];
+    ci = new VertexId[std::max<long long>(ne, 1)];
+    if (sizeof(Off) == sizeof(uint64_t)) {
+      if (fread(rp, sizeof(uint64_t), (size_t)nv + 1, f) != (size_t)nv + 1) return kLoadBadHeader;
+    } else {
+      Off *tmp = new Off[nv + 1];
+      const bool ok = fread(tmp, sizeof(Off), (size_t)nv + 1, f) == (size_t)nv + 1;
+      for (long long i = 0; ok && i <= nv; i++) rp[i] = (uint64_t)(int64_t)tmp[i];
+      delete[] tmp;
+      if (!ok) return kLoadBadHeader;
+    }
+    if (fread(ci, sizeof(VertexId), (size_t)ne, f) != (size_t)ne) return kLoadBadHeader;
+    if (rp[0] != 0 || rp[nv] != (uint64_t)ne) return kLoadBadVertex;
+    long long bad = 0;
+#pragma omp parallel for reduction(+ : bad)
+    for (long long v = 0; v < nv; v++) bad += rp[v + 1] < rp[v] || rp[v + 1] > (uint64_t)ne;
+    if (bad) return kLoadBadVertex;
+#pragma omp parallel for reduction(+ : bad)
+    for (long long e = 0; e < ne; e++) bad += ci[e] < 0 || ci[e] >= nv;
+    return bad ? kLoadBadVertex : kLoadOk;
+  };
+  int rc = read_csr(rowptr, col);
+  if (rc == kLoadOk && directed && want_inverse) rc = read_csr(t_rowptr, t_col);
+  nv_out = (VertexId)nv;
+  ne_out = (uint64_t)ne;
+  return rc;
+}
+
+int Graph::load_sg(const std::string &fname, bool need_reverse, bool verbose) {
+  if (verbose) std::cout << "Reading (.sg) input file " << fname << "\n";
+  FILE *f = fopen(fname.c_str(), "rb");
+  if (!f) return kLoadNoFile;
+  fseek(f, 0, SEEK_END);
+  const long long fsize = ftell(f);
+  unsigned char dir = 0;
+  if (fsize < 9 || fseek(f, 0, SEEK_SET) != 0 || fread(&dir, 1, 1, f) != 1 || dir > 1) { fclose(f); return kLoadBadHeader; }
+  const bool directed = dir != 0;
+  uint64_t *rp = nullptr, *trp = nullptr;
+  VertexId *ci = nullptr, *tci = nullptr;
+  VertexId nv = 0;
+  uint64_t ne = 0;
+  int rc = read_sg_body<int32_t>(f, fsize, directed, need_reverse, nv, ne, rp, ci, trp, tci);
+  if (rc == kLoadBadHeader) {                      // not the reference's 32-bit offsets: an upstream GAP file?
+    delete[] rp; delete[] ci; delete[] trp; delete[] tci;
+    rp = trp = nullptr; ci = tci = nullptr;
+    rc = read_sg_body<int64_t>(f, fsize, directed, need_reverse, nv, ne, rp, ci, trp, tci);
+  }
+  fclose(f);
+  if (rc != kLoadOk) { delete[] rp; delete[] ci; delete[] trp; delete[] tci; return rc; }
+  VertexId maxd = 0;
+#pragma omp parallel for reduction(max : maxd)
+  for (VertexId v = 0; v < nv; v++) maxd = std::max(maxd, (VertexId)(rp[v + 1] - rp[v]));
+  if (verbose) std::cout << "|V| " << nv << " |E| " << ne << "\n";
+  if (!directed) adopt_symmetric(nv, ne, rp, ci, maxd);
+  else if (need_reverse) adopt_directed(nv, ne, rp, ci, trp, tci, maxd);
+  else {
+    release();
+    n_vertices_ = nv; n_edges_ = ne; vertices_ = rp; edges_ = ci; max_degree_ = maxd;
+    directed_ = true; has_reverse_ = false;
+  }
+  return kLoadOk;
+}
+
+int Graph::write_sg(const std::string &fname, int offset_bytes) const {
+  if (offset_bytes != 4 && offset_bytes != 8) return -1;
+  if (offset_bytes == 4 && n_edges_ > 0x7fffffffull) return -1;       // does not fit the reference's SGOffset
+  if (directed_ && !has_reverse_) return -1;                          // a directed .sg carries its inverse
+  FILE *f = fopen(fname.c_str(), "wb");
+  if (!f) return -1;
+  const unsigned char dir = directed_ ? 1 : 0;
+  bool ok = fwrite(&dir, 1, 1, f) == 1;
+  auto put = [&](uint64_t v) {
+    if (offset_bytes == 4) { const int32_t w = (int32_t)v; ok = ok && fwrite(&w, 4, 1, f) == 1; }
+    else { const int64_t w = (int64_t)v; ok = ok && fwrite(&w, 8, 1, f) == 1; }
+  };
+  put(n_edges_);
+  put((uint64_t)n_vertices_);
+  auto put_csr = [&](const uint64_t *rp, const VertexId *ci) {
+    if (offset_bytes == 8) ok = ok && fwrite(rp, 8, (size_t)n_vertices_ + 1, f) == (size_t)n_vertices_ + 1;
+    else {
+      int32_t *tmp = new int32_t[(size_t)n_vertices_ + 1];
+      for (int64_t i = 0; i <= n_vertices_; i++) tmp[i] = (int32_t)rp[i];
+      ok = ok && fwrite(tmp, 4, (size_t)n_vertices_ + 1, f) == (size_t)n_vertices_ + 1;
+      delete[] tmp;
+    }
+    ok = ok && fwrite(ci, sizeof(VertexId), n_edges_, f) == n_edges_;
+  };
+  put_csr(vertices_, edges_);
+  if (directed_) put_csr(reverse_vertices_, reverse_edges_);
+  return fclose(f) == 0 && ok ? 0 : -1;
+}
+
 int Graph::load(const std::string &prefix, const std::string &filetype, bool symmetrize,
                 bool need_reverse, bool verbose) {
   release();
   int rc;
+  if (filetype == "sg") {
+    // the .sg of the GAP-style drivers (include/reader.h:259-316) keeps whatever graph it was built from: the
+    // degenerate-graph check of the gen-2 constructor does not apply
+    const bool has_suffix = prefix.size() > 3 && prefix.compare(prefix.size() - 3, 3, ".sg") == 0;
+    return load_sg(has_suffix ? prefix : prefix + ".sg", need_reverse, verbose);
+  }
   if (filetype == "mtx") rc = load_mtx(prefix + ".mtx", symmetrize, need_reverse, verbose);
   else if (filetype == "bin") rc = load_bin(prefix, symmetrize, need_reverse, verbose);
   else return kLoadBadType;

@@ -73,6 +73,9 @@ class Graph {
            bool need_reverse, bool verbose);
   int load_mtx(const std::string &fname, bool symmetrize, bool need_reverse, bool verbose);
   int load_bin(const std::string &prefix, bool symmetrize, bool need_reverse, bool verbose);
+  // Serialized graph of the GAP-style reader (include/reader.h:259-316); 32- or 64-bit offsets, recognised by file size.
+  int load_sg(const std::string &fname, bool need_reverse, bool verbose);
+  int write_sg(const std::string &fname, int offset_bytes = 4) const;
   // Adopt an already squished symmetric CSR (generator output); takes ownership.
   void adopt_symmetric(VertexId m, uint64_t nnz, uint64_t *rowptr, VertexId *col, VertexId max_degree);
   // Adopt a directed CSR pair; takes ownership.

@@ -212,8 +212,11 @@ int gdn_comm_size(void);   /* 1 when no communicator */
 
 /* ---- host graphs: readers and generator (no GPU needed) ----------------------- */
 /* filetype "mtx" | "bin": gen-2 loader (include/csr_graph.h:211-250);
+ * filetype "sg": serialized graph of the GAP-style reader (include/reader.h:259-316; prefix or full path; offsets of
+ *   4 bytes as the reference writes them or 8 as upstream GAP does, recognised by the file size; symmetrize is ignored,
+ *   the file is a finished CSR -- include/builder.h:264);
  * filetype "auto": gen-1 loader dispatching on the suffix .mtx/.graph/.gr/.el
- * (include/graph_io.h:357-377), `prefix` is then the full path. */
+ * (include/graph_io.h:357-377), `prefix` is then the full path; a .sg path goes to the "sg" reader. */
 int gdn_read_graph(const char *prefix, const char *filetype, int symmetrize, int need_reverse,
                    gdn_host_graph **hg);
 /* kind 'g' = Kronecker (R-MAT), 'u' = uniform random; always symmetrized
@@ -236,6 +239,8 @@ const uint64_t *gdn_host_graph_in_rowptr(const gdn_host_graph *hg);   /* NULL wi
 const int32_t *gdn_host_graph_in_colidx(const gdn_host_graph *hg);
 const int32_t *gdn_host_graph_weights(const gdn_host_graph *hg);      /* gen-1 loader only, else NULL */
 int gdn_host_graph_write_bin(const gdn_host_graph *hg, const char *prefix);
+/* The .sg layout read by include/reader.h:259-316; offset_bytes 4 (the reference's SGOffset) or 8 (upstream GAP). */
+int gdn_host_graph_write_sg(const gdn_host_graph *hg, const char *path, int offset_bytes);
 /* OpenMP threads used by the host side (generator, readers, layout preprocessing).  Launchers such as
  * torchrun export OMP_NUM_THREADS=1, which would make the Kronecker generator 15x slower. */
 int gdn_set_host_threads(int n);

@@ -11,25 +11,36 @@
 // The reference builder is `int`-limited (include/graph.h:77-79), so this is
 // only usable up to scale 25; it is the cross-check for our 64-bit generator.
 //
-// usage: ref_gen (-g <scale> | -u <scale>) [-k <degree>] -o <prefix>
+// With -S <file.sg> the graph comes from the reference's serialized-graph reader instead (include/reader.h:259-316,
+// Reader::ReadSerializedGraph called directly: Builder::MakeGraph, include/builder.h:258-274, reads the file and then
+// overwrites the graph with an empty edge list's) -- the cross-check of our .sg writer and reader.
+//
+// usage: ref_gen (-g <scale> | -u <scale> | -S <file.sg>) [-k <degree>] -o <prefix>
 #include "common.h"
 #include "builder.h"
 #include <cstdio>
 #include <string>
 
 int main(int argc, char **argv) {
-  std::string out;
+  std::string out, sg;
   std::vector<char *> args;
   for (int i = 0; i < argc; i++) {
     if (std::string(argv[i]) == "-o" && i + 1 < argc) { out = argv[++i]; continue; }
+    if (std::string(argv[i]) == "-S" && i + 1 < argc) { sg = argv[++i]; continue; }
     args.push_back(argv[i]);
   }
   if (out.empty()) { fprintf(stderr, "usage: ref_gen (-g s | -u s) [-k d] -o prefix\n"); return 2; }
-  CLBase cli((int)args.size(), args.data(), "ref_gen");
-  if (!cli.ParseArgs()) return 2;
-  Builder b(cli);
   Graph g;
-  b.MakeGraph(g);
+  if (!sg.empty()) {
+    Reader<VertexID, VertexID, WeightT, true> r(sg);
+    r.ReadSerializedGraph(g);
+    g.SetupRowptr();                 // the reader fills the pointer index only (include/graph.h:272-282)
+  } else {
+    CLBase cli((int)args.size(), args.data(), "ref_gen");
+    if (!cli.ParseArgs()) return 2;
+    Builder b(cli);
+    b.MakeGraph(g);
+  }
   int64_t m = g.num_vertices();
   const int *rowptr = g.out_rowptr();
   const int *col = g.out_colidx();

@@ -607,8 +607,8 @@ def test_pr_ordered_sum_slices(monkeypatch, kind, scale, cols):
     """Exact slices of the default mode (csrc/ordered_sum.cuh: gather, plan, integer block sums, in-order combine), forced
     onto small graphs by lowering the width threshold: rows wider than `cols` are summed in the reference's order by
     emulation -- same iteration count, 1e-6 L1.  With cols = 128 and the banded layout off EVERY row is summed in the
-    reference's order (narrower slices are never cut), so the scores are the oracle's bit for bit -- an exact tie of the
-    rounding is the emulation's only licence to differ: a handful of rows, by an ulp or two."""
+    reference's order (narrower slices are never cut; blocks holding a half-way addend, where the hardware's rounding looks
+    at the accumulator, are added one by one), so the scores are the oracle's bit for bit."""
     import torch
     monkeypatch.setenv("GDN_PR_EXACT_COLS", str(cols))
     monkeypatch.setenv("GDN_PR_EXACT_BUDGET", str(1 << 40))
@@ -632,10 +632,8 @@ def test_pr_ordered_sum_slices(monkeypatch, kind, scale, cols):
         assert float(np.abs(got.astype(np.float64) - oscores.astype(np.float64)).sum()) <= PR_L1_TOL
         if cols == 128:
             assert (deg > cols).sum() >= (32 if kind == "g" else 0)
-            diff = got != oscores
-            assert diff.mean() <= 0.005, float(diff.mean())
             ulp = np.abs(got.view(np.int32).astype(np.int64) - oscores.view(np.int32).astype(np.int64))
-            assert ulp.max() <= 8, int(ulp.max())
+            assert ulp.max() == 0, (int((ulp > 0).sum()), int(ulp.max()))
 
 
 def test_spmv_hot_first_columns_keep_every_bit(monkeypatch):

@@ -101,6 +101,77 @@ def test_bin_roundtrip(tmp_path):
     assert g2.symmetric and g2.has_reverse_graph()
 
 
+@pytest.mark.parametrize("offset_bytes", [4, 8])
+def test_sg_roundtrip(tmp_path, offset_bytes):
+    """Serialized graphs (include/reader.h:259-316): bool directed, SGOffset num_edges, num_vertices, offsets, neighs and,
+    when directed, the inverse CSR.  SGOffset is 4 bytes in the reference (include/graph.h:77-79), 8 in upstream GAP files;
+    the reader tells them apart by the file size."""
+    g = gb.Graph.generate("g", 10, 16)
+    p = str(tmp_path / "k10.sg")
+    g.write_sg(p, offset_bytes)
+    raw = open(p, "rb").read()
+    assert len(raw) == 1 + 2 * offset_bytes + (g.m + 1) * offset_bytes + g.nnz * 4 and raw[0] == 0
+    hdr = np.frombuffer(raw[1:1 + 2 * offset_bytes], dtype=np.int32 if offset_bytes == 4 else np.int64)
+    assert [int(x) for x in hdr] == [g.nnz, g.m]              # edges first, then vertices (reader.h:291-292)
+    for args in ((p, "sg"), (p[:-3], "sg"), (p, "auto")):      # full path, prefix, suffix dispatch
+        g2 = gb.Graph(*args)
+        assert g2.symmetric and g2.has_reverse_graph() and (g2.m, g2.nnz) == (g.m, g.nnz)
+        assert np.array_equal(g2.out_rowptr(), g.out_rowptr()) and np.array_equal(g2.out_colidx(), g.out_colidx())
+    # a directed graph carries its inverse; without need_reverse only the forward CSR is read
+    csr, _ = load_case("test_pr_dir")
+    d = gb.Graph(os.path.join(GOLDEN, "test_pr"), "mtx", False, True)
+    pd = str(tmp_path / "dir.sg")
+    d.write_sg(pd, offset_bytes)
+    assert open(pd, "rb").read(1) == b"\x01"
+    d2 = gb.Graph(pd, "sg", False, True)
+    assert not d2.symmetric and d2.has_reverse_graph()
+    assert np.array_equal(d2.out_rowptr(), csr["out_rowptr"]) and np.array_equal(d2.out_colidx(), csr["out_colidx"])
+    assert np.array_equal(d2.in_rowptr(), csr["in_rowptr"]) and np.array_equal(d2.in_colidx(), csr["in_colidx"])
+    d3 = gb.Graph(pd, "sg", False, False)
+    assert not d3.has_reverse_graph() and np.array_equal(d3.out_colidx(), csr["out_colidx"])
+    with pytest.raises(gb.GdnError):                           # a directed graph without its reverse CSR cannot be serialized
+        d3.write_sg(str(tmp_path / "x.sg"), offset_bytes)
+
+
+def test_sg_reader_rejects_damaged_files(tmp_path):
+    g = gb.Graph.generate("u", 8, 8)
+    p = str(tmp_path / "u8.sg")
+    g.write_sg(p)
+    raw = bytearray(open(p, "rb").read())
+    h = C.c_void_p()
+
+    def rc_of(data):
+        q = str(tmp_path / "bad.sg")
+        open(q, "wb").write(bytes(data))
+        return _lib.lib.gdn_read_graph(q.encode(), b"sg", 0, 0, C.byref(h))
+
+    assert rc_of(raw) == _lib.GDN_OK
+    _lib.lib.gdn_host_graph_free(h)
+    assert rc_of(raw[:-4]) == _lib.GDN_ERR_GRAPH                # truncated: no offset width fits the size
+    assert rc_of(raw[:5]) == _lib.GDN_ERR_GRAPH
+    assert rc_of(b"\x02" + raw[1:]) == _lib.GDN_ERR_GRAPH       # `directed` is a bool
+    bad = bytearray(raw); bad[-4:] = np.int32(g.m).tobytes()   # a neighbour id out of range
+    assert rc_of(bad) == _lib.GDN_ERR_GRAPH
+    bad = bytearray(raw); bad[9 + 4:9 + 8] = np.int32(g.nnz + 1).tobytes()   # offsets[1] past the end
+    assert rc_of(bad) == _lib.GDN_ERR_GRAPH
+    assert _lib.lib.gdn_read_graph(str(tmp_path / "none.sg").encode(), b"sg", 0, 0, C.byref(h)) == _lib.GDN_ERR_IO
+
+
+def test_sg_writer_is_read_by_the_reference_reader(tmp_path):
+    """Our .sg through the reference's OWN Reader::ReadSerializedGraph (oracle/_ref/ref_gen -S, built from
+    include/reader.h where it lies), dumped back in the reference's binary triple: the same CSR."""
+    import subprocess
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_gen")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ref_gen not built")
+    g = gb.Graph.generate("g", 12, 16)
+    g.write_sg(str(tmp_path / "k12.sg"))
+    r = subprocess.run([exe, "-S", str(tmp_path / "k12.sg"), "-o", str(tmp_path / "back")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    h = gb.Graph(str(tmp_path / "back"), "bin", True, False)
+    assert np.array_equal(h.out_rowptr(), g.out_rowptr()) and np.array_equal(h.out_colidx(), g.out_colidx())
+
+
 def test_gen1_readers_three_encodings():
     """datasets/4.{mtx,gr} encode the same graph; .graph lists each edge once."""
     a = gb.Graph.from_file(os.path.join(GOLDEN, "4.mtx"), symmetrize=True)

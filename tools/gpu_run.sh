@@ -9,7 +9,7 @@ for st in "$@"; do
   echo "=== [$TAG] $st"
   case $name in
     info) (nproc; free -g | head -2; nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv; nvidia-smi topo -m 2>/dev/null | head -12) > $O/${TAG}_info.txt 2>&1; cat $O/${TAG}_info.txt ;;
-    pytest) timeout 2400 python -m pytest tests -m gpu -x -q ${arg:+-k "$arg"} > $O/${TAG}_pytest.log 2>&1; echo "rc=$?"; tail -5 $O/${TAG}_pytest.log ;;
+    pytest) timeout 2400 python -m pytest tests -m gpu -q ${arg:+-k "$arg"} > $O/${TAG}_pytest.log 2>&1; echo "rc=$?"; tail -5 $O/${TAG}_pytest.log ;;
     multi) timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node=$arg --master-addr 127.0.0.1 --master-port 29517 tests/_multi_worker.py > $O/${TAG}_multi$arg.log 2>&1; echo "rc=$?"; grep -E "\[multi\]|Error|error" $O/${TAG}_multi$arg.log | tail -40 ;;
     smoke) timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $O/${TAG}_smoke.log 2>&1; echo "rc=$?"; tail -3 $O/${TAG}_smoke.log ;;
     bench) timeout 1500 python bench.py $arg > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; echo "rc=$?"; tail -4 $O/${TAG}_bench.err; head -c 1500 $O/${TAG}_bench.json; echo ;;
