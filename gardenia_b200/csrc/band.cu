@@ -172,6 +172,101 @@ band_fill(const int4 *__restrict__ sell, const uint32_t *__restrict__ slice_ptr,
   }
 }
 
+// ------------------------------------------------------------------ build pass 3: spread a row's ids over the banks
+// pr_band_kernel reads tab[id] for 32 ROWS at a time (lane = row, same position in every row): 32 random words of a
+// 192 KB table fall into the 32 banks like balls into bins -- 3.2 wavefronts per LDS measured (ncu: 113 M of 164 M
+// shared wavefronts are bank conflicts, profiles/r2_ncu_pr.txt).  The order of a row's ids INSIDE an item is free (the
+// item's partial is a band-local sum already), so one warp per item re-orders every row (lane) in chunks of 64 positions:
+// at position p lane l prefers bank (l + p) mod 32 -- a Latin square, conflict-free by construction -- and takes the
+// nearest bank it still has an id in; lanes that collide are settled lowest-lane-first and the losers look for a bank
+// nobody holds (a few match_any rounds).  Sums change by a re-ordering of <= 512 fp32 addends per (row, band, item).
+// stats[0], stats[1] = bank-conflict degree (max lanes on one bank) summed over all positions before / after.
+constexpr int kSpreadPos = 64;                               // positions (ids per row) per chunk
+__global__ void __launch_bounds__(256)
+band_spread(uint16_t *__restrict__ bsell16, const uint32_t *__restrict__ item_ptr, int32_t n_items, unsigned long long *stats) {
+  __shared__ uint16_t s_ids[8][kSpreadPos * 32];             // [position][lane]: the chunk's ids of a lane, sorted by bank
+  __shared__ uint8_t s_ptr[8][32 * 32], s_rem[8][32 * 32];   // [bank][lane]: next unused position of the bank / ids left in it
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  uint16_t *ids = s_ids[wib];
+  uint8_t *ptr = s_ptr[wib], *rem = s_rem[wib];
+  unsigned long long before = 0, after = 0;                  // (warp-uniform)
+  auto degree = [&](uint32_t bank, bool real) -> uint32_t {  // most lanes on one bank at this position
+    const unsigned peers = __match_any_sync(kFull, real ? bank : 64u + lane);
+    return __reduce_max_sync(kFull, real ? (uint32_t)__popc(peers) : 0u);
+  };
+  for (int32_t it = (blockIdx.x * 256 + threadIdx.x) >> 5; it < n_items; it += (gridDim.x * 256) >> 5) {
+    const uint32_t u0 = item_ptr[it], ng = (item_ptr[it + 1] - u0) >> 5;           // index groups (8 ids) per lane
+    for (uint32_t g0 = 0; g0 < ng; g0 += kSpreadPos / 8) {
+      const uint32_t cg = min((uint32_t)(kSpreadPos / 8), ng - g0), np = cg * 8;
+      uint16_t *base = bsell16 + ((size_t)u0 + (size_t)g0 * 32 + lane) * 8;        // group g of this lane: base + g * 256
+      // counting sort of the lane's ids by bank (everything of a lane lives in its own shared-memory column)
+      for (int b = 0; b < 32; b++) rem[b * 32 + lane] = 0;
+      for (uint32_t g = 0; g < cg; g++) {
+        const uint4 q = *reinterpret_cast<const uint4 *>(base + (size_t)g * 256);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const uint32_t id = (w[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+          const bool real = id != kBandPadId;
+          before += degree(id & 31u, real);
+          if (real) rem[(id & 31u) * 32 + lane]++;
+        }
+      }
+      uint32_t avail = 0, left = 0;
+      for (int b = 0; b < 32; b++) {
+        const uint32_t c = rem[b * 32 + lane];
+        if (c) avail |= 1u << b;
+        ptr[b * 32 + lane] = (uint8_t)left;
+        left += c;
+      }
+      for (uint32_t g = 0; g < cg; g++) {
+        const uint4 q = *reinterpret_cast<const uint4 *>(base + (size_t)g * 256);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const uint32_t id = (w[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+          if (id != kBandPadId) ids[(uint32_t)(ptr[(id & 31u) * 32 + lane]++) * 32 + lane] = (uint16_t)id;
+        }
+      }
+      for (int b = 0; b < 32; b++) ptr[b * 32 + lane] -= rem[b * 32 + lane];      // back to the start of every bank
+      uint32_t out[4] = {0, 0, 0, 0};
+      for (uint32_t p = 0; p < np; p++) {
+        const bool real = left > 0;
+        const uint32_t pref = (lane + p) & 31u;
+        auto nearest = [&](uint32_t m) -> uint32_t {         // first bank of mask m at or after pref, cyclically
+          const uint32_t r = __funnelshift_r(m, m, pref);
+          return ((uint32_t)(__ffs(r) - 1) + pref) & 31u;
+        };
+        uint32_t want = real ? nearest(avail) : 0u;
+        bool fixed = !real;
+        for (int round = 0; round < 4; round++) {
+          const unsigned fixed_mask = __ballot_sync(kFull, fixed && real);
+          const unsigned peers = __match_any_sync(kFull, real ? want : 64u + lane);
+          if (real && !fixed && !(peers & fixed_mask) && lane == __ffs(peers) - 1) fixed = true;    // lowest lane of a free bank wins
+          const uint32_t held = __reduce_or_sync(kFull, fixed && real ? 1u << want : 0u);
+          if (__all_sync(kFull, fixed)) break;
+          if (!fixed) { const uint32_t alt = avail & ~held; if (alt) want = nearest(alt); }
+        }
+        after += degree(want, real);
+        uint32_t id = kBandPadId;
+        if (real) {
+          const uint32_t pos = ptr[want * 32 + lane];
+          id = ids[pos * 32 + lane];
+          ptr[want * 32 + lane] = (uint8_t)(pos + 1);
+          if (--rem[want * 32 + lane] == 0) avail &= ~(1u << want);
+          left--;
+        }
+        out[(p & 7) >> 1] |= id << ((p & 1) * 16);
+        if ((p & 7) == 7) {
+          *reinterpret_cast<uint4 *>(base + (size_t)(p >> 3) * 256) = make_uint4(out[0], out[1], out[2], out[3]);
+          out[0] = out[1] = out[2] = out[3] = 0;
+        }
+      }
+    }
+  }
+  if (lane == 0 && stats) { atomicAdd(stats, before); atomicAdd(stats + 1, after); }
+}
+
 // ------------------------------------------------------------------ the iteration: band partial sums
 struct BandArgs {
   const uint4 *bsell;
@@ -186,7 +281,12 @@ struct BandArgs {
   unsigned long long *acc_fix; // ... whose fixed-point accumulator takes the partial
   double fix_scale;            // 2^e of the accumulators for this solve
   const int32_t *done;
+  int32_t pf_groups;           // index groups requested into L2 ahead of the loads of a warp (0 = no prefetch)
 };
+
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 
 __device__ __forceinline__ uint4 ld_stream_u4(const uint4 *p, uint64_t pol) {
   uint4 r;
@@ -230,11 +330,17 @@ pr_band_kernel(BandArgs a) {
     int32_t jrow = a.irow[(size_t)i0 * 32 + lane], jrow1 = -1, jrow2 = -1;
     if (i0 + 1 < i1) jrow1 = a.irow[(size_t)(i0 + 1) * 32 + lane];
     if (i0 + 2 < i1) jrow2 = a.irow[(size_t)(i0 + 2) * 32 + lane];
+    // the warp's run is one contiguous piece of the band's array: ask L2 for it a few KB ahead of the register loads (one
+    // bulk prefetch per 8 index groups = 4 KB, issued by lane 0), so that the PD loads in flight per lane wait for L2,
+    // not for HBM -- the kernel was latency-bound on exactly these loads (ncu: long scoreboard, DRAM at 39 %)
+    const uint32_t pf = (uint32_t)a.pf_groups;
+    if (pf && lane == 0) bulk_prefetch_l2(p - lane, min(pf, nrows) * 512u);
     uint4 q[PD];
 #pragma unroll
     for (int d = 0; d < PD; d++) q[d] = (uint32_t)d < nrows ? ld_stream_u4(p + 32 * d, pol) : padq;
     float acc = 0.f;
     for (uint32_t r = 0; r < nrows; r += PD) {
+      if (pf && (r & 7u) == 0 && lane == 0 && r + pf < nrows) bulk_prefetch_l2(p - lane + (size_t)(r + pf) * 32, min(8u, nrows - (r + pf)) * 512u);
 #pragma unroll
       for (int d = 0; d < PD; d++) {
         if (r + d < nrows) {                               // warp-uniform
@@ -771,6 +877,18 @@ static int band_build_body(gdn_graph *g) {
   else
     band_fill<false><<<grid, 128, smem2, st>>>(L.sell, L.slice_ptr, nb, mp, d_rank, n_rows, t_bslice_ptr.as<uint32_t>(), t_bslice_first.as<int32_t>(),
                                                (uint16_t *)bd.bsell, bd.sell, bd.slice_ptr);
+  double spread[2] = {0, 0};
+  if (!seg && env_int("GDN_PR_BAND_SPREAD", 1)) {   // pass 3: every row's ids re-ordered inside its items against bank conflicts
+    unsigned long long *d_stats = nullptr, h_stats[2] = {0, 0};
+    GDN_CUDA(cudaMalloc((void **)&d_stats, sizeof(h_stats)));
+    GDN_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(h_stats), st));
+    band_spread<<<sm * 8, 256, 0, st>>>((uint16_t *)bd.bsell, bd.item_ptr, n_items, d_stats);
+    GDN_CUDA(cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, st));
+    GDN_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_stats);
+    const double positions = (double)units / 4.0;            // warp-wide table reads of pr_band_kernel: 8 per 32 units
+    spread[0] = (double)h_stats[0] / std::max(positions, 1.0); spread[1] = (double)h_stats[1] / std::max(positions, 1.0);
+  }
   GDN_CUDA(cudaStreamSynchronize(st));
   GDN_CUDA(cudaGetLastError());
   GDN_CUDA(cudaFuncSetAttribute(pr_band_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * kBandTab)));
@@ -778,10 +896,10 @@ static int band_build_body(gdn_graph *g) {
   bd.built = true;
   if (getenv("GDN_TRACE"))
     fprintf(stderr, "[gdn] %s layout: B=%d band=%d cmin=%d rows=%lld  moved=%llu ids (%.1f %% of nnz) in %llu pairs, %d items, "
-                    "%llu padded ids (x%.2f), %d jobs; main array %llu -> %llu groups\n",
+                    "%llu padded ids (x%.2f), %d jobs; main array %llu -> %llu groups; lanes per bank and table read %.2f -> %.2f\n",
             seg ? "segmented" : "band", B, band, cmin, (long long)n_rows, (unsigned long long)moved, 100.0 * (double)moved / (double)std::max<uint64_t>(g->in.nnz, 1),
             (unsigned long long)pairs, n_items, (unsigned long long)(units * W), (double)(units * W) / (double)std::max<uint64_t>(moved, 1),
-            bd.n_jobs, (unsigned long long)L.n_groups, (unsigned long long)tot2);
+            bd.n_jobs, (unsigned long long)L.n_groups, (unsigned long long)tot2, spread[0], spread[1]);
   trace("band_build: done");
   return GDN_OK;
 }
@@ -847,6 +965,7 @@ int band_launch(gdn_graph *g, const SellArgs &sa, double fix_scale, cudaStream_t
   const BandLayout &bd = g->pull.band;
   BandArgs a;
   a.bsell = bd.bsell; a.item_ptr = bd.item_ptr; a.job = bd.job; a.job_first = bd.job_first; a.wrun = bd.wrun;
+  a.pf_groups = env_int("GDN_PR_BAND_PF", 16);
   a.band_start = bd.band_start; a.band_len = bd.band_len; a.contrib_in = sa.contrib_in; a.done = sa.done;
   a.irow = bd.irow; a.acc_fix = (unsigned long long *)bd.acc_fix; a.fix_scale = fix_scale;
   if (bd.seg) {

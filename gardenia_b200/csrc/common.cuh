@@ -106,6 +106,10 @@ struct DevCsr {
   int32_t *chunk_row = nullptr;    // int32[n_chunks+1]
   int32_t n_heavy_rows = 0;
   int32_t n_heavy_segs = 0;
+  // the heavy rows of at most kSpmvExactLen entries come first in the lists below: SpMV sums those by segments and the
+  // longer ones in the reference's order (gather.cu, SpmvExact); the PageRank fallback walks the whole list
+  int32_t n_heavy_rows_lt = 0;
+  int32_t n_heavy_segs_lt = 0;
   int32_t *heavy_row = nullptr;    // int32[n_heavy_rows]      local row id
   int32_t *heavy_first = nullptr;  // int32[n_heavy_rows+1]    first segment index of that row
   int2 *heavy_seg = nullptr;       // int2[n_heavy_segs]       {local row, segment number within the row}
@@ -203,6 +207,17 @@ struct gdn_graph {
   int n_err_partial = 0;
   gdn::PullLayout pull;
   float *scores_sorted = nullptr;    // PR scores in sorted row order during a solve
+  // SpMV rows longer than kSpmvExactLen: products row-major in 512-entry blocks + the per-block tables of ordered_core.cuh
+  struct SpmvExact {
+    bool tried = false;
+    int32_t n_rows = 0;
+    uint32_t n_blocks = 0;
+    uint32_t *blk_base = nullptr;    // [n_rows + 1] first block of exact row i (= heavy_row[n_heavy_rows_lt + i])
+    float4 *vals = nullptr;
+    double *S = nullptr;
+    uint32_t *mx = nullptr, *Q = nullptr;
+    uint8_t *plan = nullptr;
+  } spmv_exact;
   // SpMV on skewed graphs: hot-first column ids + x scattered into that order (gather.cu spmv_hot_columns)
   bool spmv_tried = false;
   int32_t *spmv_col = nullptr;

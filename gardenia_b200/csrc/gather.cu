@@ -21,7 +21,9 @@
 //            per row by finalize_heavy in a fixed order.
 // No atomics, deterministic run to run.
 #include "common.cuh"
+#include "ordered_core.cuh"
 #include <chrono>
+#include <vector>
 #include <cstdlib>
 
 namespace gdn {
@@ -30,6 +32,9 @@ constexpr int kChunk = 512;            // non-zeros per light block (target)
 constexpr int kCap = 2 * kChunk + 8;   // staged products per warp
 constexpr int kSeg = 1024;             // non-zeros per heavy-row segment
 constexpr int kWarps = 8;              // warps per CTA
+// SpMV rows longer than this are summed in the reference's order (SpmvExact below); GDN_SPMV_EXACT_LEN overrides it when a
+// graph is created (0 = never)
+constexpr int64_t kSpmvExactLen = 32768;
 constexpr int kThreads = kWarps * 32;
 
 enum { kModeSpmv = 0, kModePr = 1 };
@@ -47,6 +52,8 @@ struct GatherArgs {
   int64_t rows;
   // SpMV:  y[r] += sum Ax[j] * x[col[j]]
   const float *Ax;
+  const int32_t *col;     // (spmv_pipe: the column array, for its L2 prefetches)
+  int pf;                 // spmv_pipe: prefetch the next items' col / Ax into L2 (GDN_SPMV_PF, default on)
   uint64_t nnz;           // bound for guarded Ax tail loads
   const float *vec;       // x (SpMV) or contrib_in (PR), GLOBAL length m
   float *y;               // SpMV y (local rows)
@@ -236,6 +243,15 @@ struct SpGen {
   }
   __device__ __forceinline__ void loadA(int64_t it) {
     itA = it;
+    // light block `it` is (about) entries [512 it, 512 it + 512): two items before the warp streams them, ask L2 for
+    // that piece of col and Ax (2 KB each), so the stream loads of the trip pipeline wait for L2, not for HBM
+    if (a.pf && it < a.n_chunks && (threadIdx.x & 31) == 0) {
+      const uint64_t e0 = (uint64_t)it * kChunk;
+      if (e0 + kChunk <= a.nnz) {
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.col + e0), "r"(kChunk * 4) : "memory");
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.Ax + e0), "r"(kChunk * 4) : "memory");
+      }
+    }
     if (it < a.n_chunks) { xA0 = __ldcs(a.chunk_row + it); xA1 = __ldcs(a.chunk_row + it + 1); }
     else if (it < n_items) { const int2 hs = a.heavy_seg[it - a.n_chunks]; xA0 = hs.x; xA1 = hs.y; }
   }
@@ -422,18 +438,19 @@ __global__ void build_chunk_rows(const OffT *__restrict__ rowptr, int64_t rows, 
   chunk_row[k] = (int32_t)lo;
 }
 
-// counters: one 64-bit word, high 32 = heavy rows, low 32 = heavy segments, so
-// that a row's slot and its first segment are allocated by ONE atomic.
+// counters: one 64-bit word per class, high 32 = heavy rows, low 32 = heavy segments, so that a row's slot and its first
+// segment are allocated by ONE atomic.  Class 1 = rows longer than xlen (listed after all rows of class 0).
 template <typename OffT, bool FILL>
-__global__ void scan_heavy(const OffT *__restrict__ rowptr, int64_t rows, unsigned long long *counter,
-                           int32_t *heavy_row, int32_t *heavy_first, int2 *heavy_seg) {
+__global__ void scan_heavy(const OffT *__restrict__ rowptr, int64_t rows, unsigned long long *counter, OffT xlen, int32_t rows_lt,
+                           int32_t segs_lt, int32_t *heavy_row, int32_t *heavy_first, int2 *heavy_seg) {
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
     const OffT len = rowptr[r + 1] - rowptr[r];
     if (len > (OffT)kChunk) {
+      const int cls = len > xlen ? 1 : 0;
       const unsigned nseg = (unsigned)((len + kSeg - 1) / kSeg);
-      const unsigned long long old = atomicAdd(counter, (1ull << 32) | nseg);
+      const unsigned long long old = atomicAdd(counter + cls, (1ull << 32) | nseg);
       if (FILL) {
-        const int32_t slot = (int32_t)(old >> 32), first = (int32_t)(old & 0xffffffffu);
+        const int32_t slot = (int32_t)(old >> 32) + (cls ? rows_lt : 0), first = (int32_t)(old & 0xffffffffu) + (cls ? segs_lt : 0);
         heavy_row[slot] = (int32_t)r;
         heavy_first[slot] = first;
         for (unsigned s = 0; s < nseg; s++) heavy_seg[first + s] = make_int2((int)r, (int)s);
@@ -458,22 +475,27 @@ static int build_schedule_t(gdn_graph *g, DevCsr &c) {
   const OffT *rp = (const OffT *)c.rowptr;
   build_chunk_rows<OffT><<<(unsigned)((nch + 1 + 255) / 256), 256, 0, st>>>(rp, c.rows, c.n_chunks, c.chunk_row);
   unsigned long long *counter;
-  GDN_CUDA(cudaMalloc((void **)&counter, 8));
-  GDN_CUDA(cudaMemsetAsync(counter, 0, 8, st));
+  GDN_CUDA(cudaMalloc((void **)&counter, 16));
+  GDN_CUDA(cudaMemsetAsync(counter, 0, 16, st));
   const int grid = (int)std::min<int64_t>((c.rows + 255) / 256 + 1, 148 * 16);
-  scan_heavy<OffT, false><<<grid, 256, 0, st>>>(rp, c.rows, counter, nullptr, nullptr, nullptr);
-  unsigned long long h = 0;
-  GDN_CUDA(cudaMemcpyAsync(&h, counter, 8, cudaMemcpyDeviceToHost, st));
+  const char *xe = getenv("GDN_SPMV_EXACT_LEN");
+  const int64_t xl = xe ? atoll(xe) : kSpmvExactLen;
+  const OffT xlen = xl <= 0 ? (OffT)~(OffT)0 : (OffT)std::max<int64_t>(xl, kChunk);
+  scan_heavy<OffT, false><<<grid, 256, 0, st>>>(rp, c.rows, counter, xlen, 0, 0, nullptr, nullptr, nullptr);
+  unsigned long long h[2] = {0, 0};
+  GDN_CUDA(cudaMemcpyAsync(h, counter, 16, cudaMemcpyDeviceToHost, st));
   GDN_CUDA(cudaStreamSynchronize(st));
-  c.n_heavy_rows = (int32_t)(h >> 32);
-  c.n_heavy_segs = (int32_t)(h & 0xffffffffu);
+  c.n_heavy_rows_lt = (int32_t)(h[0] >> 32);
+  c.n_heavy_segs_lt = (int32_t)(h[0] & 0xffffffffu);
+  c.n_heavy_rows = c.n_heavy_rows_lt + (int32_t)(h[1] >> 32);
+  c.n_heavy_segs = c.n_heavy_segs_lt + (int32_t)(h[1] & 0xffffffffu);
   if (c.n_heavy_rows > 0) {
     GDN_CHECK(dev_alloc(g, (void **)&c.heavy_row, sizeof(int32_t) * c.n_heavy_rows));
     GDN_CHECK(dev_alloc(g, (void **)&c.heavy_first, sizeof(int32_t) * c.n_heavy_rows));
     GDN_CHECK(dev_alloc(g, (void **)&c.heavy_seg, sizeof(int2) * c.n_heavy_segs));
     GDN_CHECK(dev_alloc(g, (void **)&c.heavy_partial, sizeof(float) * c.n_heavy_segs));
-    GDN_CUDA(cudaMemsetAsync(counter, 0, 8, st));
-    scan_heavy<OffT, true><<<grid, 256, 0, st>>>(rp, c.rows, counter, c.heavy_row, c.heavy_first, c.heavy_seg);
+    GDN_CUDA(cudaMemsetAsync(counter, 0, 16, st));
+    scan_heavy<OffT, true><<<grid, 256, 0, st>>>(rp, c.rows, counter, xlen, c.n_heavy_rows_lt, c.n_heavy_segs_lt, c.heavy_row, c.heavy_first, c.heavy_seg);
   }
   GDN_CUDA(cudaStreamSynchronize(st));
   GDN_CUDA(cudaFree(counter));
@@ -548,12 +570,125 @@ static int spmv_hot_columns(gdn_graph *g) {
   return GDN_OK;
 }
 
+// ---- rows longer than kSpmvExactLen: summed in the reference's order ------------------------------------------------
+// A sequential fp32 sum (src/spmv/omp_base.cc:27-31) of n addends drifts from the exact sum by an amount that grows with n
+// (measured against spmv_omp_base: 1.2e-5 relative on the longest row of Kronecker scale 22, 1.4e-4 at scale 26, where
+// segment partials + a tree stay within 1e-7) -- so to meet the reference within 1e-5 per row the long rows have to be
+// ROUNDED like the reference, i.e. summed in its order.  That is the ordered sum of ordered_core.cuh: products of a row
+// written row-major in 512-entry blocks (pass 1, the only pass that touches the matrix), per-block plans and integer sums,
+// and one warp per row walking its blocks in order from y[row].  Bit-identical to the reference for these rows.
+template <typename OffT>
+__global__ void __launch_bounds__(256, 4)
+spmv_exact_gather(const OffT *__restrict__ rowptr, const int32_t *__restrict__ col, const float *__restrict__ Ax,
+                  const float *__restrict__ vec, const int32_t *__restrict__ xrow, ExactArgs x) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t pol_x = l2_policy_evict_last();
+  const uint32_t warp = (blockIdx.x * 256 + threadIdx.x) >> 5, nwarps = (gridDim.x * 256) >> 5;
+  for (uint32_t k = warp; k < (uint32_t)x.n_blocks_total; k += nwarps) {
+    int lo = 0, hi = x.n_exact;                                            // last row i with blk_base[i] <= k
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (x.blk_base[mid] <= k) lo = mid; else hi = mid; }
+    const int32_t row = xrow[lo];
+    const OffT rb = rowptr[row] + (OffT)(k - x.blk_base[lo]) * 512u, re = rowptr[row + 1];
+    // lane l owns entries 16 l .. 16 l + 15 of the block (the layout ordered_block wants): 64 contiguous bytes per lane
+    int32_t c[16];
+    float w[16], v[16];
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      const OffT j = rb + (OffT)(lane * 16 + u);
+      c[u] = j < re ? __ldg(col + j) : -1;
+      w[u] = j < re ? __ldg(Ax + j) : 0.f;
+    }
+    double s = 0.0;
+    uint32_t mbits = 0;
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      v[u] = c[u] >= 0 ? __fmul_rn(ld_gather_f32(vec + c[u], pol_x), w[u]) : 0.f;   // x[j] * Ax[jj], rounded like the reference's
+      s += (double)v[u];
+      mbits = max(mbits, __float_as_uint(v[u]));
+    }
+    float4 *dst = x.vals + (size_t)k * kOrdBlockGroups + lane * 4;
+#pragma unroll
+    for (int i = 0; i < 4; i++) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    s = warp_sum(s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mbits = max(mbits, __shfl_xor_sync(kFull, mbits, o));
+    if (lane == 0) { x.S[k] = s; x.mx[k] = mbits; }
+  }
+}
+
+__global__ void __launch_bounds__(256, 4)
+spmv_exact_plan(const int32_t *__restrict__ xrow, const float *__restrict__ y, ExactArgs x) {
+  const int lane = threadIdx.x & 31;
+  const int i = (blockIdx.x * 256 + threadIdx.x) >> 5;
+  if (i >= x.n_exact) return;
+  exact_plan_row(x, x.blk_base[i], x.blk_base[i + 1] - x.blk_base[i], (double)y[xrow[i]], lane);
+}
+
+__global__ void __launch_bounds__(256, 4)
+spmv_exact_combine(const int32_t *__restrict__ xrow, float *__restrict__ y, ExactArgs x) {
+  __shared__ float s_stage[8][512];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int i = (blockIdx.x * 256 + threadIdx.x) >> 5;
+  if (i >= x.n_exact) return;
+  const int32_t row = xrow[i];
+  const uint32_t ab = exact_combine_row(x, x.blk_base[i], x.blk_base[i + 1] - x.blk_base[i], __float_as_uint(y[row]), lane, s_stage[wib]);
+  if (lane == 0) y[row] = __uint_as_float(ab);
+}
+
+template <typename OffT>
+__global__ void spmv_exact_blocks(const OffT *__restrict__ rowptr, const int32_t *__restrict__ xrow, int32_t n, uint32_t *__restrict__ nb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) nb[i] = (uint32_t)((rowptr[xrow[i] + 1] - rowptr[xrow[i]] + 511) / 512);
+}
+
+// Tables of the exact rows, once per graph.  An optimisation for parity only: if the memory is not there the long rows
+// stay with the segment sums (n_heavy_*_lt are reset to the full list).
+template <typename OffT>
+static int spmv_exact_setup(gdn_graph *g) {
+  auto &X = g->spmv_exact;
+  DevCsr &c = g->in;
+  if (X.tried) return GDN_OK;
+  X.tried = true;
+  const int32_t n = c.n_heavy_rows - c.n_heavy_rows_lt;
+  if (n <= 0) return GDN_OK;
+  cudaStream_t st = lib().stream;
+  const int32_t *xrow = c.heavy_row + c.n_heavy_rows_lt;
+  auto give_up = [&]() {
+    cudaGetLastError();
+    cudaFree(X.blk_base); cudaFree(X.vals); cudaFree(X.S); cudaFree(X.mx); cudaFree(X.Q); cudaFree(X.plan);
+    X = gdn_graph::SpmvExact();
+    X.tried = true;
+    c.n_heavy_rows_lt = c.n_heavy_rows; c.n_heavy_segs_lt = c.n_heavy_segs;
+    return GDN_OK;
+  };
+  if (cudaMalloc((void **)&X.blk_base, sizeof(uint32_t) * ((size_t)n + 1)) != cudaSuccess) return give_up();
+  spmv_exact_blocks<OffT><<<(n + 255) / 256, 256, 0, st>>>((const OffT *)c.rowptr, xrow, n, X.blk_base);
+  std::vector<uint32_t> nb((size_t)n + 1);
+  GDN_CUDA(cudaMemcpyAsync(nb.data(), X.blk_base, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  GDN_CUDA(cudaStreamSynchronize(st));
+  uint64_t tot = 0;
+  for (int32_t i = 0; i < n; i++) { const uint32_t v = nb[i]; nb[i] = (uint32_t)tot; tot += v; }
+  nb[n] = (uint32_t)tot;
+  if (tot >= 0x7fffffffull) return give_up();
+  GDN_CUDA(cudaMemcpyAsync(X.blk_base, nb.data(), sizeof(uint32_t) * ((size_t)n + 1), cudaMemcpyHostToDevice, st));
+  GDN_CUDA(cudaStreamSynchronize(st));
+  if (cudaMalloc((void **)&X.vals, sizeof(float) * 512 * (size_t)tot) != cudaSuccess || cudaMalloc((void **)&X.S, sizeof(double) * (size_t)tot) != cudaSuccess ||
+      cudaMalloc((void **)&X.mx, sizeof(uint32_t) * (size_t)tot) != cudaSuccess || cudaMalloc((void **)&X.Q, sizeof(uint32_t) * (size_t)tot) != cudaSuccess ||
+      cudaMalloc((void **)&X.plan, (size_t)tot + 16) != cudaSuccess)
+    return give_up();
+  X.n_rows = n; X.n_blocks = (uint32_t)tot;
+  g->device_bytes += (sizeof(float) * 512 + 17) * (size_t)tot;
+  return GDN_OK;
+}
+
 template <typename OffT>
 static int spmv_t(gdn_graph *g, const float *d_Ax, const float *d_x, float *d_y, gdn_stats *st) {
   const DevCsr &c = g->in;
   GDN_CHECK(spmv_hot_columns(g));
+  GDN_CHECK(spmv_exact_setup<OffT>(g));
   GatherArgs a = {};
   fill_sched(c, a);
+  a.n_heavy_rows = c.n_heavy_rows_lt; a.n_heavy_segs = c.n_heavy_segs_lt;      // the longer rows: exact passes below
   a.Ax = d_Ax; a.vec = d_x; a.y = d_y;
   cudaStream_t s = lib().stream;
   const OffT *rp = (const OffT *)c.rowptr;
@@ -574,13 +709,28 @@ static int spmv_t(gdn_graph *g, const float *d_Ax, const float *d_x, float *d_y,
   constexpr int kPipeThreads = 384, kPipeCtas = 2;
   const size_t smem = sizeof(float) * (size_t)kCap * (kPipeThreads / 32);
   GDN_CUDA(cudaFuncSetAttribute(spmv_pipe<OffT, kPipeThreads, kPipeCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  a.col = col;
+  { const char *e = getenv("GDN_SPMV_PF"); a.pf = e ? atoi(e) : 1; }
   kev_begin();
   spmv_pipe<OffT, kPipeThreads, kPipeCtas><<<lib().sm_count * kPipeCtas, kPipeThreads, smem, s>>>(rp, col, a);
   kev_end();
   launches++;
-  if (c.n_heavy_rows > 0) {
+  if (a.n_heavy_rows > 0) {
     finalize_heavy<OffT, kModeSpmv><<<heavy_grid(c), kThreads, 0, s>>>(rp, a);
     launches++;
+  }
+  if (g->spmv_exact.n_rows > 0) {
+    const auto &X = g->spmv_exact;
+    ExactArgs xa;
+    xa.n_exact = X.n_rows; xa.n_blocks_total = (int32_t)X.n_blocks; xa.blk_base = X.blk_base; xa.vals = X.vals;
+    xa.S = X.S; xa.mx = X.mx; xa.plan = X.plan; xa.Q = X.Q;
+    const int32_t *xrow = c.heavy_row + c.n_heavy_rows_lt;
+    const int sm = lib().sm_count, rgrid = (X.n_rows + 7) / 8;
+    spmv_exact_gather<OffT><<<sm * 8, 256, 0, s>>>(rp, col, d_Ax, a.vec, xrow, xa);
+    spmv_exact_plan<<<rgrid, 256, 0, s>>>(xrow, d_y, xa);
+    exact_qsum<<<sm * 8, 256, 0, s>>>(nullptr, xa);
+    spmv_exact_combine<<<rgrid, 256, 0, s>>>(xrow, d_y, xa);
+    launches += 4;
   }
   GDN_CUDA(cudaEventRecord(lib().ev1, s));
   GDN_CUDA(cudaStreamSynchronize(s));

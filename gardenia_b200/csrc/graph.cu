@@ -411,6 +411,7 @@ int gdn_graph_destroy(gdn_graph *g) {
   else { free_csr(g->out); free_csr(g->in); }
   cudaFree(g->contrib[0]); cudaFree(g->contrib[1]); cudaFree(g->out_degree); cudaFree(g->err_partial);
   cudaFree(g->spmv_col); cudaFree(g->spmv_x);
+  { auto &x = g->spmv_exact; cudaFree(x.blk_base); cudaFree(x.vals); cudaFree(x.S); cudaFree(x.mx); cudaFree(x.Q); cudaFree(x.plan); }
   cudaFree(g->err_trace); cudaFree(g->pr_done); cudaFree(g->pr_work); cudaFree(g->abs_partial);
   cudaFree(g->visited); cudaFree(g->front); cudaFree(g->next); cudaFree(g->iso); cudaFree(g->queue[0]); cudaFree(g->queue[1]);
   cudaFree(g->heavy_queue); cudaFree(g->heavy_off); cudaFree(g->deg_class); cudaFree(g->col_bu); cudaFree(g->bu_head); cudaFree(g->bfs_reached);

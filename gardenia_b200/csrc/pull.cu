@@ -610,6 +610,11 @@ struct TripIter {
       if (g < g_end) {
         TripDesc d;
         const uint32_t left = (g_end - g) >> 5;
+        // a slice (or segment) is one contiguous piece of the index array: every 8 trips ask L2 for the 4 KB that lie
+        // pf_trips ahead, so that the index loads of the pipeline wait for L2 and not for HBM
+        if (a.pf_trips && lane == 0 && (((g_end - g) >> 5) & 7u) == 0 && left > (uint32_t)a.pf_trips)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.sell + g + ((size_t)a.pf_trips << 5)),
+                       "r"(min(8u, left - (uint32_t)a.pf_trips) * 512u) : "memory");
         d.g = g;
         d.n = left < (uint32_t)G ? (int32_t)left : G;
         g += (uint32_t)d.n << 5;
@@ -1199,6 +1204,7 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
   a.damp = damp; a.err_partial = g->err_partial; a.done = g->pr_done;
   a.strict_chain = L.exact ? 1 : 0;
   a.group_ch = L.group_ch; a.n_exact = L.n_exact; a.work_counter = g->pr_work; a.exact_vals = L.exact_vals;
+  { const char *e = getenv("GDN_PR_MAIN_PF"); a.pf_trips = e ? atoi(e) : 0; }
   a.P = L.P; a.inv_wc = L.Wc > 0 ? 1.0f / (float)L.Wc : 0.f;
   // the warm budget is shared by the ranks' slices (tier_id): every rank's hottest cold ids stay L2-resident
   a.warm = (int32_t)std::min<int64_t>(L.P > 1 ? L.H + std::max<int64_t>(warm_ids - L.H, 0) / L.P : warm_ids, 0x7fffffff);
@@ -1284,7 +1290,7 @@ int pr_run_sell(gdn_graph *g, float *d_scores, float damp, double eps, int max_i
       pr_exact_gather<<<sm * 8, 256, 0, s>>>(a, xa);
       probe(iter, "exact gather");
       pr_exact_plan<<<(L.n_exact * 32 + 7) / 8, 256, 0, s>>>(a, xa);
-      pr_exact_qsum<<<sm * 8, 256, 0, s>>>(a, xa);
+      exact_qsum<<<sm * 8, 256, 0, s>>>(a.done, xa);
       launches += 3;
       probe(iter, "exact plan + qsum");
     }

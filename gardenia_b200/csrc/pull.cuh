@@ -41,6 +41,7 @@ struct SellArgs {
   uint32_t group_ch;           // int4 groups per work item; slices wider than this are cut into segments (0xffffffff: never, exact order)
   int32_t n_exact;             // the first n_exact slices are exact slices: one item each, never cut, never banded
   int32_t *work_counter;       // batches of work items drawn so far by the warps of this launch
+  int32_t pf_trips;            // index groups of a slice requested into L2 ahead of the trip being cut (0 = none; GDN_PR_MAIN_PF)
   int32_t strict_chain;        // exact-order mode: exact slices by a true sequential chain (bit-exact) instead of the ordered-sum emulation
   const float4 *exact_vals;    // gathered values of the exact slices (pr_exact_gather), laid out like their index groups
   // banded layout (band.cu): sorted rows below n_band_rows (a multiple of 32) only deposit the sum over the columns left

@@ -1,6 +1,10 @@
 // csr_graph.cc -- see csr_graph.hpp.  Reader semantics follow the reference's
 // include/csr_graph.h:55-250 (cited inline); the algorithms are our own.
 #include "csr_graph.hpp"
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <omp.h>
 #include <cerrno>
 #include <vector>
@@ -102,6 +106,9 @@ void transpose_csr(int64_t m, const uint64_t *rowptr, const VertexId *col,
 void Graph::release() {
   if (reverse_vertices_ != vertices_) delete[] reverse_vertices_;
   if (reverse_edges_ != edges_) delete[] reverse_edges_;
+  if (map_bytes_[0]) { munmap(vertices_, map_bytes_[0]); vertices_ = nullptr; }
+  if (map_bytes_[1]) { munmap(edges_, map_bytes_[1]); edges_ = nullptr; }
+  map_bytes_[0] = map_bytes_[1] = 0;
   delete[] vertices_;
   delete[] edges_;
   vertices_ = reverse_vertices_ = nullptr;
@@ -333,10 +340,50 @@ int Graph::write_sg(const std::string &fname, int offset_bytes) const {
   return fclose(f) == 0 && ok ? 0 : -1;
 }
 
+static void *map_file(const std::string &fname, size_t bytes) {
+  const int fd = open(fname.c_str(), O_RDONLY);
+  if (fd < 0) return nullptr;
+  struct stat st;
+  void *p = MAP_FAILED;
+  if (fstat(fd, &st) == 0 && (size_t)st.st_size >= bytes && bytes > 0)
+    p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE, fd, 0);       // private: page-lockable, never written
+  close(fd);
+  return p == MAP_FAILED ? nullptr : p;
+}
+
+int Graph::load_bin_mapped(const std::string &prefix, bool verbose) {
+  std::ifstream meta((prefix + ".meta.txt").c_str());
+  if (!meta) return kLoadNoFile;
+  long long nv = 0, ne = 0, maxd = 0;
+  int vid_size = 0;
+  meta >> nv >> ne >> vid_size >> maxd;
+  if (!meta || vid_size != (int)sizeof(VertexId) || nv < 0 || ne <= 0) return kLoadBadHeader;
+  const size_t vb = sizeof(uint64_t) * ((size_t)nv + 1), eb = sizeof(VertexId) * (size_t)ne;
+  void *v = map_file(prefix + ".vertex.bin", vb), *e = map_file(prefix + ".edge.bin", eb);
+  if (!v || !e) {
+    if (v) munmap(v, vb);
+    if (e) munmap(e, eb);
+    return kLoadNoFile;
+  }
+  n_vertices_ = (VertexId)nv; n_edges_ = (uint64_t)ne; max_degree_ = (VertexId)maxd;
+  vertices_ = (uint64_t *)v; edges_ = (VertexId *)e;
+  map_bytes_[0] = vb; map_bytes_[1] = eb;
+  if (verbose) std::cout << "|V| " << n_vertices_ << " |E| " << n_edges_ << " (mapped)\n";
+  finish(true, false, verbose);
+  return kLoadOk;
+}
+
 int Graph::load(const std::string &prefix, const std::string &filetype, bool symmetrize,
                 bool need_reverse, bool verbose) {
   release();
   int rc;
+  if (filetype == "bin:mmap") {
+    if (!symmetrize) return kLoadBadType;                  // (the reverse graph of a directed one would have to be built)
+    rc = load_bin_mapped(prefix, verbose);
+    if (rc != kLoadOk) return rc;
+    if (max_degree_ == 0 || max_degree_ >= n_vertices_) return kLoadDegenerate;
+    return kLoadOk;
+  }
   if (filetype == "sg") {
     // the .sg of the GAP-style drivers (include/reader.h:259-316) keeps whatever graph it was built from: the
     // degenerate-graph check of the gen-2 constructor does not apply

@@ -55,6 +55,7 @@ class Graph {
   VertexId max_degree_ = 0;
   uint64_t *vertices_ = nullptr, *reverse_vertices_ = nullptr;
   VertexId *edges_ = nullptr, *reverse_edges_ = nullptr;
+  size_t map_bytes_[2] = {0, 0};          // > 0: vertices_ / edges_ are file mappings (load_bin_mapped), not new[] blocks
   void release();
   void finish(bool symmetrize, bool need_reverse, bool verbose);
 
@@ -73,6 +74,9 @@ class Graph {
            bool need_reverse, bool verbose);
   int load_mtx(const std::string &fname, bool symmetrize, bool need_reverse, bool verbose);
   int load_bin(const std::string &prefix, bool symmetrize, bool need_reverse, bool verbose);
+  // The binary triple mapped copy-on-write instead of read: N processes of one box share ONE copy of a cached graph
+  // in the page cache (filetype "bin:mmap"; symmetric graphs, nothing is ever written).
+  int load_bin_mapped(const std::string &prefix, bool verbose);
   // Serialized graph of the GAP-style reader (include/reader.h:259-316); 32- or 64-bit offsets, recognised by file size.
   int load_sg(const std::string &fname, bool need_reverse, bool verbose);
   int write_sg(const std::string &fname, int offset_bytes = 4) const;

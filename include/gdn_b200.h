@@ -212,6 +212,8 @@ int gdn_comm_size(void);   /* 1 when no communicator */
 
 /* ---- host graphs: readers and generator (no GPU needed) ----------------------- */
 /* filetype "mtx" | "bin": gen-2 loader (include/csr_graph.h:211-250);
+ * filetype "bin:mmap": the same binary triple mapped copy-on-write instead of read (symmetrize must be set): the
+ *   processes of one box share one copy of the graph in the page cache;
  * filetype "sg": serialized graph of the GAP-style reader (include/reader.h:259-316; prefix or full path; offsets of
  *   4 bytes as the reference writes them or 8 as upstream GAP does, recognised by the file size; symmetrize is ignored,
  *   the file is a finished CSR -- include/builder.h:264);

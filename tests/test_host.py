@@ -99,6 +99,12 @@ def test_bin_roundtrip(tmp_path):
     g2 = gb.Graph(str(tmp_path / "u10"), "bin", True, False)
     assert np.array_equal(g2.out_rowptr(), g.out_rowptr()) and np.array_equal(g2.out_colidx(), g.out_colidx())
     assert g2.symmetric and g2.has_reverse_graph()
+    g3 = gb.Graph(str(tmp_path / "u10"), "bin:mmap", True, False)        # mapped copy-on-write instead of read
+    assert np.array_equal(g3.out_rowptr(), g.out_rowptr()) and np.array_equal(g3.out_colidx(), g.out_colidx())
+    assert g3.symmetric and g3.has_reverse_graph() and np.array_equal(g3.pick_sources(4), g.pick_sources(4))
+    del g3
+    with pytest.raises(gb.GdnError):
+        gb.Graph(str(tmp_path / "u10"), "bin:mmap", False, True)
 
 
 @pytest.mark.parametrize("offset_bytes", [4, 8])

@@ -1,6 +1,6 @@
 #!/bin/bash
 # gpu_run.sh TAG STAGE... -- one gpurun call: runs the named stages, each under its own timeout, logs into gpurun_out/TAG_*.
-# stages: info | pytest[:expr] | multi:N | smoke | bench[:args] | benchN:N[:args] | ncu_list[:args] | ncu_full:KERNEL_REGEX[:args] | prof:ARGS | sweep:ARGS | script:PATH
+# stages: info | pytest[:expr] | multi:N | smoke | bench[:args] | benchN:N[:args] | ncu_list:NAME:ARGS | ncu_full:NAME:KERNEL_REGEX:ARGS | prof:ARGS | sweep:ARGS | script:PATH
 TAG=$1; shift
 O=gpurun_out; mkdir -p $O
 export PYTHONPATH=$PWD
@@ -15,9 +15,10 @@ for st in "$@"; do
     bench) timeout 1500 python bench.py $arg > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; echo "rc=$?"; tail -4 $O/${TAG}_bench.err; head -c 1500 $O/${TAG}_bench.json; echo ;;
     benchN) n=${arg%%:*}; rest=""; [[ "$arg" == *:* ]] && rest=${arg#*:}; sfx=$(echo "$rest" | tr -c "a-zA-Z0-9" "_" | cut -c1-24)
       timeout 1800 python -m torch.distributed.run --nnodes=1 --nproc-per-node=$n --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus $n $rest > $O/${TAG}_bench_n${n}_$sfx.json 2> $O/${TAG}_bench_n${n}_$sfx.err; echo "rc=$?"; grep -v "^W\|^\*\*\*" $O/${TAG}_bench_n${n}_$sfx.err | tail -6; head -c 1500 $O/${TAG}_bench_n${n}_$sfx.json; echo ;;
-    ncu_list) timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/${TAG}_launches.csv python tools/prof_run.py $arg > $O/${TAG}_ncu_list.log 2>&1; echo "rc=$?"; python tools/launch_list.py $O/${TAG}_launches.csv | tee $O/${TAG}_launches.txt | head -30 ;;
-    ncu_full) k=${arg%%:*}; rest=${arg#*:}
-      timeout 1500 ncu --set full --clock-control none --import-source on -k "regex:$k" -c 3 -o $O/${TAG}_full -f python tools/prof_run.py $rest > $O/${TAG}_ncu_full.log 2>&1; echo "rc=$?"; tail -3 $O/${TAG}_ncu_full.log ;;
+    ncu_list) nm=${arg%%:*}; rest=${arg#*:}
+      timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/${TAG}_launches_$nm.csv python tools/prof_run.py $rest > $O/${TAG}_ncu_list_$nm.log 2>&1; echo "rc=$?"; python tools/launch_list.py $O/${TAG}_launches_$nm.csv | tee $O/${TAG}_launches_$nm.txt | head -30 ;;
+    ncu_full) nm=${arg%%:*}; rest=${arg#*:}; k=${rest%%:*}; rest=${rest#*:}
+      timeout 1500 ncu --set full --clock-control none --import-source on -k "regex:$k" -c 4 -o $O/${TAG}_full_$nm -f python tools/prof_run.py $rest > $O/${TAG}_ncu_full_$nm.log 2>&1; echo "rc=$?"; tail -3 $O/${TAG}_ncu_full_$nm.log ;;
     prof) timeout 1500 python tools/prof_run.py $arg > $O/${TAG}_prof.json 2> $O/${TAG}_prof.err; echo "rc=$?"; tail -3 $O/${TAG}_prof.err; head -c 3000 $O/${TAG}_prof.json; echo ;;
     sweep) timeout 3000 python tools/sweep.py $arg > $O/${TAG}_sweep.jsonl 2> $O/${TAG}_sweep.err; echo "rc=$?"; tail -12 $O/${TAG}_sweep.err ;;
     script) timeout 1500 bash $arg > $O/${TAG}_script.log 2>&1; echo "rc=$?"; tail -30 $O/${TAG}_script.log ;;
