@@ -965,7 +965,7 @@ int band_launch(gdn_graph *g, const SellArgs &sa, double fix_scale, cudaStream_t
   const BandLayout &bd = g->pull.band;
   BandArgs a;
   a.bsell = bd.bsell; a.item_ptr = bd.item_ptr; a.job = bd.job; a.job_first = bd.job_first; a.wrun = bd.wrun;
-  a.pf_groups = env_int("GDN_PR_BAND_PF", 16);
+  a.pf_groups = env_int("GDN_PR_BAND_PF", 8);      // 8 index groups = 4 KB ahead (0.84 ms; 16: 0.87, 24: 0.98, none: 1.10)
   a.band_start = bd.band_start; a.band_len = bd.band_len; a.contrib_in = sa.contrib_in; a.done = sa.done;
   a.irow = bd.irow; a.acc_fix = (unsigned long long *)bd.acc_fix; a.fix_scale = fix_scale;
   if (bd.seg) {

@@ -52,8 +52,6 @@ struct GatherArgs {
   int64_t rows;
   // SpMV:  y[r] += sum Ax[j] * x[col[j]]
   const float *Ax;
-  const int32_t *col;     // (spmv_pipe: the column array, for its L2 prefetches)
-  int pf;                 // spmv_pipe: prefetch the next items' col / Ax into L2 (GDN_SPMV_PF, default on)
   uint64_t nnz;           // bound for guarded Ax tail loads
   const float *vec;       // x (SpMV) or contrib_in (PR), GLOBAL length m
   float *y;               // SpMV y (local rows)
@@ -243,15 +241,6 @@ struct SpGen {
   }
   __device__ __forceinline__ void loadA(int64_t it) {
     itA = it;
-    // light block `it` is (about) entries [512 it, 512 it + 512): two items before the warp streams them, ask L2 for
-    // that piece of col and Ax (2 KB each), so the stream loads of the trip pipeline wait for L2, not for HBM
-    if (a.pf && it < a.n_chunks && (threadIdx.x & 31) == 0) {
-      const uint64_t e0 = (uint64_t)it * kChunk;
-      if (e0 + kChunk <= a.nnz) {
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.col + e0), "r"(kChunk * 4) : "memory");
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.Ax + e0), "r"(kChunk * 4) : "memory");
-      }
-    }
     if (it < a.n_chunks) { xA0 = __ldcs(a.chunk_row + it); xA1 = __ldcs(a.chunk_row + it + 1); }
     else if (it < n_items) { const int2 hs = a.heavy_seg[it - a.n_chunks]; xA0 = hs.x; xA1 = hs.y; }
   }
@@ -709,8 +698,8 @@ static int spmv_t(gdn_graph *g, const float *d_Ax, const float *d_x, float *d_y,
   constexpr int kPipeThreads = 384, kPipeCtas = 2;
   const size_t smem = sizeof(float) * (size_t)kCap * (kPipeThreads / 32);
   GDN_CUDA(cudaFuncSetAttribute(spmv_pipe<OffT, kPipeThreads, kPipeCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  a.col = col;
-  { const char *e = getenv("GDN_SPMV_PF"); a.pf = e ? atoi(e) : 1; }
+  // (an L2 bulk prefetch of the next items' col / Ax, the trick that pays in pr_band_kernel, was measured 18 % SLOWER here:
+  // 2.82 -> 3.33 ms on urand-24 -- this kernel is bound by the sector rate of its gathers, not by stream latency)
   kev_begin();
   spmv_pipe<OffT, kPipeThreads, kPipeCtas><<<lib().sm_count * kPipeCtas, kPipeThreads, smem, s>>>(rp, col, a);
   kev_end();
