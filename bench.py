@@ -275,6 +275,11 @@ class Ctx:
         self.dev = torch.device("cuda", self.local_rank)
         _lib.check(_lib.lib.gdn_init(self.local_rank))
         if self.world > 1:
+            # communicator set-up prints "NCCL version ..." on STDOUT (seen in front of the one JSON line at N=8): while the
+            # communicators are made, file descriptor 1 points at stderr
+            sys.stdout.flush()
+            saved_fd = os.dup(1)
+            os.dup2(2, 1)
             dist.init_process_group("nccl", device_id=self.dev)
             uid = torch.zeros(128, dtype=torch.uint8)
             if self.rank == 0:
@@ -285,6 +290,11 @@ class Ctx:
             dist.broadcast(uid, 0)
             self._uid = np.ascontiguousarray(uid.cpu().numpy())       # keep alive across the C call
             _lib.check(_lib.lib.gdn_comm_init(self.rank, self.world, self._uid.ctypes.data))
+            dist.barrier()
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
             # a barrier that leaves the GPUs alone (an NCCL barrier is a kernel spinning on every waiting rank's GPU)
             self.cpu_group = dist.new_group(backend="gloo")
         self.ncpu = os.cpu_count() or 1
@@ -656,8 +666,13 @@ def bench_bfs(ctx, args, scale, steps, warmup, side=False):
     }
     if world == 1:
         achieved = alg / (tot_ms / 1e3) / 1e9
+        bfs_traffic = None       # ncu capture of ONE BFS of this graph (profiles/r2_ncu_bfs.txt), per launch like `achieved`
+        try:
+            bfs_traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"bfs_kron{scale}")
+        except Exception:
+            pass
         line["roofline"] = {"bound": "hbm", "kernel": "bfs_persist (whole BFS: top-down expand + bottom-up sweeps + controller)",
-                            "achieved": achieved, "peak": ctx.peak, "unit": "GB/s", "frac": achieved / ctx.peak, "traffic": None,
+                            "achieved": achieved, "peak": ctx.peak, "unit": "GB/s", "frac": achieved / ctx.peak, "traffic": bfs_traffic,
                             "peak_source": ctx.peak_src, "algorithmic_bytes_per_launch": alg / nb, "avg_launch_ms": tot_ms / nb,
                             "bu_sweep_share": kern_ms / tot_ms if tot_ms else None,
                             "note": "bytes of SURVEY 8(d) over the schedule actually run (hubs-first rows probe fewer in-edges than the oracle order)"}

@@ -34,7 +34,7 @@ constexpr int kSeg = 1024;             // non-zeros per heavy-row segment
 constexpr int kWarps = 8;              // warps per CTA
 // SpMV rows longer than this are summed in the reference's order (SpmvExact below); GDN_SPMV_EXACT_LEN overrides it when a
 // graph is created (0 = never)
-constexpr int64_t kSpmvExactLen = 32768;
+constexpr int64_t kSpmvExactLen = 8192;
 constexpr int kThreads = kWarps * 32;
 
 enum { kModeSpmv = 0, kModePr = 1 };

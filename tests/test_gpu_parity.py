@@ -709,7 +709,7 @@ def test_gpu_csr_build_edge_cases():
 
 @pytest.mark.parametrize("kind,scale,signed,hot", [("g", 16, False, "0"), ("g", 18, False, "1"), ("g", 16, True, "0"), ("u", 14, False, "0")])
 def test_spmv_long_rows_keep_the_reference_order(monkeypatch, kind, scale, signed, hot):
-    """SpMV rows longer than kSpmvExactLen (32768; lowered to the heavy-row limit here, so EVERY row that is not summed by
+    """SpMV rows longer than kSpmvExactLen (8192; lowered to the heavy-row limit here, so EVERY row that is not summed by
     one lane goes this way) are summed in the order of src/spmv/omp_base.cc:27-31 by the ordered sum of
     csrc/ordered_core.cuh: with the light rows bit-identical already, the whole of y equals the oracle's bit for bit --
     with y != 0 on entry, with negative values (blocks that hold one are added one by one), on the hot-first column path,

@@ -12,7 +12,7 @@ scale = int(sys.argv[1]) if len(sys.argv) > 1 else 26
 _, g = bench.load_graph("g", scale)
 for a in (g.out_rowptr(), g.out_colidx()):
     _lib.lib.gdn_host_pin(a.ctypes.data, a.nbytes)
-for rep in range(2):
+for rep in range(int(sys.argv[2]) if len(sys.argv) > 2 else 2):
     s = np.full(g.m, np.float32(1.0) / np.float32(g.m), dtype=np.float32)
     t = time.time()
     st = gb.PRSolver(g, s, verbose=False)
