@@ -150,7 +150,10 @@ int pr_oneshot(int64_t m, int64_t nnz, const OffT *irp, const int32_t *ici, cons
     delete J;
     return rc;
   }
+  struct TraceAt { const char *what; ~TraceAt() { trace(what); } };
+  TraceAt t_exit{"pr_oneshot: arena scope closed"};
   PoolScope arena;                 // declared before every buffer of the call: they are parked, not freed, on the way out
+  TraceAt t_freed{"pr_oneshot: buffers released"};
   const double t0 = now_ms();
   // the two small inputs go first (queued, not waited for); then the CSR, whose column array crosses PCIe in
   // pieces with the PageRank layout built behind them (Lib::stream_fill, graph.cu / pull.cu)

@@ -3,7 +3,7 @@
 // A one-shot PRSolver call at Kronecker scale 26 allocates ~18 GB in two dozen cudaMalloc calls and frees them at the
 // end; the cudaFree calls (each a device synchronisation + unmapping) cost 15 ms per call and 80 ms in two of five
 // (bench.py e2e, profiles/r1_bench_kron26_v5.json: 257 ms vs 325/340 ms per call with identical upload / solve /
-// download times).  While a one-shot call is running (PoolScope in oneshot.cu) blocks of >= 1 MB are tracked; freeing
+// download times).  While a one-shot call is running (PoolScope in oneshot.cu) all blocks are tracked; freeing
 // one parks it in the arena instead, and the next call's allocation of the SAME size on the SAME device takes it back.
 // Repeated calls on the same graph -- what a caller of the reference's solver loop does -- then allocate nothing.
 // What a caller sharing the device has to know (include/gdn_b200.h): memory parked by the last one-shot call stays
@@ -30,7 +30,8 @@ unsigned generation = 0;                                    // one-shot calls so
 std::unordered_map<void *, std::pair<size_t, int>> live;    // blocks handed out while the arena was on: size, device
 std::multimap<std::pair<int, size_t>, Block> idle;          // parked blocks by (device, size)
 size_t idle_bytes = 0;
-constexpr size_t kMinBlock = (size_t)1 << 20;
+constexpr size_t kMinBlock = 1;                             // every block: a REAL cudaFree of even a small one stalled 150-380 ms in
+                                                            // one call of three (GDN_TRACE, "buffers released"), so none is left
 
 bool enabled_by_env() {
   static const bool on = [] { const char *e = getenv("GDN_DEVICE_ARENA"); return !(e && atoi(e) == 0); }();

@@ -97,7 +97,7 @@ int gdn_init_gpus(int ngpus);
 int gdn_gpus(void);           /* GPUs the one-shot solvers use (1 unless gdn_init_gpus) */
 int gdn_finalize(void);
 int gdn_device_count(void);   /* 0 when no driver / device */
-/* One-shot calls park their device blocks (>= 1 MB) in a bounded arena instead of freeing them, so that the next
+/* One-shot calls park their device blocks in a bounded arena instead of freeing them, so that the next
  * call on the same graph allocates nothing (csrc/pool.cu).  A process that shares the device with another allocator
  * calls this to hand the parked memory back; GDN_DEVICE_ARENA=0 in the environment turns the arena off. */
 int gdn_device_trim(void);
